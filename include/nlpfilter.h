@@ -1,0 +1,179 @@
+/* nlpfilter.h -- C ABI of libnlpfilter.so: the B200 (sm_100a) replacement for the numerical
+ * back end of kingdwd/nlp-filter's estimator hot path.
+ *
+ * The reference has no FFI of its own: its hot path runs inside CasADi/IPOPT/MUMPS (NLP) and
+ * NumPy/LAPACK (EKF, least squares), reached from plain Python.  Each entry point below names
+ * the reference interface whose arithmetic it takes over (paths relative to the reference
+ * repository).  Conventions:
+ *   - every function returns 0 on success and a negative NLPF_E_* code on failure; it never
+ *     throws and never aborts.  nlpf_last_error() gives a thread-local message.
+ *   - `stream` is a cudaStream_t passed as void* (NULL = default stream); calls only enqueue
+ *     work, they do not synchronise.
+ *   - all batch buffers are DEVICE pointers to contiguous fp64 / int32 arrays owned by the
+ *     caller; descriptor arrays in nlpf_desc are HOST pointers, copied at create time.
+ *   - the unknown vector of one window is z = [V_0 .. V_{K-1}, globals], V_k in R^nv,
+ *     nz = K*nv + ng (see nlp_filter_b200/desc.py).
+ */
+#ifndef NLPFILTER_H
+#define NLPFILTER_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NLPF_VERSION 100
+
+/* error codes */
+#define NLPF_OK 0
+#define NLPF_E_ARG (-1)      /* bad argument / unsupported size */
+#define NLPF_E_CUDA (-2)     /* CUDA runtime error (message in nlpf_last_error) */
+#define NLPF_E_NOGPU (-3)    /* no CUDA device: there is no CPU fallback */
+
+/* dynamics models, nlp/dynamics.py */
+#define NLPF_DYN_AFFINE 0        /* f = A x + B u + c0: dynamics.py:4-38,68-115 */
+#define NLPF_DYN_VDP 1           /* dynamics.py:61-66 */
+#define NLPF_DYN_BICYCLE 2       /* dynamics.py:117-136 */
+#define NLPF_DYN_VEHICLE 3       /* dynamics.py:148-164 */
+#define NLPF_DYN_VEHICLE_GNSS 4  /* dynamics.py:166-174 */
+#define NLPF_DYN_QUADCOPTER 5    /* dynamics.py:40-59 */
+
+/* residual (measurement) types, nlp/measurements.py; per-window record = [y, weight, aux..] */
+#define NLPF_RT_STATE 0       /* full_state component             measurements.py:4       rec 2 */
+#define NLPF_RT_PR 1          /* pseudorange                      measurements.py:56-70   rec 5: +sat_pos[3] */
+#define NLPF_RT_PRR 2         /* pseudorange_rate                 measurements.py:72-79   rec 8: +sat_pos[3], sat_vel[3] */
+#define NLPF_RT_RANGE 3       /* range between two index sets     measurements.py:13-19   rec 2 */
+#define NLPF_RT_RANGE_PT 4    /* range to a point / global var    measurements.py:8-12    rec 5: +point[3] */
+#define NLPF_RT_HEADING 5     /* heading between two index sets   measurements.py:30-36   rec 2 */
+#define NLPF_RT_HEADING_PT 6  /* heading to a point / global var  measurements.py:25-29   rec 5 */
+
+#define NLPF_LOSS_L2 0        /* weighted_l2_norm,  cost_functions.py:20-22 */
+#define NLPF_LOSS_HUBER 1     /* pseudo_huber_loss, cost_functions.py:25-31 */
+
+#define NLPF_NIDX 8
+#define NLPF_NDYNPAR 16
+
+/* solve status per window */
+#define NLPF_ST_CONVERGED 0
+#define NLPF_ST_STALLED 1     /* no damping produced a decrease: stationary to rounding */
+#define NLPF_ST_MAXITER 2
+#define NLPF_ST_NUMERIC 3     /* non-finite objective at the starting point */
+
+/* Problem class = everything the reference fixes when a script has finished calling
+ * addVariables/addDynamics/addDynamicsCost/addResidualCost/addInitialCost/addVarBounds/
+ * addEqConstraint and build() (nlp/nlp.py:18-69,135-186,202-317).  Host pointers. */
+typedef struct nlpf_desc {
+    int K, n, m, nv, ng;          /* nodes N+1, states, controls, node variables, globals */
+    int dyn_id, loss, has_prior;
+    int nb, E, M, Ldata;          /* bounded components, epochs, residuals, doubles per window record block */
+    double T, delta;
+    const double* dyn_par;        /* [NLPF_NDYNPAR] model constants (car: C_AF C_AR M D_F D_R I_Z) */
+    const double* A;              /* [n*n]   affine model */
+    const double* Bm;             /* [n*max(m,1)] */
+    const double* c0;             /* [n] */
+    const int* cmap;              /* [n]  state component -> node-variable column */
+    const int* ucol;              /* [max(m,1)] control -> node-variable column, or -1: per-window parameter */
+    const double* Dt;             /* [K*K] (2/T) D, nlp/collocation.py:42-64 */
+    const double* cw;             /* [K]  weight of defect row k ((T/2) w_k), nlp.py:244-245 */
+    const double* cq;             /* [K]  quadrature weight of the node (stage) cost, nlp.py:167-168 */
+    const double* qinv;           /* [n]  diagonal of Q^-1 */
+    const double* pinv;           /* [n]  diagonal of P^-1 (arrival cost, nlp.py:279-286) */
+    const double* snode;          /* [nv] diagonal node cost */
+    const int* bidx;              /* [nb] bounded node-variable columns (nlp.py:314-317) */
+    const double* blo;            /* [nb] may be -inf */
+    const double* bhi;            /* [nb] may be +inf */
+    const double* Phi;            /* [E*K] Lagrange basis rows at the measurement epochs, nlp.py:264-269 */
+    const int* rtype;             /* [M] */
+    const int* repoch;            /* [M] row of Phi */
+    const int* ridx;              /* [M*NLPF_NIDX] state / global indices, meaning per type */
+    const int* roff;              /* [M] offset of the residual's record in the window's data block */
+} nlpf_desc;
+
+typedef struct nlpf_opts {
+    int max_iter;                 /* total accepted steps per window */
+    int max_stage_iter;           /* accepted steps per barrier stage */
+    double tol_step;              /* stop when |step|_inf < tol_step (1 + |z|_inf) */
+    double lam0;                  /* initial damping */
+    double mu0, mu_min;           /* barrier schedule (only with bounds) */
+    double bound_push;            /* initial distance from a bound */
+    double tau_ftb;               /* fraction to the boundary */
+} nlpf_opts;
+
+typedef struct nlpf_problem nlpf_problem;   /* opaque */
+
+int nlpf_version(void);
+const char* nlpf_last_error(void);
+int nlpf_device_count(void);
+
+/* replaces: problem construction up to NLP.build(), nlp/nlp.py:61-69 */
+int nlpf_problem_create(const nlpf_desc* desc, nlpf_problem** out);
+int nlpf_problem_destroy(nlpf_problem* p);
+/* packed size of the lower triangle incl. the appended right-hand-side row, doubles */
+int nlpf_problem_nz(const nlpf_problem* p);
+
+/* Kernels (1)+(2): residuals, analytic Jacobians, J^T W J and J^T W r of B windows at z.
+ * replaces: the CasADi AD evaluation IPOPT requests each iteration for the graph built by
+ * nlp/nlp.py:225-235 (defects), :242-245, :264-273, :279-286.
+ *   z[B*nz] U[B*K*m] data[B*Ldata] xprior[B*n] wshift[B*K*n] (wshift, U, xprior may be NULL)
+ *   H_out[B*nz*nz] full symmetric row-major, g_out[B*nz], cost_out[B*2] = {J, merit} */
+int nlpf_assemble(nlpf_problem* p, int B, const double* z, const double* U, const double* data,
+                  const double* xprior, const double* wshift, double mu,
+                  double* H_out, double* g_out, double* cost_out, void* stream);
+
+/* Kernel (3): dz = -(H + lam (diag H + eps))^-1 g by an in-shared-memory LDL^T.
+ * replaces: the MUMPS factorisation inside IPOPT (reached through nlp/nlp.py:82).
+ *   H[B*nz*nz] (lower triangle read), g[B*nz]; dz_out[B*nz]; info_out[B] 0 ok / 1 not SPD */
+int nlpf_factor_solve(nlpf_problem* p, int B, const double* H, const double* g, double lam,
+                      double* dz_out, int* info_out, void* stream);
+
+/* Whole solve of B independent windows, one CTA per window, iterating on chip.
+ * replaces: NLP.solve(), nlp/nlp.py:76-83 (opti.solve() -> CasADi -> IPOPT -> MUMPS).
+ *   z_inout[B*nz] initial guess in, minimiser out;
+ *   cost_out[B] objective J; iters_out[B]; status_out[B] NLPF_ST_* */
+int nlpf_solve(nlpf_problem* p, int B, double* z_inout, const double* U, const double* data,
+               const double* xprior, const double* wshift, const nlpf_opts* opts,
+               double* cost_out, int* iters_out, int* status_out, void* stream);
+
+/* x(t) = sum_j phi_j(t) X_j for B windows at nt times.
+ * replaces: NLP.extractSolution, nlp/nlp.py:99-119 (collocation.py:113-121).
+ *   PhiT[nt*K] device; out[B*nt*n] */
+int nlpf_sample(nlpf_problem* p, int B, const double* z, int nt, const double* PhiT,
+                double* out, void* stream);
+
+/* EKF models (utils/gnss.py, autonomous-car.py:18-79) */
+#define NLPF_EKF_GNSS5 0      /* gnss.gnss_pos_and_bias + gnss.multi_pseudorange, n = 5 */
+#define NLPF_EKF_CAR9 1       /* discrete_vehicle_dynamics + vehicle_sensors_model, n = 9 */
+
+/* Kernel (4): `steps` fused predict/update steps of B independent filters.
+ * replaces: EKF.update/predict/correct, utils/ekf.py:20-61, with the model functions above.
+ *   mu_inout[B*n], S_inout[B*n*n];
+ *   u[B*steps*m]   (m = 3 for GNSS5, 2 for CAR9)
+ *   z[B*steps*smax], sat[B*steps*smax*3], nsat[B*steps] (0 = no measurement: predict only,
+ *   ekf.py:32-38); Q[n] diagonal, r scalar pseudorange variance; dt; par[NLPF_NDYNPAR];
+ *   mu_traj_out[B*steps*n] state after each step (may be NULL) */
+int nlpf_ekf_run(int model, int B, int steps, int smax, double* mu_inout, double* S_inout,
+                 const double* u, const double* z, const double* sat, const int* nsat,
+                 const double* Q, double r, double dt, const double* par,
+                 double* mu_traj_out, void* stream);
+
+/* Iterative GNSS least squares of B independent epochs (one solve per epoch).
+ * replaces: iterativeLeastSquares, utils/leastsquares.py:19-42 (and, with tcol != NULL,
+ * iterativeLeastSquares_multiTimeStep, :66-94, unknowns x,y,z,b0,alpha).
+ *   sat[B*smax*3], pr[B*smax], nsat[B]; tcol[B*smax] or NULL; x_inout[B*nu] (nu = 4 or 5)
+ *   warm start in, solution out; iters_out[B] */
+int nlpf_ls_solve(int B, int smax, const double* sat, const double* pr, const int* nsat,
+                  const double* tcol, double* x_inout, int maxiter, double tol,
+                  int* iters_out, void* stream);
+
+/* One-shot velocity solve, utils/leastsquares.py:45-63.
+ *   sat[B*smax*3], satvel[B*smax*3], prr[B*smax], nsat[B], x[B*3] position; out[B*4] = v, bdot */
+int nlpf_ls_vel(int B, int smax, const double* sat, const double* satvel, const double* prr,
+                const int* nsat, const double* x, double* out, void* stream);
+
+/* FP64 FMA throughput probe used for the roofline denominator (bench.py): runs `iters`
+ * dependent-chain-free DFMA per thread on a full grid, returns FLOP count in *flops_out. */
+int nlpf_fp64_probe(int iters, double* sink_dev, double* flops_out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NLPFILTER_H */
