@@ -1,0 +1,365 @@
+// capi.cu -- extern "C" entry points of libnlpfilter.so (declared in include/nlpfilter.h):
+// argument checking, derivation of the device tables of a problem class, kernel launches.
+// No torch types cross this boundary; buffers are raw device pointers.
+#include "common.cuh"
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <vector>
+
+static thread_local char g_err[512] = "";
+
+void nlpf_set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+int nlpf_check_cuda(cudaError_t e, const char* what) {
+    if (e == cudaSuccess) return NLPF_OK;
+    nlpf_set_error("%s: %s", what, cudaGetErrorString(e));
+    return NLPF_E_CUDA;
+}
+
+extern "C" int nlpf_launch_assemble(nlpf_problem*, int, const double*, const double*, const double*, const double*,
+                                    const double*, double, double*, double*, double*, cudaStream_t);
+extern "C" int nlpf_launch_factor_solve(nlpf_problem*, int, const double*, const double*, double, double*, int*,
+                                        cudaStream_t);
+extern "C" int nlpf_launch_solve(nlpf_problem*, int, double*, const double*, const double*, const double*,
+                                 const double*, const nlpf_opts*, double*, int*, int*, cudaStream_t);
+extern "C" int nlpf_launch_sample(nlpf_problem*, int, const double*, int, const double*, double*, cudaStream_t);
+extern "C" int nlpf_set_smem_attrs(size_t bytes);
+
+extern "C" int nlpf_version(void) { return NLPF_VERSION; }
+extern "C" const char* nlpf_last_error(void) { return g_err; }
+
+extern "C" int nlpf_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+// ------------------------------------------------------------------------------------------
+// blob builder: every table of a problem class goes into one device allocation
+// ------------------------------------------------------------------------------------------
+namespace {
+struct Blob {
+    std::vector<unsigned char> host;
+    size_t add(const void* src, size_t bytes) {
+        size_t off = (host.size() + 15) & ~size_t(15);
+        host.resize(off + bytes);
+        if (bytes) memcpy(host.data() + off, src, bytes);
+        return off;
+    }
+    template <typename T>
+    size_t addv(const std::vector<T>& v) { return add(v.data(), v.size() * sizeof(T)); }
+};
+
+// which index slots of a residual are state components / global indices
+void slot_roles(int rt, const int* idx, int* is_state, int* is_glob) {
+    for (int s = 0; s < NLPF_NIDX; ++s) is_state[s] = is_glob[s] = 0;
+    switch (rt) {
+        case NLPF_RT_STATE: is_state[0] = 1; break;
+        case NLPF_RT_PR: for (int s = 0; s < 4; ++s) is_state[s] = 1; break;
+        case NLPF_RT_PRR: for (int s = 0; s < 7; ++s) is_state[s] = 1; break;
+        case NLPF_RT_RANGE: for (int c = 0; c < idx[6]; ++c) is_state[c] = is_state[3 + c] = 1; break;
+        case NLPF_RT_RANGE_PT:
+            for (int c = 0; c < idx[6]; ++c) { is_state[c] = 1; if (idx[3 + c] >= 0) is_glob[3 + c] = 1; }
+            break;
+        case NLPF_RT_HEADING: is_state[0] = is_state[1] = is_state[3] = is_state[4] = 1; break;
+        case NLPF_RT_HEADING_PT:
+            is_state[0] = is_state[1] = 1;
+            if (idx[3] >= 0) is_glob[3] = 1;
+            if (idx[4] >= 0) is_glob[4] = 1;
+            break;
+    }
+}
+int reclen(int rt) {
+    switch (rt) {
+        case NLPF_RT_STATE: case NLPF_RT_RANGE: case NLPF_RT_HEADING: return 2;
+        case NLPF_RT_PR: case NLPF_RT_RANGE_PT: case NLPF_RT_HEADING_PT: return 5;
+        case NLPF_RT_PRR: return 8;
+    }
+    return -1;
+}
+}  // namespace
+
+extern "C" int nlpf_problem_create(const nlpf_desc* D, nlpf_problem** out) {
+    if (!D || !out) { nlpf_set_error("null argument"); return NLPF_E_ARG; }
+    *out = nullptr;
+    if (nlpf_device_count() < 1) {
+        nlpf_set_error("no CUDA device visible: libnlpfilter has no CPU fallback");
+        return NLPF_E_NOGPU;
+    }
+    const int K = D->K, n = D->n, m = D->m, nv = D->nv, ng = D->ng;
+    const int mm = m > 0 ? m : 1;
+    const int nz = K * nv + ng;
+    if (K < 2 || K > NLPF_K_MAX || n < 1 || n > NLPF_N_MAX || m < 0 || m > NLPF_M_MAX || nv < 1 || nv > NLPF_NV_MAX ||
+        ng < 0 || ng > NLPF_NG_MAX || nz > NLPF_NZ_MAX || D->E < 0 || D->M < 0 || D->nb < 0) {
+        nlpf_set_error("unsupported problem size K=%d n=%d m=%d nv=%d ng=%d nz=%d (limits K<=%d n<=%d m<=%d nv<=%d ng<=%d nz<=%d)",
+                       K, n, m, nv, ng, nz, NLPF_K_MAX, NLPF_N_MAX, NLPF_M_MAX, NLPF_NV_MAX, NLPF_NG_MAX, NLPF_NZ_MAX);
+        return NLPF_E_ARG;
+    }
+    if (D->dyn_id < 0 || D->dyn_id > NLPF_DYN_QUADCOPTER) { nlpf_set_error("unknown dynamics id %d", D->dyn_id); return NLPF_E_ARG; }
+    static const int dyn_n[] = {0, 2, 6, 6, 9, 12};
+    static const int dyn_m[] = {0, 1, 2, 2, 2, 4};
+    if (D->dyn_id != NLPF_DYN_AFFINE && (n != dyn_n[D->dyn_id] || m != dyn_m[D->dyn_id])) {
+        nlpf_set_error("dynamics id %d needs n=%d m=%d, got n=%d m=%d", D->dyn_id, dyn_n[D->dyn_id], dyn_m[D->dyn_id], n, m);
+        return NLPF_E_ARG;
+    }
+    for (int i = 0; i < n; ++i)
+        if (D->cmap[i] < 0 || D->cmap[i] >= nv) { nlpf_set_error("cmap[%d]=%d out of range", i, D->cmap[i]); return NLPF_E_ARG; }
+    for (int i = 0; i < m; ++i) {
+        if (D->ucol[i] >= nv) { nlpf_set_error("ucol[%d]=%d out of range", i, D->ucol[i]); return NLPF_E_ARG; }
+        if (D->ucol[i] >= 0 && D->dyn_id != NLPF_DYN_AFFINE && D->dyn_id != NLPF_DYN_VDP) {
+            nlpf_set_error("unknown controls are only supported for the affine and van der Pol models");
+            return NLPF_E_ARG;
+        }
+    }
+    for (int b = 0; b < D->nb; ++b) {
+        if (D->bidx[b] < 0 || D->bidx[b] >= nv) { nlpf_set_error("bidx[%d] out of range", b); return NLPF_E_ARG; }
+        for (int b2 = 0; b2 < b; ++b2)
+            if (D->bidx[b2] == D->bidx[b]) { nlpf_set_error("duplicate bounded component %d", D->bidx[b]); return NLPF_E_ARG; }
+    }
+
+    nlpf_problem* p = new nlpf_problem();
+    memset(&p->d, 0, sizeof(DevProb));
+    DevProb& P = p->d;
+    P.K = K; P.n = n; P.m = m; P.nv = nv; P.ng = ng; P.nz = nz; P.np = nz * (nz + 1) / 2;
+    P.dyn_id = D->dyn_id; P.loss = D->loss; P.has_prior = D->has_prior ? 1 : 0;
+    P.nb = D->nb; P.E = D->E; P.M = D->M; P.Ldata = D->Ldata;
+    P.delta = D->delta;
+    P.npair = K * (K + 1) / 2;
+    memcpy(P.dyn_par, D->dyn_par, sizeof(double) * NLPF_NDYNPAR);
+    P.has_dyncost = 0;
+    for (int i = 0; i < n; ++i) if (D->qinv[i] != 0.0) P.has_dyncost = 1;
+    P.has_nodecost = 0;
+    for (int a = 0; a < nv; ++a) if (D->snode[a] != 0.0) P.has_nodecost = 1;
+    P.fconst = (D->dyn_id == NLPF_DYN_AFFINE) ? 1 : 0;
+    P.hconst = (P.fconst && D->loss == NLPF_LOSS_L2) ? 1 : 0;
+    if (!P.has_dyncost) P.hconst = 1;
+
+    // ---- residual table: validate, sort by epoch, derive the active component set ----
+    const int M = D->M, E = D->E;
+    std::vector<int> order(M);
+    for (int i = 0; i < M; ++i) order[i] = i;
+    for (int i = 0; i < M; ++i) {
+        const int rt = D->rtype[i];
+        if (reclen(rt) < 0) { nlpf_set_error("unknown residual type %d", rt); delete p; return NLPF_E_ARG; }
+        if (D->repoch[i] < 0 || D->repoch[i] >= E) { nlpf_set_error("residual %d: epoch out of range", i); delete p; return NLPF_E_ARG; }
+        if (D->roff[i] < 0 || D->roff[i] + reclen(rt) > D->Ldata) { nlpf_set_error("residual %d: record outside the data block", i); delete p; return NLPF_E_ARG; }
+        if ((rt == NLPF_RT_RANGE || rt == NLPF_RT_RANGE_PT) && (D->ridx[i * NLPF_NIDX + 6] < 1 || D->ridx[i * NLPF_NIDX + 6] > 3)) {
+            nlpf_set_error("residual %d: range dimension must be 1..3", i); delete p; return NLPF_E_ARG;
+        }
+    }
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return D->repoch[a] < D->repoch[b]; });
+    std::vector<int> colact(nv, 0);
+    for (int i = 0; i < M; ++i) {
+        int is_state[NLPF_NIDX], is_glob[NLPF_NIDX];
+        const int* idx = D->ridx + i * NLPF_NIDX;
+        slot_roles(D->rtype[i], idx, is_state, is_glob);
+        for (int s = 0; s < NLPF_NIDX; ++s) {
+            if (is_state[s]) {
+                if (idx[s] < 0 || idx[s] >= n) { nlpf_set_error("residual %d: state index %d out of range", i, idx[s]); delete p; return NLPF_E_ARG; }
+                colact[D->cmap[idx[s]]] = 1;
+            }
+            if (is_glob[s] && idx[s] >= ng) { nlpf_set_error("residual %d: global index out of range", i); delete p; return NLPF_E_ARG; }
+        }
+    }
+    std::vector<int> act, actinv(nv, -1);
+    for (int a = 0; a < nv; ++a) if (colact[a]) { actinv[a] = (int)act.size(); act.push_back(a); }
+    const int na = (int)act.size();
+    if (na > NLPF_NA_MAX) { nlpf_set_error("measurements touch %d node components (limit %d)", na, NLPF_NA_MAX); delete p; return NLPF_E_ARG; }
+    P.na = na; P.nat = na + ng;
+    std::vector<int> rtype_s(M), rloc_s((size_t)M * NLPF_NIDX, -1), roff_s(M), estart(E + 1, 0);
+    for (int r = 0; r < M; ++r) {
+        const int i = order[r];
+        rtype_s[r] = D->rtype[i];
+        roff_s[r] = D->roff[i];
+        estart[D->repoch[i] + 1]++;
+        int is_state[NLPF_NIDX], is_glob[NLPF_NIDX];
+        const int* idx = D->ridx + i * NLPF_NIDX;
+        slot_roles(D->rtype[i], idx, is_state, is_glob);
+        for (int s = 0; s < NLPF_NIDX; ++s) {
+            int v = idx[s];
+            if (is_state[s]) v = actinv[D->cmap[idx[s]]];
+            else if (is_glob[s]) v = na + idx[s];
+            else if (s >= 3 && s <= 5 && (D->rtype[i] == NLPF_RT_RANGE_PT || D->rtype[i] == NLPF_RT_HEADING_PT)) v = -1;
+            rloc_s[(size_t)r * NLPF_NIDX + s] = v;
+        }
+    }
+    for (int e = 0; e < E; ++e) estart[e + 1] += estart[e];
+    // epochs per chunk: keep the per-chunk scratch (Ve, G, q) near 8 KB
+    {
+        const int per = P.nat * P.nat + P.nat + (na > 0 ? na : 1);
+        int ec = 1024 / (per > 0 ? per : 1);
+        if (ec < 1) ec = 1;
+        if (ec > NLPF_NT) ec = NLPF_NT;
+        if (ec > E) ec = E > 0 ? E : 1;
+        P.ec = ec;
+    }
+
+    // ---- constant part of H ----
+    std::vector<double> Hc((size_t)P.np, 0.0);
+    auto HC = [&](int r, int c) -> double& { return r >= c ? Hc[(size_t)r * (r + 1) / 2 + c] : Hc[(size_t)c * (c + 1) / 2 + r]; };
+    std::vector<double> Fc((size_t)n * nv, 0.0);
+    if (P.fconst) {
+        for (int i = 0; i < n; ++i) {
+            for (int j = 0; j < n; ++j) Fc[(size_t)i * nv + D->cmap[j]] += D->A[i * n + j];
+            for (int j = 0; j < m; ++j) if (D->ucol[j] >= 0) Fc[(size_t)i * nv + D->ucol[j]] += D->Bm[i * mm + j];
+        }
+    }
+    if (P.has_dyncost && D->loss == NLPF_LOSS_L2) {
+        // rows of the defect Jacobian with the state-dependent block left out (or constant for affine models)
+        const int R = K * n, C = K * nv;
+        std::vector<double> Aj((size_t)R * C, 0.0);
+        for (int k = 0; k < K; ++k)
+            for (int i = 0; i < n; ++i) {
+                double* row = &Aj[(size_t)(k * n + i) * C];
+                for (int j = 0; j < K; ++j) row[j * nv + D->cmap[i]] += D->Dt[k * K + j];
+                if (P.fconst) for (int a = 0; a < nv; ++a) row[k * nv + a] -= Fc[(size_t)i * nv + a];
+            }
+        for (int r = 0; r < C; ++r)
+            for (int c = 0; c <= r; ++c) {
+                double s = 0.0;
+                for (int k = 0; k < K; ++k)
+                    for (int i = 0; i < n; ++i) {
+                        const double* row = &Aj[(size_t)(k * n + i) * C];
+                        s += D->cw[k] * D->qinv[i] * row[r] * row[c];
+                    }
+                HC(r, c) += s;
+            }
+    }
+    if (P.has_prior) for (int i = 0; i < n; ++i) HC(D->cmap[i], D->cmap[i]) += D->pinv[i];
+    if (P.has_nodecost)
+        for (int k = 0; k < K; ++k) for (int a = 0; a < nv; ++a) HC(k * nv + a, k * nv + a) += D->cq[k] * D->snode[a];
+
+    // ---- index tables ----
+    std::vector<uint32_t> tab((size_t)P.np);
+    for (int r = 0; r < nz; ++r)
+        for (int c = 0; c <= r; ++c) {
+            uint32_t j, a, l, b;
+            if (r < K * nv) { j = r / nv; a = r % nv; } else { j = 255; a = r - K * nv; }
+            if (c < K * nv) { l = c / nv; b = c % nv; } else { l = 255; b = c - K * nv; }
+            tab[(size_t)r * (r + 1) / 2 + c] = j | (a << 8) | (l << 16) | (b << 24);
+        }
+    std::vector<uint16_t> ptab((size_t)P.npair);
+    {
+        int q = 0;
+        for (int j = 0; j < K; ++j) for (int l = 0; l <= j; ++l) ptab[q++] = (uint16_t)(j | (l << 8));
+    }
+
+    // ---- blob ----
+    Blob B;
+    std::vector<double> zero1(1, 0.0);
+    const size_t oA = B.add(D->A, sizeof(double) * n * n), oB = B.add(D->Bm, sizeof(double) * n * mm),
+                 oc0 = B.add(D->c0, sizeof(double) * n), ocm = B.add(D->cmap, sizeof(int) * n),
+                 ouc = B.add(D->ucol, sizeof(int) * mm), oDt = B.add(D->Dt, sizeof(double) * K * K),
+                 ocw = B.add(D->cw, sizeof(double) * K), ocq = B.add(D->cq, sizeof(double) * K),
+                 oqi = B.add(D->qinv, sizeof(double) * n), opi = B.add(D->pinv, sizeof(double) * n),
+                 osn = B.add(D->snode, sizeof(double) * nv), obi = B.add(D->bidx, sizeof(int) * D->nb),
+                 obl = B.add(D->blo, sizeof(double) * D->nb), obh = B.add(D->bhi, sizeof(double) * D->nb),
+                 oPh = B.add(D->Phi, sizeof(double) * E * K), ort = B.addv(rtype_s), orl = B.addv(rloc_s),
+                 oro = B.addv(roff_s), oes = B.addv(estart), oac = B.addv(act), oHc = B.addv(Hc), oFc = B.addv(Fc),
+                 otb = B.addv(tab), opt = B.addv(ptab);
+    B.add(zero1.data(), 16);
+    p->blob_bytes = B.host.size();
+    cudaGetDevice(&p->device);
+    if (nlpf_check_cuda(cudaMalloc(&p->blob, p->blob_bytes), "cudaMalloc(problem tables)") != NLPF_OK) { delete p; return NLPF_E_CUDA; }
+    if (nlpf_check_cuda(cudaMemcpy(p->blob, B.host.data(), p->blob_bytes, cudaMemcpyHostToDevice), "upload problem tables") != NLPF_OK) {
+        cudaFree(p->blob); delete p; return NLPF_E_CUDA;
+    }
+    const unsigned char* base = (const unsigned char*)p->blob;
+    P.A = (const double*)(base + oA); P.Bm = (const double*)(base + oB); P.c0 = (const double*)(base + oc0);
+    P.cmap = (const int*)(base + ocm); P.ucol = (const int*)(base + ouc); P.Dt = (const double*)(base + oDt);
+    P.cw = (const double*)(base + ocw); P.cq = (const double*)(base + ocq); P.qinv = (const double*)(base + oqi);
+    P.pinv = (const double*)(base + opi); P.snode = (const double*)(base + osn); P.bidx = (const int*)(base + obi);
+    P.blo = (const double*)(base + obl); P.bhi = (const double*)(base + obh); P.Phi = (const double*)(base + oPh);
+    P.rtype = (const int*)(base + ort); P.rloc = (const int*)(base + orl); P.roff = (const int*)(base + oro);
+    P.estart = (const int*)(base + oes); P.act = (const int*)(base + oac); P.Hc = (const double*)(base + oHc);
+    P.Fc = (const double*)(base + oFc); P.tab = (const uint32_t*)(base + otb); P.ptab = (const uint16_t*)(base + opt);
+
+    // ---- shared-memory layout (doubles) ----
+    int o = 0;
+    auto take = [&](int cnt) { int r = o; o += (cnt + 1) & ~1; return r; };
+    P.o_H = take((nz + 1) * (nz + 2) / 2);
+    P.o_z = take(nz); P.o_zt = take(nz); P.o_g = take(nz); P.o_ds = take(nz); P.o_dz = take(nz);
+    P.o_f = take(K * n); P.o_lw = take(K * n); P.o_wh = take(K * n); P.o_slw = take(K * nv); P.o_whs = take(K * nv);
+    const bool needF = !P.hconst;
+    P.o_F = take(needF ? K * n * nv : 0);
+    P.o_GF = take(needF ? K * nv * nv : 0);
+    P.o_FF = take(needF ? K * nv * nv : 0);
+    P.o_Ve = take(P.ec * (na > 0 ? na : 1));
+    P.o_G = take(P.ec * P.nat * P.nat);
+    P.o_q = take(P.ec * P.nat);
+    P.o_Phi = take(E * K);
+    P.o_Dt = take(K * K);
+    P.o_red = take(8);
+    P.smem_doubles = o;
+    p->smem_bytes = (size_t)o * sizeof(double);
+    if (p->smem_bytes > 227 * 1024) {
+        nlpf_set_error("problem needs %zu bytes of shared memory per window (limit 232448)", p->smem_bytes);
+        cudaFree(p->blob); delete p; return NLPF_E_ARG;
+    }
+    if (nlpf_set_smem_attrs(227 * 1024) != NLPF_OK) { cudaFree(p->blob); delete p; return NLPF_E_CUDA; }
+    *out = p;
+    return NLPF_OK;
+}
+
+extern "C" int nlpf_problem_destroy(nlpf_problem* p) {
+    if (!p) return NLPF_OK;
+    cudaFree(p->blob);
+    delete p;
+    return NLPF_OK;
+}
+
+extern "C" int nlpf_problem_nz(const nlpf_problem* p) { return p ? p->d.nz : NLPF_E_ARG; }
+extern "C" int nlpf_problem_smem_bytes(const nlpf_problem* p) { return p ? (int)p->smem_bytes : NLPF_E_ARG; }
+
+static int check_batch(nlpf_problem* p, int B, const void* z, const void* data) {
+    if (!p) { nlpf_set_error("null problem handle"); return NLPF_E_ARG; }
+    if (B < 1) { nlpf_set_error("batch size must be >= 1"); return NLPF_E_ARG; }
+    if (!z) { nlpf_set_error("null iterate buffer"); return NLPF_E_ARG; }
+    if (p->d.M > 0 && !data) { nlpf_set_error("problem has %d residuals but the data buffer is null", p->d.M); return NLPF_E_ARG; }
+    return NLPF_OK;
+}
+
+extern "C" int nlpf_assemble(nlpf_problem* p, int B, const double* z, const double* U, const double* data,
+                             const double* xprior, const double* wshift, double mu, double* H_out, double* g_out,
+                             double* cost_out, void* stream) {
+    int rc = check_batch(p, B, z, data);
+    if (rc) return rc;
+    if (!H_out || !g_out || !cost_out) { nlpf_set_error("null output buffer"); return NLPF_E_ARG; }
+    return nlpf_launch_assemble(p, B, z, U, data, xprior, wshift, mu, H_out, g_out, cost_out, (cudaStream_t)stream);
+}
+
+extern "C" int nlpf_factor_solve(nlpf_problem* p, int B, const double* H, const double* g, double lam, double* dz_out,
+                                 int* info_out, void* stream) {
+    if (!p || B < 1 || !H || !g || !dz_out || !info_out) { nlpf_set_error("bad argument"); return NLPF_E_ARG; }
+    return nlpf_launch_factor_solve(p, B, H, g, lam, dz_out, info_out, (cudaStream_t)stream);
+}
+
+extern "C" int nlpf_solve(nlpf_problem* p, int B, double* z, const double* U, const double* data, const double* xprior,
+                          const double* wshift, const nlpf_opts* opts, double* cost_out, int* iters_out,
+                          int* status_out, void* stream) {
+    int rc = check_batch(p, B, z, data);
+    if (rc) return rc;
+    if (!opts || !cost_out || !iters_out || !status_out) { nlpf_set_error("null opts/output buffer"); return NLPF_E_ARG; }
+    if (p->d.m > 0 && !U) {
+        bool need = false;
+        // host copy of ucol is not kept; a parameter control without a U buffer reads as zero
+        (void)need;
+    }
+    return nlpf_launch_solve(p, B, z, U, data, xprior, wshift, opts, cost_out, iters_out, status_out, (cudaStream_t)stream);
+}
+
+extern "C" int nlpf_sample(nlpf_problem* p, int B, const double* z, int nt, const double* PhiT, double* out, void* stream) {
+    if (!p || B < 1 || nt < 1 || !z || !PhiT || !out) { nlpf_set_error("bad argument"); return NLPF_E_ARG; }
+    return nlpf_launch_sample(p, B, z, nt, PhiT, out, (cudaStream_t)stream);
+}

@@ -1,0 +1,67 @@
+// common.cuh -- shared declarations of libnlpfilter.so (sm_100a, fp64 throughout).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "nlpfilter.h"
+
+#define NLPF_NT 128            // threads per window CTA (4 warps: one per SM sub-partition)
+#define NLPF_NW (NLPF_NT / 32)
+#define NLPF_NA_MAX 8          // active node-variable components a measurement set may touch
+#define NLPF_NG_MAX 8
+#define NLPF_N_MAX 12
+#define NLPF_M_MAX 6
+#define NLPF_K_MAX 64
+#define NLPF_NV_MAX 24
+#define NLPF_NZ_MAX 224
+
+// Device-side image of one problem class.  Passed to kernels by value.
+struct DevProb {
+    int K, n, m, nv, ng, nz, np;      // np = packed lower-triangle size nz(nz+1)/2
+    int dyn_id, loss, has_prior, has_dyncost, has_nodecost;
+    int hconst;                       // 1: the dynamics part of H is constant (L2 loss, affine model)
+    int fconst;                       // 1: dF/dv is constant (affine model)
+    int nb, E, M, Ldata;
+    int na, nat;                      // active node components, na + ng
+    int ec;                           // epochs per measurement chunk
+    int npair;                        // K(K+1)/2
+    double delta;
+    double dyn_par[NLPF_NDYNPAR];
+    const double* A;                  // n*n
+    const double* Bm;                 // n*mm
+    const double* c0;                 // n
+    const int* cmap;                  // n
+    const int* ucol;                  // mm
+    const double* Dt;                 // K*K
+    const double* cw;                 // K
+    const double* cq;                 // K
+    const double* qinv;               // n
+    const double* pinv;               // n
+    const double* snode;              // nv
+    const int* bidx;                  // nb
+    const double* blo;
+    const double* bhi;
+    const double* Phi;                // E*K
+    const int* rtype;                 // M (sorted by epoch)
+    const int* rloc;                  // M*8 local indices: <na active comp, >=na global, -1 unused
+    const int* roff;                  // M
+    const int* estart;                // E+1
+    const int* act;                   // na  -> node-variable column
+    const double* Hc;                 // np  constant part of H (packed lower, row-major)
+    const double* Fc;                 // n*nv constant dF/dv (affine models)
+    const uint32_t* tab;              // np  packed index -> j | a<<8 | l<<16 | b<<24 (255 = global)
+    const uint16_t* ptab;             // npair  pair index -> j | l<<8
+    // shared-memory layout, offsets in doubles
+    int o_H, o_z, o_zt, o_g, o_ds, o_dz, o_f, o_lw, o_wh, o_slw, o_F, o_GF, o_FF, o_whs;
+    int o_Ve, o_G, o_q, o_Phi, o_Dt, o_red, smem_doubles;
+};
+
+struct nlpf_problem {
+    DevProb d;
+    void* blob;          // one device allocation holding every table
+    size_t blob_bytes;
+    size_t smem_bytes;
+    int device;
+};
+
+void nlpf_set_error(const char* fmt, ...);
+int nlpf_check_cuda(cudaError_t e, const char* what);

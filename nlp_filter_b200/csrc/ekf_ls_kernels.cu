@@ -1,0 +1,416 @@
+// ekf_ls_kernels.cu -- kernel (4): fused EKF predict/update, and the GNSS iterative least squares.
+//
+// EKF: one warp per filter, `steps` consecutive predict/update steps per launch; the mean and
+// covariance stay in shared memory for the whole trajectory, only u, z, satellite positions
+// stream in and the mean streams out.  Replaces utils/ekf.py:20-61 with the model functions
+// utils/gnss.py:4-44,64-76 (5-state GNSS) and autonomous-car.py:18-79 (9-state vehicle),
+// quirks included: the dynamics act on the mean in place and the vehicle
+// Jacobian is evaluated at the already-propagated state; the covariance update is the plain
+// S_pred - K (H S_pred) form without symmetrisation (ekf.py:54-59).
+//
+// LS: Gauss-Newton on pseudoranges in ECEF (utils/leastsquares.py:19-94); the reference's
+// pinv(G) dx (SVD) is replaced by the normal equations G^T G dx = G^T drho solved by Cholesky
+// (G has full column rank whenever >= 4 (5) satellites are in view).
+#include "common.cuh"
+#include <math.h>
+
+#define EKF_NMAX 9
+#define EKF_SMAX 16
+#define EKF_WARPS 4
+
+struct EkfSm {
+    double mu[EKF_NMAX];
+    double S[EKF_NMAX * EKF_NMAX];
+    double Sp[EKF_NMAX * EKF_NMAX];
+    double G[EKF_NMAX * EKF_NMAX];
+    double T[EKF_NMAX * EKF_NMAX];
+    double H[EKF_SMAX * EKF_NMAX];
+    double HS[EKF_SMAX * EKF_NMAX];
+    double Kt[EKF_SMAX * EKF_NMAX];      // K^T: row s, column i
+    double P[EKF_SMAX * (EKF_SMAX + 1)];
+    double v[EKF_SMAX];
+};
+
+// gnss.gnss_pos_and_bias, utils/gnss.py:64-76: x += dt*[u, x4, 0]; G = I, G[3][4] = dt
+__device__ void ekf_dyn_gnss5(double* mu, const double* u, double dt, double* G) {
+    for (int i = 0; i < 25; ++i) G[i] = 0.0;
+    for (int i = 0; i < 5; ++i) G[i * 5 + i] = 1.0;
+    G[3 * 5 + 4] = dt;
+    const double b4 = mu[4];
+    mu[0] += dt * u[0];
+    mu[1] += dt * u[1];
+    mu[2] += dt * u[2];
+    mu[3] += dt * b4;
+    mu[4] += dt * 0.0;
+}
+
+// discrete_vehicle_dynamics, autonomous-car.py:18-56 with the linear tyre model
+// utils/vehicle_sim.py:50-58,60-72 (no epsilon), explicit Euler; the Jacobian uses the state
+// AFTER the update (x is modified in place before J is formed).  par = C_AF C_AR M D_F D_R I_Z
+__device__ void ekf_dyn_car9(double* x, const double* u, double dt, const double* par, double* J) {
+    const double C_AF = par[0], C_AR = par[1], M = par[2], D_F = par[3], D_R = par[4], I_Z = par[5];
+    {
+        const double vx = x[3], vy = x[4], r = x[5];
+        const double a_r = (vy - D_R * r) / vx;
+        const double a_f = (vy + D_F * r) / vx - u[1];
+        const double Fyr = -C_AR * a_r, Fyf = -C_AF * a_f;
+        double sp, cp, sd, cd;
+        sincos(x[2], &sp, &cp);
+        sincos(u[1], &sd, &cd);
+        double xd[9];
+        xd[0] = vx * cp - vy * sp;
+        xd[1] = vx * sp + vy * cp;
+        xd[2] = r;
+        xd[3] = (-Fyf * sd + u[0]) / M + r * vy;
+        xd[4] = (Fyf * cd + Fyr) / M - r * vx;
+        xd[5] = (D_F * Fyf * cd - D_R * Fyr) / I_Z;
+        xd[6] = x[7];
+        xd[7] = 0.0;
+        xd[8] = 0.0;
+        for (int i = 0; i < 9; ++i) x[i] += dt * xd[i];
+    }
+    for (int i = 0; i < 81; ++i) J[i] = 0.0;
+    for (int i = 0; i < 9; ++i) J[i * 9 + i] = 1.0;
+    const double ivx = 1.0 / x[3], ivx2 = 1.0 / (x[3] * x[3]);
+    const double dFyf_dvx = C_AF * (x[4] + D_F * x[5]) * ivx2;
+    const double dFyf_dvy = -C_AF * ivx;
+    const double dFyf_dr = -C_AF * D_F * ivx;
+    const double dFyr_dvx = C_AR * (x[4] - D_R * x[5]) * ivx2;
+    const double dFyr_dvy = -C_AR * ivx;
+    const double dFyr_dr = C_AR * D_R * ivx;
+    double s2, c2, su, cu;
+    sincos(x[2], &s2, &c2);
+    sincos(u[1], &su, &cu);
+    J[0 * 9 + 2] += dt * (-x[3] * s2 - x[4] * c2);
+    J[0 * 9 + 3] += dt * c2;
+    J[0 * 9 + 4] += -dt * s2;
+    J[1 * 9 + 2] += dt * (x[3] * c2 - x[4] * s2);
+    J[1 * 9 + 3] += dt * s2;
+    J[1 * 9 + 4] += dt * c2;
+    J[2 * 9 + 5] += dt;
+    J[3 * 9 + 3] += -(dt / M) * (su * dFyf_dvx);
+    J[3 * 9 + 4] += dt * (x[5] - (su * dFyf_dvy) / M);
+    J[3 * 9 + 5] += dt * (x[4] - (su * dFyf_dr) / M);
+    J[4 * 9 + 3] += dt * ((cu * dFyf_dvx + dFyr_dvx) / M - x[5]);
+    J[4 * 9 + 4] += (dt / M) * (cu * dFyf_dvy + dFyr_dvy);
+    J[4 * 9 + 5] += dt * ((cu * dFyf_dr + dFyr_dr) / M - x[3]);
+    J[5 * 9 + 3] += (dt / I_Z) * (D_F * cu * dFyf_dvx - D_R * dFyr_dvx);
+    J[5 * 9 + 4] += (dt / I_Z) * (D_F * cu * dFyf_dvy - D_R * dFyr_dvy);
+    J[5 * 9 + 5] += (dt / I_Z) * (D_F * cu * dFyf_dr - D_R * dFyr_dr);
+    J[6 * 9 + 7] += dt;
+}
+
+__global__ void __launch_bounds__(EKF_WARPS * 32)
+ekf_kernel(int model, int B, int steps, int smax, double* __restrict__ mu_io, double* __restrict__ S_io,
+           const double* __restrict__ u, const double* __restrict__ z, const double* __restrict__ sat,
+           const int* __restrict__ nsat, const double* __restrict__ Q, double rvar, double dt,
+           const double* __restrict__ par, double* __restrict__ traj) {
+    extern __shared__ double ekf_sm_raw[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    EkfSm& W = reinterpret_cast<EkfSm*>(ekf_sm_raw)[warp];
+    const int n = (model == NLPF_EKF_GNSS5) ? 5 : 9;
+    const int m = (model == NLPF_EKF_GNSS5) ? 3 : 2;
+    // position / bias columns of the pseudorange model inside the state
+    // GNSS5: x,y,z,b = 0,1,2,3 (utils/gnss.py:4-21); CAR9: x,y,z,b = 0,1,8,6 (autonomous-car.py:58-79)
+    const int ix = 0, iy = 1, iz = (model == NLPF_EKF_GNSS5) ? 2 : 8, ib = (model == NLPF_EKF_GNSS5) ? 3 : 6;
+    double cpar[NLPF_NDYNPAR];
+    for (int i = 0; i < NLPF_NDYNPAR; ++i) cpar[i] = par ? par[i] : 0.0;
+
+    for (int f = blockIdx.x * EKF_WARPS + warp; f < B; f += gridDim.x * EKF_WARPS) {
+        for (int i = lane; i < n; i += 32) W.mu[i] = mu_io[(size_t)f * n + i];
+        for (int i = lane; i < n * n; i += 32) W.S[i] = S_io[(size_t)f * n * n + i];
+        __syncwarp();
+        for (int t = 0; t < steps; ++t) {
+            const size_t ft = (size_t)f * steps + t;
+            // ---- predict (ekf.py:40-44) ----
+            if (lane == 0) {
+                double uu[3];
+                for (int i = 0; i < m; ++i) uu[i] = u[ft * m + i];
+                if (model == NLPF_EKF_GNSS5) ekf_dyn_gnss5(W.mu, uu, dt, W.G);
+                else ekf_dyn_car9(W.mu, uu, dt, cpar, W.G);
+            }
+            __syncwarp();
+            for (int e = lane; e < n * n; e += 32) {      // T = S G^T
+                const int i = e / n, j = e - i * n;
+                double s = 0.0;
+                for (int k = 0; k < n; ++k) s = fma(W.S[i * n + k], W.G[j * n + k], s);
+                W.T[e] = s;
+            }
+            __syncwarp();
+            for (int e = lane; e < n * n; e += 32) {      // S_pred = G T + Q
+                const int i = e / n, j = e - i * n;
+                double s = 0.0;
+                for (int k = 0; k < n; ++k) s = fma(W.G[i * n + k], W.T[k * n + j], s);
+                W.Sp[e] = s + ((i == j) ? Q[i] : 0.0);
+            }
+            __syncwarp();
+            const int ns = nsat[ft];
+            if (ns > 0) {
+                // ---- correct (ekf.py:46-61) ----
+                for (int s = lane; s < ns; s += 32) {
+                    const double* sp = sat + (ft * smax + s) * 3;
+                    const double d0 = W.mu[ix] - sp[0], d1 = W.mu[iy] - sp[1], d2 = W.mu[iz] - sp[2];
+                    const double rho = sqrt(d0 * d0 + d1 * d1 + d2 * d2);
+                    for (int i = 0; i < n; ++i) W.H[s * n + i] = 0.0;
+                    W.H[s * n + ix] = d0 / rho;       // -LoS/|LoS|, LoS = sat - x (gnss.py:16-18)
+                    W.H[s * n + iy] = d1 / rho;
+                    W.H[s * n + iz] = d2 / rho;
+                    W.H[s * n + ib] = 1.0;
+                    W.v[s] = z[ft * smax + s] - (rho + W.mu[ib]);
+                }
+                __syncwarp();
+                for (int e = lane; e < ns * n; e += 32) {          // HS = H S_pred
+                    const int s = e / n, j = e - s * n;
+                    double acc = 0.0;
+                    for (int k = 0; k < n; ++k) acc = fma(W.H[s * n + k], W.Sp[k * n + j], acc);
+                    W.HS[e] = acc;
+                }
+                __syncwarp();
+                for (int e = lane; e < ns * ns; e += 32) {         // P = (H S_pred) H^T + R  (ekf.py:54)
+                    const int s = e / ns, s2 = e - s * ns;
+                    double acc = 0.0;
+                    for (int k = 0; k < n; ++k) acc = fma(W.HS[s * n + k], W.H[s2 * n + k], acc);
+                    W.P[s * (EKF_SMAX + 1) + s2] = acc + ((s == s2) ? rvar : 0.0);
+                }
+                __syncwarp();
+                // Cholesky P = L L^T in place (lower), lane = row
+                for (int j = 0; j < ns; ++j) {
+                    double djj = sqrt(W.P[j * (EKF_SMAX + 1) + j]);
+                    __syncwarp();
+                    if (lane == j) W.P[j * (EKF_SMAX + 1) + j] = djj;
+                    if (lane > j && lane < ns) W.P[lane * (EKF_SMAX + 1) + j] /= djj;
+                    __syncwarp();
+                    if (lane > j && lane < ns) {
+                        const double lij = W.P[lane * (EKF_SMAX + 1) + j];
+                        for (int k = j + 1; k <= lane; ++k)
+                            W.P[lane * (EKF_SMAX + 1) + k] = fma(-lij, W.P[k * (EKF_SMAX + 1) + j], W.P[lane * (EKF_SMAX + 1) + k]);
+                    }
+                    __syncwarp();
+                }
+                // K^T = P^-1 (H S_pred): one right-hand-side column per lane (K = S_pred H^T P^-1)
+                for (int c = lane; c < n; c += 32) {
+                    for (int s = 0; s < ns; ++s) {
+                        double acc = W.HS[s * n + c];
+                        for (int k = 0; k < s; ++k) acc = fma(-W.P[s * (EKF_SMAX + 1) + k], W.Kt[k * n + c], acc);
+                        W.Kt[s * n + c] = acc / W.P[s * (EKF_SMAX + 1) + s];
+                    }
+                    for (int s = ns - 1; s >= 0; --s) {
+                        double acc = W.Kt[s * n + c];
+                        for (int k = s + 1; k < ns; ++k) acc = fma(-W.P[k * (EKF_SMAX + 1) + s], W.Kt[k * n + c], acc);
+                        W.Kt[s * n + c] = acc / W.P[s * (EKF_SMAX + 1) + s];
+                    }
+                }
+                __syncwarp();
+                // Note: K uses HS^T = S_pred^T H^T; the reference forms S_pred H^T.  S_pred is symmetric up
+                // to rounding, so the two differ at the 1e-16 level only.
+                double mucor = 0.0;
+                if (lane < n) {
+                    for (int s = 0; s < ns; ++s) mucor = fma(W.Kt[s * n + lane], W.v[s], mucor);
+                }
+                for (int e = lane; e < n * n; e += 32) {           // S = S_pred - K (H S_pred)
+                    const int i = e / n, j = e - i * n;
+                    double acc = 0.0;
+                    for (int s = 0; s < ns; ++s) acc = fma(W.Kt[s * n + i], W.HS[s * n + j], acc);
+                    W.S[e] = W.Sp[e] - acc;
+                }
+                __syncwarp();
+                if (lane < n) W.mu[lane] += mucor;
+            } else {
+                for (int e = lane; e < n * n; e += 32) W.S[e] = W.Sp[e];
+            }
+            __syncwarp();
+            if (traj)
+                for (int i = lane; i < n; i += 32) traj[ft * n + i] = W.mu[i];
+        }
+        for (int i = lane; i < n; i += 32) mu_io[(size_t)f * n + i] = W.mu[i];
+        for (int i = lane; i < n * n; i += 32) S_io[(size_t)f * n * n + i] = W.S[i];
+        __syncwarp();
+    }
+}
+
+extern "C" int nlpf_ekf_run(int model, int B, int steps, int smax, double* mu_inout, double* S_inout, const double* u,
+                            const double* z, const double* sat, const int* nsat, const double* Q, double r, double dt,
+                            const double* par, double* mu_traj_out, void* stream) {
+    if (model != NLPF_EKF_GNSS5 && model != NLPF_EKF_CAR9) { nlpf_set_error("unknown EKF model %d", model); return NLPF_E_ARG; }
+    if (B < 1 || steps < 1 || smax < 1 || smax > EKF_SMAX) { nlpf_set_error("bad EKF sizes B=%d steps=%d smax=%d (smax<=%d)", B, steps, smax, EKF_SMAX); return NLPF_E_ARG; }
+    if (!mu_inout || !S_inout || !u || !z || !sat || !nsat || !Q) { nlpf_set_error("null EKF buffer"); return NLPF_E_ARG; }
+    if (model == NLPF_EKF_CAR9 && !par) { nlpf_set_error("vehicle EKF needs the car constants"); return NLPF_E_ARG; }
+    const size_t smem = sizeof(EkfSm) * EKF_WARPS;
+    static bool attr_done = false;
+    if (!attr_done) {
+        if (nlpf_check_cuda(cudaFuncSetAttribute(ekf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "ekf smem attr")) return NLPF_E_CUDA;
+        attr_done = true;
+    }
+    int blocks = (B + EKF_WARPS - 1) / EKF_WARPS;
+    ekf_kernel<<<blocks, EKF_WARPS * 32, smem, (cudaStream_t)stream>>>(model, B, steps, smax, mu_inout, S_inout, u, z, sat, nsat,
+                                                                        Q, r, dt, par, mu_traj_out);
+    return nlpf_check_cuda(cudaGetLastError(), "ekf_kernel launch");
+}
+
+// ------------------------------------------------------------------------------------------
+// GNSS iterative least squares: one warp per epoch / problem, lanes over satellites.
+// ------------------------------------------------------------------------------------------
+template <int NU>
+__device__ bool chol_solve_small(double* N, double* b) {   // N packed lower NU(NU+1)/2, in place; b -> solution
+    for (int j = 0; j < NU; ++j) {
+        double d = N[j * (j + 1) / 2 + j];
+        for (int k = 0; k < j; ++k) d -= N[j * (j + 1) / 2 + k] * N[j * (j + 1) / 2 + k];
+        if (!(d > 0.0)) return false;
+        d = sqrt(d);
+        N[j * (j + 1) / 2 + j] = d;
+        for (int i = j + 1; i < NU; ++i) {
+            double s = N[i * (i + 1) / 2 + j];
+            for (int k = 0; k < j; ++k) s -= N[i * (i + 1) / 2 + k] * N[j * (j + 1) / 2 + k];
+            N[i * (i + 1) / 2 + j] = s / d;
+        }
+    }
+    for (int i = 0; i < NU; ++i) {
+        double s = b[i];
+        for (int k = 0; k < i; ++k) s -= N[i * (i + 1) / 2 + k] * b[k];
+        b[i] = s / N[i * (i + 1) / 2 + i];
+    }
+    for (int i = NU - 1; i >= 0; --i) {
+        double s = b[i];
+        for (int k = i + 1; k < NU; ++k) s -= N[k * (k + 1) / 2 + i] * b[k];
+        b[i] = s / N[i * (i + 1) / 2 + i];
+    }
+    return true;
+}
+
+template <int NU>
+__global__ void __launch_bounds__(128)
+ls_kernel(int B, int smax, const double* __restrict__ sat, const double* __restrict__ pr, const int* __restrict__ nsat,
+          const double* __restrict__ tcol, double* __restrict__ x_io, int maxiter, double tol, int* __restrict__ iters_out) {
+    const int lane = threadIdx.x & 31;
+    const int wglob = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int nwarps = (gridDim.x * blockDim.x) >> 5;
+    constexpr int NP = NU * (NU + 1) / 2;
+    for (int e = wglob; e < B; e += nwarps) {
+        double x[NU];
+        for (int i = 0; i < NU; ++i) x[i] = x_io[(size_t)e * NU + i];
+        const int ns = nsat[e];
+        const double* se = sat + (size_t)e * smax * 3;
+        const double* pe = pr + (size_t)e * smax;
+        const double* te = tcol ? tcol + (size_t)e * smax : nullptr;
+        int it = 0;
+        for (; it < maxiter;) {
+            double N[NP], rhs[NU];
+            for (int i = 0; i < NP; ++i) N[i] = 0.0;
+            for (int i = 0; i < NU; ++i) rhs[i] = 0.0;
+            for (int s = lane; s < ns; s += 32) {
+                const double d0 = x[0] - se[s * 3 + 0], d1 = x[1] - se[s * 3 + 1], d2 = x[2] - se[s * 3 + 2];
+                const double rho = sqrt(d0 * d0 + d1 * d1 + d2 * d2);
+                double row[NU];
+                row[0] = d0 / rho;      // -(sat - x)/|sat - x|, leastsquares.py:6-16
+                row[1] = d1 / rho;
+                row[2] = d2 / rho;
+                row[3] = 1.0;
+                double pred = rho + x[3];
+                if (NU == 5) {
+                    row[NU - 1] = te[s];
+                    pred += x[NU - 1] * te[s];
+                }
+                const double dr = pe[s] - pred;
+                int q = 0;
+                for (int i = 0; i < NU; ++i) {
+                    for (int j = 0; j <= i; ++j) N[q++] += row[i] * row[j];
+                    rhs[i] += row[i] * dr;
+                }
+            }
+            for (int i = 0; i < NP; ++i)
+                for (int o = 16; o > 0; o >>= 1) N[i] += __shfl_xor_sync(0xffffffffu, N[i], o);
+            for (int i = 0; i < NU; ++i)
+                for (int o = 16; o > 0; o >>= 1) rhs[i] += __shfl_xor_sync(0xffffffffu, rhs[i], o);
+            ++it;
+            if (!chol_solve_small<NU>(N, rhs)) break;        // rank deficient geometry: leave x as is
+            double nrm = 0.0;
+            for (int i = 0; i < NU; ++i) { x[i] += rhs[i]; nrm += rhs[i] * rhs[i]; }
+            if (sqrt(nrm) < tol) break;                      // leastsquares.py:39
+        }
+        if (lane == 0) {
+            for (int i = 0; i < NU; ++i) x_io[(size_t)e * NU + i] = x[i];
+            if (iters_out) iters_out[e] = it;
+        }
+    }
+}
+
+extern "C" int nlpf_ls_solve(int B, int smax, const double* sat, const double* pr, const int* nsat, const double* tcol,
+                             double* x_inout, int maxiter, double tol, int* iters_out, void* stream) {
+    if (B < 1 || smax < 1 || !sat || !pr || !nsat || !x_inout) { nlpf_set_error("bad LS argument"); return NLPF_E_ARG; }
+    const int threads = 128;
+    int blocks = (int)(((size_t)B * 32 + threads - 1) / threads);
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    if (tcol) ls_kernel<5><<<blocks, threads, 0, (cudaStream_t)stream>>>(B, smax, sat, pr, nsat, tcol, x_inout, maxiter, tol, iters_out);
+    else ls_kernel<4><<<blocks, threads, 0, (cudaStream_t)stream>>>(B, smax, sat, pr, nsat, nullptr, x_inout, maxiter, tol, iters_out);
+    return nlpf_check_cuda(cudaGetLastError(), "ls_kernel launch");
+}
+
+// one-shot velocity solve, leastsquares.py:45-63
+__global__ void __launch_bounds__(128)
+ls_vel_kernel(int B, int smax, const double* __restrict__ sat, const double* __restrict__ satvel,
+              const double* __restrict__ prr, const int* __restrict__ nsat, const double* __restrict__ xpos,
+              double* __restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const int wglob = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int nwarps = (gridDim.x * blockDim.x) >> 5;
+    for (int e = wglob; e < B; e += nwarps) {
+        const int ns = nsat[e];
+        const double* se = sat + (size_t)e * smax * 3;
+        const double* ve = satvel + (size_t)e * smax * 3;
+        const double* pe = prr + (size_t)e * smax;
+        const double x0 = xpos[(size_t)e * 3], x1 = xpos[(size_t)e * 3 + 1], x2 = xpos[(size_t)e * 3 + 2];
+        double N[10], rhs[4];
+        for (int i = 0; i < 10; ++i) N[i] = 0.0;
+        for (int i = 0; i < 4; ++i) rhs[i] = 0.0;
+        for (int s = lane; s < ns; s += 32) {
+            const double d0 = x0 - se[s * 3], d1 = x1 - se[s * 3 + 1], d2 = x2 - se[s * 3 + 2];
+            const double rho = sqrt(d0 * d0 + d1 * d1 + d2 * d2);
+            const double row[4] = {d0 / rho, d1 / rho, d2 / rho, 1.0};
+            // drho = pr_rate - sat_vel . LoS_dir with LoS_dir = -G[k,:3]
+            const double dr = pe[s] - (ve[s * 3] * (-row[0]) + ve[s * 3 + 1] * (-row[1]) + ve[s * 3 + 2] * (-row[2]));
+            int q = 0;
+            for (int i = 0; i < 4; ++i) {
+                for (int j = 0; j <= i; ++j) N[q++] += row[i] * row[j];
+                rhs[i] += row[i] * dr;
+            }
+        }
+        for (int i = 0; i < 10; ++i)
+            for (int o = 16; o > 0; o >>= 1) N[i] += __shfl_xor_sync(0xffffffffu, N[i], o);
+        for (int i = 0; i < 4; ++i)
+            for (int o = 16; o > 0; o >>= 1) rhs[i] += __shfl_xor_sync(0xffffffffu, rhs[i], o);
+        if (!chol_solve_small<4>(N, rhs)) { for (int i = 0; i < 4; ++i) rhs[i] = nan(""); }
+        if (lane == 0) for (int i = 0; i < 4; ++i) out[(size_t)e * 4 + i] = rhs[i];
+    }
+}
+
+extern "C" int nlpf_ls_vel(int B, int smax, const double* sat, const double* satvel, const double* prr, const int* nsat,
+                           const double* x, double* out, void* stream) {
+    if (B < 1 || smax < 1 || !sat || !satvel || !prr || !nsat || !x || !out) { nlpf_set_error("bad LS-vel argument"); return NLPF_E_ARG; }
+    const int threads = 128;
+    int blocks = (int)(((size_t)B * 32 + threads - 1) / threads);
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    ls_vel_kernel<<<blocks, threads, 0, (cudaStream_t)stream>>>(B, smax, sat, satvel, prr, nsat, x, out);
+    return nlpf_check_cuda(cudaGetLastError(), "ls_vel_kernel launch");
+}
+
+// ------------------------------------------------------------------------------------------
+// FP64 FMA throughput probe (roofline denominator; MEASURED_PEAKS.json has no FP64 figure)
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) fp64_probe_kernel(int iters, double* sink) {
+    double a0 = threadIdx.x * 1e-9, a1 = a0 + 1.0, a2 = a0 + 2.0, a3 = a0 + 3.0;
+    double a4 = a0 + 4.0, a5 = a0 + 5.0, a6 = a0 + 6.0, a7 = a0 + 7.0;
+    const double m = 0.999999999, c = 1e-9;
+    for (int i = 0; i < iters; ++i) {
+        a0 = fma(a0, m, c); a1 = fma(a1, m, c); a2 = fma(a2, m, c); a3 = fma(a3, m, c);
+        a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
+    }
+    const double s = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+    if (s == 123.456) sink[0] = s;
+}
+
+extern "C" int nlpf_fp64_probe(int iters, double* sink_dev, double* flops_out, void* stream) {
+    const int blocks = 148 * 8, threads = 256;
+    fp64_probe_kernel<<<blocks, threads, 0, (cudaStream_t)stream>>>(iters, sink_dev);
+    if (flops_out) *flops_out = 2.0 * 8.0 * (double)iters * blocks * threads;
+    return nlpf_check_cuda(cudaGetLastError(), "fp64_probe launch");
+}

@@ -1,0 +1,1023 @@
+// nls_kernels.cu -- one CTA per estimation window: residual/Jacobian evaluation, structured
+// assembly of the normal equations, in-shared-memory LDL^T and the damped Gauss-Newton /
+// log-barrier iteration, all on chip (fp64).
+//
+// Replaces, for B windows at once, what the reference runs per window inside
+// CasADi -> IPOPT -> MUMPS when a script calls NLP.solve() (nlp/nlp.py:76-83) on a problem built
+// with nlp/nlp.py:202-286.  The mathematics:
+//   W_k = sum_j Dt_kj X_j - f(X_k,U_k) (+ shift)           defects, nlp.py:225-235
+//   J   = sum_k cw_k rho(W_k) + sum_i w_i (y_i - h_i(Phi_i V))^2 + (X_0-x0)^T P^-1 (X_0-x0)
+//         + sum_k cq_k V_k^T S V_k
+//   H   = Hc + sum_e (phi_e phi_e^T) (x) G_e + dynamics cross/diagonal blocks,   g = J^T W r
+// H is dense (nz x nz) because the Chebyshev differentiation matrix and the Lagrange
+// interpolation couple all nodes (collocation.py:42-64, nlp.py:266-269); it lives packed
+// (lower triangle, row-major) in shared memory with the right-hand side appended as one more
+// row, so the forward substitution happens inside the factorisation.
+#include "common.cuh"
+#include <math.h>
+
+// ------------------------------------------------------------------------------------------
+// block-wide reductions; every thread returns the same value (same summation order)
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ double warp_max(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+__device__ __forceinline__ double warp_min(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+__device__ double block_sum(double v, double* red) {
+    v = warp_sum(v);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    double s = 0.0;
+#pragma unroll
+    for (int i = 0; i < NLPF_NW; ++i) s += red[i];
+    return s;
+}
+__device__ double block_max(double v, double* red) {
+    v = warp_max(v);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    double s = red[0];
+#pragma unroll
+    for (int i = 1; i < NLPF_NW; ++i) s = fmax(s, red[i]);
+    return s;
+}
+__device__ double block_min(double v, double* red) {
+    v = warp_min(v);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    double s = red[0];
+#pragma unroll
+    for (int i = 1; i < NLPF_NW; ++i) s = fmin(s, red[i]);
+    return s;
+}
+
+// ------------------------------------------------------------------------------------------
+// Kernel (1a): continuous-time models f(x,u) and dF/dv, nlp/dynamics.py.
+// Fk is the n x nv Jacobian w.r.t. the node variables (state columns through cmap, unknown
+// controls through ucol), row-major, zeroed by the caller when jac is set.
+// ------------------------------------------------------------------------------------------
+struct FAcc {
+    double* Fk;
+    const int* cmap;
+    int nv;
+    __device__ __forceinline__ void add(int row, int statecomp, double v) const {
+        Fk[row * nv + cmap[statecomp]] += v;
+    }
+};
+
+__device__ void vehicle6(const double* par, const double* x, const double* u, double* f, bool jac,
+                         const FAcc& F) {
+    // vehicle_dynamics, dynamics.py:148-164; par = C_AF C_AR M D_F D_R I_Z
+    const double C_AF = par[0], C_AR = par[1], M = par[2], D_F = par[3], D_R = par[4], I_Z = par[5];
+    const double psi = x[2], vx = x[3], vy = x[4], r = x[5];
+    const double Fx = u[0], dl = u[1];
+    const double den = vx + 0.001;
+    const double Fyr = -C_AR * (vy - D_R * r) / den;
+    const double Fyf = -C_AF * ((vy + D_F * r) / den - dl);
+    double sp, cp, sd, cd;
+    sincos(psi, &sp, &cp);
+    sincos(dl, &sd, &cd);
+    f[0] = vx * cp - vy * sp;
+    f[1] = vx * sp + vy * cp;
+    f[2] = r;
+    f[3] = (-Fyf * sd + Fx) / M + r * vy;
+    f[4] = (Fyf * cd + Fyr) / M - r * vx;
+    f[5] = (D_F * Fyf * cd - D_R * Fyr) / I_Z;
+    if (!jac) return;
+    const double den2 = den * den;
+    const double a_r = C_AR * (vy - D_R * r) / den2, b_r = -C_AR / den, c_r = C_AR * D_R / den;
+    const double a_f = C_AF * (vy + D_F * r) / den2, b_f = -C_AF / den, c_f = -C_AF * D_F / den;
+    F.add(0, 2, -vx * sp - vy * cp);
+    F.add(0, 3, cp);
+    F.add(0, 4, -sp);
+    F.add(1, 2, vx * cp - vy * sp);
+    F.add(1, 3, sp);
+    F.add(1, 4, cp);
+    F.add(2, 5, 1.0);
+    F.add(3, 3, -sd * a_f / M);
+    F.add(3, 4, -sd * b_f / M + r);
+    F.add(3, 5, -sd * c_f / M + vy);
+    F.add(4, 3, (cd * a_f + a_r) / M - r);
+    F.add(4, 4, (cd * b_f + b_r) / M);
+    F.add(4, 5, (cd * c_f + c_r) / M - vx);
+    F.add(5, 3, (D_F * cd * a_f - D_R * a_r) / I_Z);
+    F.add(5, 4, (D_F * cd * b_f - D_R * b_r) / I_Z);
+    F.add(5, 5, (D_F * cd * c_f - D_R * c_r) / I_Z);
+}
+
+__device__ void quadcopter12(const double* par, const double* x, const double* u, double* f, bool jac,
+                             const FAcc& F) {
+    // quadcopter, dynamics.py:40-59; par = m Ixx Iyy Izz
+    const double m = par[0], Ix = par[1], Iy = par[2], Iz = par[3];
+    const double p = x[9], q = x[10], r = x[11];
+    double sph, cph, sth, cth, sps, cps;
+    sincos(x[3], &sph, &cph);
+    sincos(x[4], &sth, &cth);
+    sincos(x[5], &sps, &cps);
+    const double tth = sth / cth;
+    const double a = q * sph + r * cph;
+    const double tm = u[0] / m;
+    f[0] = x[6];
+    f[1] = x[7];
+    f[2] = x[8];
+    f[3] = p + a * tth;
+    f[4] = q * cph - r * sph;
+    f[5] = a / cth;
+    f[6] = tm * (sph * sps + cph * sth * cps);
+    f[7] = tm * (cph * sth * sps - sph * cps);
+    f[8] = tm * (cph * cth) - 9.81;
+    f[9] = (u[1] - (Iz - Iy) * q * r) / Ix;
+    f[10] = (u[2] - (Ix - Iz) * r * p) / Iy;
+    f[11] = (u[3] - (Iy - Ix) * p * q) / Iz;
+    if (!jac) return;
+    const double da = q * cph - r * sph;
+    F.add(0, 6, 1.0);
+    F.add(1, 7, 1.0);
+    F.add(2, 8, 1.0);
+    F.add(3, 3, da * tth);
+    F.add(3, 4, a / (cth * cth));
+    F.add(3, 9, 1.0);
+    F.add(3, 10, sph * tth);
+    F.add(3, 11, cph * tth);
+    F.add(4, 3, -q * sph - r * cph);
+    F.add(4, 10, cph);
+    F.add(4, 11, -sph);
+    F.add(5, 3, da / cth);
+    F.add(5, 4, a * sth / (cth * cth));
+    F.add(5, 10, sph / cth);
+    F.add(5, 11, cph / cth);
+    F.add(6, 3, tm * (cph * sps - sph * sth * cps));
+    F.add(6, 4, tm * (cph * cth * cps));
+    F.add(6, 5, tm * (sph * cps - cph * sth * sps));
+    F.add(7, 3, tm * (-sph * sth * sps - cph * cps));
+    F.add(7, 4, tm * (cph * cth * sps));
+    F.add(7, 5, tm * (cph * sth * cps + sph * sps));
+    F.add(8, 3, tm * (-sph * cth));
+    F.add(8, 4, tm * (-cph * sth));
+    F.add(9, 10, -(Iz - Iy) * r / Ix);
+    F.add(9, 11, -(Iz - Iy) * q / Ix);
+    F.add(10, 9, -(Ix - Iz) * r / Iy);
+    F.add(10, 11, -(Ix - Iz) * p / Iy);
+    F.add(11, 9, -(Iy - Ix) * q / Iz);
+    F.add(11, 10, -(Iy - Ix) * p / Iz);
+}
+
+// f and (optionally) dF/dv of node k.  x, u are the node's full state / control values.
+__device__ void dyn_eval(const DevProb& P, const double* x, const double* u, double* f, bool jac, double* Fk) {
+    const int n = P.n, m = P.m, nv = P.nv;
+    FAcc F{Fk, P.cmap, nv};
+    switch (P.dyn_id) {
+        case NLPF_DYN_AFFINE: {
+            for (int i = 0; i < n; ++i) {
+                double s = P.c0[i];
+                for (int j = 0; j < n; ++j) s = fma(P.A[i * n + j], x[j], s);
+                for (int j = 0; j < m; ++j) s = fma(P.Bm[i * m + j], u[j], s);
+                f[i] = s;
+            }
+            if (jac)
+                for (int i = 0; i < n * nv; ++i) Fk[i] = P.Fc[i];
+            return;
+        }
+        case NLPF_DYN_VDP: {   // dynamics.py:61-66
+            f[0] = (1.0 - x[1] * x[1]) * x[0] - x[1] + u[0];
+            f[1] = x[0];
+            if (jac) {
+                F.add(0, 0, 1.0 - x[1] * x[1]);
+                F.add(0, 1, -2.0 * x[0] * x[1] - 1.0);
+                F.add(1, 0, 1.0);
+                if (P.ucol[0] >= 0) Fk[0 * nv + P.ucol[0]] += 1.0;
+            }
+            return;
+        }
+        case NLPF_DYN_BICYCLE: {   // dynamics.py:117-136 (heading is x[2])
+            const double v = 8.72649116358 * u[0] - 0.856053299155;
+            const double dl = 0.48869219055841229 * u[1];   // deg2rad(28)
+            double s2, c2;
+            sincos(x[2], &s2, &c2);
+            f[0] = v * c2;
+            f[1] = v * s2;
+            f[2] = 0.0;
+            f[3] = x[4];
+            f[4] = 0.0;
+            f[5] = (v / 0.28) * tan(dl);
+            if (jac) {
+                F.add(0, 2, -v * s2);
+                F.add(1, 2, v * c2);
+                F.add(3, 4, 1.0);
+            }
+            return;
+        }
+        case NLPF_DYN_VEHICLE:
+            vehicle6(P.dyn_par, x, u, f, jac, F);
+            return;
+        case NLPF_DYN_VEHICLE_GNSS:   // dynamics.py:166-174
+            vehicle6(P.dyn_par, x, u, f, jac, F);
+            f[6] = x[7];
+            f[7] = 0.0;
+            f[8] = 0.0;
+            if (jac) F.add(6, 7, 1.0);
+            return;
+        case NLPF_DYN_QUADCOPTER:
+            quadcopter12(P.dyn_par, x, u, f, jac, F);
+            return;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Kernel (1b): measurement models h and their sparse gradients, nlp/measurements.py.
+// loc[] are local indices (< na: interpolated active component, >= na: global unknown).
+// Returns the number of gradient entries written to (gl[], gv[]).
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ double lval(int l, const double* xe, const double* glob, int na) {
+    return l < na ? xe[l] : glob[l - na];
+}
+
+__device__ int meas_eval(int rt, const int* loc, const double* rec, const double* xe, const double* glob,
+                         int na, double& h, int* gl, double* gv) {
+    switch (rt) {
+        case NLPF_RT_STATE:
+            h = lval(loc[0], xe, glob, na);
+            gl[0] = loc[0];
+            gv[0] = 1.0;
+            return 1;
+        case NLPF_RT_PR: {   // measurements.py:56-70, 81-87
+            const double d0 = lval(loc[0], xe, glob, na) - rec[2];
+            const double d1 = lval(loc[1], xe, glob, na) - rec[3];
+            const double d2 = lval(loc[2], xe, glob, na) - rec[4];
+            const double rho = sqrt(d0 * d0 + d1 * d1 + d2 * d2);
+            h = rho + lval(loc[3], xe, glob, na);
+            const double ir = 1.0 / rho;
+            gl[0] = loc[0]; gv[0] = d0 * ir;
+            gl[1] = loc[1]; gv[1] = d1 * ir;
+            gl[2] = loc[2]; gv[2] = d2 * ir;
+            gl[3] = loc[3]; gv[3] = 1.0;
+            return 4;
+        }
+        case NLPF_RT_PRR: {   // measurements.py:72-79
+            const double r0 = rec[2] - lval(loc[0], xe, glob, na);
+            const double r1 = rec[3] - lval(loc[1], xe, glob, na);
+            const double r2 = rec[4] - lval(loc[2], xe, glob, na);
+            const double rho = sqrt(r0 * r0 + r1 * r1 + r2 * r2);
+            const double ir = 1.0 / rho;
+            const double e0 = r0 * ir, e1 = r1 * ir, e2 = r2 * ir;
+            const double v0 = rec[5] - lval(loc[3], xe, glob, na);
+            const double v1 = rec[6] - lval(loc[4], xe, glob, na);
+            const double v2 = rec[7] - lval(loc[5], xe, glob, na);
+            const double ev = e0 * v0 + e1 * v1 + e2 * v2;
+            h = ev + lval(loc[6], xe, glob, na);
+            gl[0] = loc[0]; gv[0] = -(v0 - e0 * ev) * ir;
+            gl[1] = loc[1]; gv[1] = -(v1 - e1 * ev) * ir;
+            gl[2] = loc[2]; gv[2] = -(v2 - e2 * ev) * ir;
+            gl[3] = loc[3]; gv[3] = -e0;
+            gl[4] = loc[4]; gv[4] = -e1;
+            gl[5] = loc[5]; gv[5] = -e2;
+            gl[6] = loc[6]; gv[6] = 1.0;
+            return 7;
+        }
+        case NLPF_RT_RANGE:        // measurements.py:13-19, 46-53: loc[0..2] vs loc[3..5], dim = loc[6]
+        case NLPF_RT_RANGE_PT: {   // measurements.py:8-12, 40-45: loc[3..5] < 0 => point from the record
+            const int dim = loc[6];
+            double d[3] = {0.0, 0.0, 0.0};
+            double s = .000001;
+            for (int c = 0; c < dim; ++c) {
+                const double other = (loc[3 + c] >= 0) ? lval(loc[3 + c], xe, glob, na) : rec[2 + c];
+                d[c] = lval(loc[c], xe, glob, na) - other;
+                s += d[c] * d[c];
+            }
+            h = sqrt(s);
+            const double ih = 1.0 / h;
+            int nn = 0;
+            for (int c = 0; c < dim; ++c) {
+                gl[nn] = loc[c]; gv[nn] = d[c] * ih; ++nn;
+                if (loc[3 + c] >= 0) { gl[nn] = loc[3 + c]; gv[nn] = -d[c] * ih; ++nn; }
+            }
+            return nn;
+        }
+        case NLPF_RT_HEADING: {   // measurements.py:30-36 (atan2(r_x, r_y): angle from +y)
+            const double ry = lval(loc[4], xe, glob, na) - lval(loc[1], xe, glob, na);
+            const double rx = lval(loc[3], xe, glob, na) - lval(loc[0], xe, glob, na) + .00001;
+            const double id2 = 1.0 / (rx * rx + ry * ry);
+            h = atan2(rx, ry);
+            gl[0] = loc[0]; gv[0] = -ry * id2;
+            gl[1] = loc[1]; gv[1] = rx * id2;
+            gl[2] = loc[3]; gv[2] = ry * id2;
+            gl[3] = loc[4]; gv[3] = -rx * id2;
+            return 4;
+        }
+        case NLPF_RT_HEADING_PT: {   // measurements.py:25-29
+            const double p0 = (loc[3] >= 0) ? lval(loc[3], xe, glob, na) : rec[2];
+            const double p1 = (loc[4] >= 0) ? lval(loc[4], xe, glob, na) : rec[3];
+            const double ry = p1 - lval(loc[1], xe, glob, na);
+            const double rx = p0 - lval(loc[0], xe, glob, na);
+            const double id2 = 1.0 / (rx * rx + ry * ry);
+            h = atan2(rx, ry);
+            int nn = 0;
+            gl[nn] = loc[0]; gv[nn] = -ry * id2; ++nn;
+            gl[nn] = loc[1]; gv[nn] = rx * id2; ++nn;
+            if (loc[3] >= 0) { gl[nn] = loc[3]; gv[nn] = ry * id2; ++nn; }
+            if (loc[4] >= 0) { gl[nn] = loc[4]; gv[nn] = -rx * id2; ++nn; }
+            return nn;
+        }
+    }
+    h = 0.0;
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// Per-window pointers
+// ------------------------------------------------------------------------------------------
+struct WinPtr {
+    const double* U;       // K*m   or NULL
+    const double* data;    // Ldata
+    const double* xprior;  // n     or NULL
+    const double* wshift;  // K*n   or NULL
+};
+
+__device__ __forceinline__ int pk(int r, int c) { return ((r * (r + 1)) >> 1) + c; }
+
+// ------------------------------------------------------------------------------------------
+// Kernels (1)+(2): objective, merit and -- when FULL -- gradient g and Gauss-Newton matrix H
+// (packed, in shared memory) of one window at the iterate zc (shared memory).
+// Returns J and merit = J/2 + barrier (identical in every thread).  merit = +inf flags an
+// iterate outside the bounds or a non-finite objective.
+// ------------------------------------------------------------------------------------------
+template <bool FULL>
+__device__ void eval_window(const DevProb& P, double* sm, const double* zc, const WinPtr& wp, double mu,
+                            double& J_out, double& merit_out, double& noise_out) {
+    const int tid = threadIdx.x;
+    const int K = P.K, n = P.n, m = P.m, nv = P.nv, ng = P.ng, nz = P.nz, na = P.na, nat = P.nat;
+    double* Hp = sm + P.o_H;
+    double* g = sm + P.o_g;
+    double* fbuf = sm + P.o_f;     // K*n  f(X_k,U_k)
+    double* lw = sm + P.o_lw;      // K*n  weight * W   (half gradient of the dynamics cost w.r.t. W)
+    double* wh = sm + P.o_wh;      // K*n  curvature weight
+    double* slw = sm + P.o_slw;    // K*nv S^T lw
+    double* Fs = sm + P.o_F;       // K*n*nv
+    double* GF = sm + P.o_GF;      // K*nv*nv  S^T Lambda_k F_k
+    double* FF = sm + P.o_FF;      // K*nv*nv  F_k^T Lambda_k F_k
+    double* whs = sm + P.o_whs;    // K*nv     S^T Lambda_k S (diagonal), Huber only
+    double* Ve = sm + P.o_Ve;
+    double* G = sm + P.o_G;
+    double* q = sm + P.o_q;
+    const double* Phi = sm + P.o_Phi;
+    const double* Dt = sm + P.o_Dt;
+    double* red = sm + P.o_red;
+    const bool dyn_h = FULL && !P.hconst;            // H has a state-dependent dynamics part
+    const bool need_F = dyn_h;                       // ... which needs dF/dv per node in shared memory
+
+    double cost = 0.0;      // thread-local share of J
+    double bar = 0.0;       // thread-local share of the barrier
+    double nse = 0.0;       // thread-local share of the first-order rounding bound of J (in units of eps)
+    bool bad = false;
+
+    // ---- phase A: H <- constant part, g <- 0 ----
+    if (FULL) {
+        for (int p = tid; p < P.np; p += NLPF_NT) Hp[p] = P.Hc[p];
+        for (int i = tid; i < nz; i += NLPF_NT) g[i] = 0.0;
+    }
+    // ---- phase B: node dynamics f (and dF/dv) ----
+    if (P.has_dyncost) {
+        for (int k = tid; k < K; k += NLPF_NT) {
+            double x[NLPF_N_MAX], u[NLPF_M_MAX], f[NLPF_N_MAX];
+            for (int i = 0; i < n; ++i) x[i] = zc[k * nv + P.cmap[i]];
+            for (int i = 0; i < m; ++i)
+                u[i] = (P.ucol[i] >= 0) ? zc[k * nv + P.ucol[i]] : (wp.U ? wp.U[k * m + i] : 0.0);
+            double* Fk = Fs + k * n * nv;
+            if (need_F)
+                for (int i = 0; i < n * nv; ++i) Fk[i] = 0.0;
+            dyn_eval(P, x, u, f, need_F, Fk);
+            for (int i = 0; i < n; ++i) fbuf[k * n + i] = f[i];
+        }
+        __syncthreads();
+        // ---- phase C: defects W, weights ----
+        for (int t = tid; t < K * n; t += NLPF_NT) {
+            const int k = t / n, i = t - k * n;
+            const int col = P.cmap[i];
+            double W = -fbuf[t];
+            double mag = fabs(fbuf[t]);
+            for (int j = 0; j < K; ++j) {
+                const double dx = Dt[k * K + j] * zc[j * nv + col];
+                W += dx;
+                mag += fabs(dx);
+            }
+            if (wp.wshift) W += wp.wshift[t];
+            const double cq = P.cw[k] * P.qinv[i];
+            if (P.loss == NLPF_LOSS_HUBER) {
+                const double wd = W / P.delta;
+                const double s = sqrt(1.0 + wd * wd);
+                cost += cq * 2.0 * P.delta * P.delta * (s - 1.0);
+                lw[t] = cq * W / s;
+                wh[t] = cq * (s + 1.0) / (2.0 * s * s);
+            } else {
+                cost += cq * W * W;
+                lw[t] = cq * W;
+                wh[t] = cq;
+            }
+            nse += 2.0 * fabs(lw[t]) * mag;
+        }
+        __syncthreads();
+        if (FULL) {
+            // ---- phase D: S^T lw, and the per-node blocks GF, FF (and S^T Lambda S) ----
+            for (int t = tid; t < K * nv; t += NLPF_NT) {
+                const int k = t / nv, a = t - k * nv;
+                double s = 0.0, sw = 0.0;
+                for (int i = 0; i < n; ++i)
+                    if (P.cmap[i] == a) { s += lw[k * n + i]; sw += wh[k * n + i]; }
+                slw[t] = s;
+                whs[t] = sw;
+            }
+            if (dyn_h) {
+                for (int t = tid; t < K * nv * nv; t += NLPF_NT) {
+                    const int k = t / (nv * nv);
+                    const int rem = t - k * nv * nv;
+                    const int a = rem / nv, b = rem - a * nv;
+                    const double* Fk = Fs + k * n * nv;
+                    double sgf = 0.0, sff = 0.0;
+                    for (int i = 0; i < n; ++i) {
+                        const double w_i = wh[k * n + i];
+                        const double fib = Fk[i * nv + b];
+                        if (P.cmap[i] == a) sgf = fma(w_i, fib, sgf);          // GF[a][b] = sum_{cmap[i]=a} w F[i][b]
+                        sff = fma(Fk[i * nv + a] * w_i, fib, sff);             // FF[a][b]
+                    }
+                    GF[t] = sgf;
+                    FF[t] = sff;
+                }
+            }
+            __syncthreads();
+            // ---- phase E: gradient of the dynamics cost, arrival cost, node cost ----
+            for (int t = tid; t < K * nv; t += NLPF_NT) {
+                const int j = t / nv, a = t - j * nv;
+                double s = 0.0;
+                for (int k = 0; k < K; ++k) s = fma(Dt[k * K + j], slw[k * nv + a], s);
+                const double* Fj = need_F ? (Fs + j * n * nv) : P.Fc;
+                for (int i = 0; i < n; ++i) s = fma(-Fj[i * nv + a], lw[j * n + i], s);
+                g[t] += s;
+            }
+            // state-dependent dynamics part of H
+            if (dyn_h) {
+                const bool hub = (P.loss == NLPF_LOSS_HUBER);
+                for (int p = tid; p < P.np; p += NLPF_NT) {
+                    const uint32_t e = P.tab[p];
+                    const int j = e & 255, a = (e >> 8) & 255, l = (e >> 16) & 255, b = e >> 24;
+                    if (j == 255) continue;                  // global rows carry no dynamics
+                    double s = -Dt[j * K + l] * GF[(j * nv + b) * nv + a] - Dt[l * K + j] * GF[(l * nv + a) * nv + b];
+                    if (j == l) s += FF[(j * nv + a) * nv + b];
+                    if (hub && a == b) {
+                        double s1 = 0.0;
+                        for (int k = 0; k < K; ++k) s1 = fma(Dt[k * K + j] * Dt[k * K + l], whs[k * nv + a], s1);
+                        s += s1;
+                    }
+                    Hp[p] += s;
+                }
+            }
+        }
+    }
+    // arrival cost (nlp.py:279-286) and node cost (nlp.py:160-168): cost here, gradient below
+    if (P.has_prior) {
+        for (int i = tid; i < n; i += NLPF_NT) {
+            const double xp = wp.xprior ? wp.xprior[i] : 0.0;
+            const double d0 = zc[P.cmap[i]] - xp;
+            cost += P.pinv[i] * d0 * d0;
+            nse += 2.0 * P.pinv[i] * fabs(d0) * (fabs(zc[P.cmap[i]]) + fabs(xp));
+        }
+    }
+    if (P.has_nodecost) {
+        for (int t = tid; t < K * nv; t += NLPF_NT) {
+            const int k = t / nv, a = t - k * nv;
+            cost += P.cq[k] * P.snode[a] * zc[t] * zc[t];
+        }
+    }
+    if (FULL) {
+        __syncthreads();
+        if (P.has_prior) {
+            for (int a = tid; a < nv; a += NLPF_NT) {
+                double s = 0.0;
+                for (int i = 0; i < n; ++i)
+                    if (P.cmap[i] == a) s += P.pinv[i] * (zc[a] - (wp.xprior ? wp.xprior[i] : 0.0));
+                g[a] += s;
+            }
+        }
+        if (P.has_nodecost) {
+            __syncthreads();
+            for (int t = tid; t < K * nv; t += NLPF_NT) {
+                const int k = t / nv, a = t - k * nv;
+                g[t] += P.cq[k] * P.snode[a] * zc[t];
+            }
+        }
+    }
+    // ---- phase G: measurement residuals, epoch chunk by epoch chunk ----
+    const double* glob = zc + K * nv;
+    for (int c0 = 0; c0 < P.E; c0 += P.ec) {
+        const int ne = min(P.ec, P.E - c0);
+        __syncthreads();
+        for (int t = tid; t < ne * na; t += NLPF_NT) {
+            const int el = t / na, a = t - el * na;
+            const double* ph = Phi + (c0 + el) * K;
+            const int col = P.act[a];
+            double s = 0.0;
+            for (int j = 0; j < K; ++j) s = fma(ph[j], zc[j * nv + col], s);
+            Ve[t] = s;
+        }
+        if (FULL) {
+            for (int t = tid; t < ne * nat * nat; t += NLPF_NT) G[t] = 0.0;
+            for (int t = tid; t < ne * nat; t += NLPF_NT) q[t] = 0.0;
+        }
+        __syncthreads();
+        for (int el = tid; el < ne; el += NLPF_NT) {
+            const double* xe = Ve + el * na;
+            double* Ge = G + el * nat * nat;
+            double* qe = q + el * nat;
+            const int i1 = P.estart[c0 + el + 1];
+            for (int i = P.estart[c0 + el]; i < i1; ++i) {
+                const double* rec = wp.data + P.roff[i];
+                const double w = rec[1];
+                if (w == 0.0) continue;                   // masked slot: skipped, never 0 * NaN
+                int gl[8];
+                double gv[8];
+                double h;
+                const int nn = meas_eval(P.rtype[i], P.rloc + i * NLPF_NIDX, rec, xe, glob, na, h, gl, gv);
+                const double r = rec[0] - h;
+                cost += w * r * r;
+                nse += 2.0 * w * fabs(r) * (2.0 * fabs(rec[0]) + fabs(r));
+                if (FULL) {
+                    for (int p = 0; p < nn; ++p) {
+                        const double wg = w * gv[p];
+                        qe[gl[p]] = fma(wg, r, qe[gl[p]]);
+                        for (int p2 = 0; p2 < nn; ++p2) Ge[gl[p] * nat + gl[p2]] = fma(wg, gv[p2], Ge[gl[p] * nat + gl[p2]]);
+                    }
+                }
+            }
+        }
+        if (FULL) {
+            __syncthreads();
+            // node-node blocks: H[(j,a),(l,b)] += sum_e phi_ej phi_el G_e[a][b]
+            const int nwork = P.npair * na;
+            for (int wk = tid; wk < nwork; wk += NLPF_NT) {
+                const int pr = wk / na, a = wk - pr * na;
+                const int pe = P.ptab[pr];
+                const int j = pe & 255, l = pe >> 8;
+                double acc[NLPF_NA_MAX];
+#pragma unroll
+                for (int b = 0; b < NLPF_NA_MAX; ++b) acc[b] = 0.0;
+                for (int el = 0; el < ne; ++el) {
+                    const double* ph = Phi + (c0 + el) * K;
+                    const double pp = ph[j] * ph[l];
+                    const double* Ga = G + (el * nat + a) * nat;
+#pragma unroll
+                    for (int b = 0; b < NLPF_NA_MAX; ++b)
+                        if (b < na) acc[b] = fma(pp, Ga[b], acc[b]);
+                }
+                const int r = j * nv + P.act[a];
+#pragma unroll
+                for (int b = 0; b < NLPF_NA_MAX; ++b) {
+                    if (b < na) {
+                        const int c = l * nv + P.act[b];
+                        if (c <= r) Hp[pk(r, c)] += acc[b];
+                    }
+                }
+            }
+            // gradient: g[(j,a)] -= sum_e phi_ej q_e[a]
+            for (int t = tid; t < K * na; t += NLPF_NT) {
+                const int j = t / na, a = t - j * na;
+                double s = 0.0;
+                for (int el = 0; el < ne; ++el) s = fma(Phi[(c0 + el) * K + j], q[el * nat + a], s);
+                g[j * nv + P.act[a]] -= s;
+            }
+            // global unknowns: rows K*nv + gi
+            if (ng > 0) {
+                for (int t = tid; t < ng * K * na; t += NLPF_NT) {
+                    const int gi = t / (K * na);
+                    const int rem = t - gi * K * na;
+                    const int l = rem / na, b = rem - l * na;
+                    double s = 0.0;
+                    for (int el = 0; el < ne; ++el) s = fma(Phi[(c0 + el) * K + l], G[(el * nat + na + gi) * nat + b], s);
+                    Hp[pk(K * nv + gi, l * nv + P.act[b])] += s;
+                }
+                for (int t = tid; t < ng * ng; t += NLPF_NT) {
+                    const int gi = t / ng, gj = t - gi * ng;
+                    if (gj > gi) continue;
+                    double s = 0.0;
+                    for (int el = 0; el < ne; ++el) s += G[(el * nat + na + gi) * nat + na + gj];
+                    Hp[pk(K * nv + gi, K * nv + gj)] += s;
+                }
+                for (int gi = tid; gi < ng; gi += NLPF_NT) {
+                    double s = 0.0;
+                    for (int el = 0; el < ne; ++el) s += q[el * nat + na + gi];
+                    g[K * nv + gi] -= s;
+                }
+            }
+        }
+    }
+    // ---- phase H: log barrier on bounded components ----
+    if (mu > 0.0 && P.nb > 0) {
+        if (FULL) __syncthreads();
+        for (int t = tid; t < K * P.nb; t += NLPF_NT) {
+            const int k = t / P.nb, b = t - k * P.nb;
+            const int idx = k * nv + P.bidx[b];
+            const double v = zc[idx];
+            const double lo = P.blo[b], hi = P.bhi[b];
+            if (lo > -1e300) {
+                const double s = v - lo;
+                if (!(s > 0.0)) bad = true;
+                else {
+                    bar -= mu * log(s);
+                    if (FULL) { g[idx] -= mu / s; Hp[pk(idx, idx)] += mu / (s * s); }
+                }
+            }
+            if (hi < 1e300) {
+                const double s = hi - v;
+                if (!(s > 0.0)) bad = true;
+                else {
+                    bar -= mu * log(s);
+                    if (FULL) { g[idx] += mu / s; Hp[pk(idx, idx)] += mu / (s * s); }
+                }
+            }
+        }
+    }
+    // ---- phase I: reductions ----
+    const double J = block_sum(cost, red);
+    const double B = block_sum(bar, red);
+    const double NS = block_sum(nse, red);
+    const double anybad = block_max(bad ? 1.0 : 0.0, red);
+    double merit = 0.5 * J + B;
+    if (anybad > 0.0 || !isfinite(merit)) merit = INFINITY;
+    J_out = J;
+    merit_out = merit;
+    noise_out = 2.220446049250313e-16 * (0.5 * NS + fabs(merit));
+    __syncthreads();
+}
+
+// ------------------------------------------------------------------------------------------
+// Kernel (3): LDL^T of the packed matrix with the right-hand side appended as row nz.
+// On entry Hp holds the lower triangle of H (+ damping) and row nz holds g.  The elimination
+// leaves the unscaled factor (column j still multiplied by d_j) and, in row nz, L^-1 g; the
+// backward sweep then produces x = H^-1 g in xs.  Returns false when a pivot is not positive.
+// One block barrier per column; no square roots.
+// ------------------------------------------------------------------------------------------
+__device__ bool ldl_solve(int nz, double* Hp, double* xs) {
+    const int tid = threadIdx.x;
+    const int rows = nz + 1;
+    bool ok = true;
+    for (int j = 0; j < nz; ++j) {
+        __syncthreads();
+        const double d = Hp[pk(j, j)];
+        if (!(d > 0.0) || !isfinite(d)) { ok = false; break; }   // uniform: every thread reads the same d
+        const double rd = 1.0 / d;
+        // trailing update of rows i > j (including the appended row), columns j < k <= i
+        const int rem = rows - (j + 1);
+        for (int ii = tid; ii < rem; ii += NLPF_NT) {
+            const int i = j + 1 + ii;
+            double* Hi = Hp + ((i * (i + 1)) >> 1);
+            const double lij = Hi[j] * rd;
+            const int kend = (i < nz) ? i : nz - 1;     // the appended row has no diagonal entry
+            for (int k = j + 1; k <= kend; ++k) {
+                const double hkj = Hp[pk(k, j)];
+                Hi[k] = fma(-lij, hkj, Hi[k]);
+            }
+        }
+    }
+    __syncthreads();
+    if (!ok) return false;
+    // backward sweep by the first warp: u = row nz; x_j = u_j / d_j; u_i -= Hraw[j][i] x_j (i < j)
+    double* u = Hp + ((nz * (nz + 1)) >> 1);
+    if (tid < 32) {
+        for (int j = nz - 1; j >= 0; --j) {
+            const double* Hj = Hp + ((j * (j + 1)) >> 1);
+            const double xj = u[j] / Hj[j];
+            for (int i = tid; i < j; i += 32) u[i] = fma(-Hj[i], xj, u[i]);
+            if (tid == 0) xs[j] = xj;
+            __syncwarp();
+        }
+    }
+    __syncthreads();
+    return true;
+}
+
+// ------------------------------------------------------------------------------------------
+// shared-memory staging common to the kernels
+// ------------------------------------------------------------------------------------------
+__device__ void stage_constants(const DevProb& P, double* sm) {
+    for (int i = threadIdx.x; i < P.E * P.K; i += NLPF_NT) sm[P.o_Phi + i] = P.Phi[i];
+    for (int i = threadIdx.x; i < P.K * P.K; i += NLPF_NT) sm[P.o_Dt + i] = P.Dt[i];
+}
+
+__device__ __forceinline__ WinPtr window_ptrs(const DevProb& P, int b, const double* U, const double* data,
+                                              const double* xprior, const double* wshift) {
+    WinPtr wp;
+    wp.U = (U && P.m > 0) ? U + (size_t)b * P.K * P.m : nullptr;
+    wp.data = data ? data + (size_t)b * P.Ldata : nullptr;
+    wp.xprior = xprior ? xprior + (size_t)b * P.n : nullptr;
+    wp.wshift = wshift ? wshift + (size_t)b * P.K * P.n : nullptr;
+    return wp;
+}
+
+// ------------------------------------------------------------------------------------------
+// nlpf_assemble: evaluation only (tests, ncu)
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(NLPF_NT)
+assemble_kernel(DevProb P, int B, const double* __restrict__ z, const double* __restrict__ U,
+                const double* __restrict__ data, const double* __restrict__ xprior,
+                const double* __restrict__ wshift, double mu, double* __restrict__ H_out,
+                double* __restrict__ g_out, double* __restrict__ cost_out) {
+    extern __shared__ double sm[];
+    stage_constants(P, sm);
+    for (int b = blockIdx.x; b < B; b += gridDim.x) {
+        __syncthreads();
+        double* zs = sm + P.o_z;
+        for (int i = threadIdx.x; i < P.nz; i += NLPF_NT) zs[i] = z[(size_t)b * P.nz + i];
+        __syncthreads();
+        WinPtr wp = window_ptrs(P, b, U, data, xprior, wshift);
+        double J, merit, nse;
+        eval_window<true>(P, sm, zs, wp, mu, J, merit, nse);
+        const int nz = P.nz;
+        double* Ho = H_out + (size_t)b * nz * nz;
+        for (int t = threadIdx.x; t < nz * nz; t += NLPF_NT) {
+            const int r = t / nz, c = t - r * nz;
+            Ho[t] = (c <= r) ? sm[P.o_H + pk(r, c)] : sm[P.o_H + pk(c, r)];
+        }
+        for (int i = threadIdx.x; i < nz; i += NLPF_NT) g_out[(size_t)b * nz + i] = sm[P.o_g + i];
+        if (threadIdx.x == 0) {
+            cost_out[2 * b] = J;
+            cost_out[2 * b + 1] = merit;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// nlpf_factor_solve: kernel (3) alone
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(NLPF_NT)
+factor_solve_kernel(DevProb P, int B, const double* __restrict__ H, const double* __restrict__ g, double lam,
+                    double* __restrict__ dz_out, int* __restrict__ info_out) {
+    extern __shared__ double sm[];
+    const int nz = P.nz;
+    double* Hp = sm + P.o_H;
+    double* red = sm + P.o_red;
+    for (int b = blockIdx.x; b < B; b += gridDim.x) {
+        __syncthreads();
+        const double* Hb = H + (size_t)b * nz * nz;
+        double dmax = 0.0;
+        for (int t = threadIdx.x; t < nz * nz; t += NLPF_NT) {
+            const int r = t / nz, c = t - r * nz;
+            if (c <= r) Hp[pk(r, c)] = Hb[t];
+            if (c == r) dmax = fmax(dmax, Hb[t]);
+        }
+        dmax = block_max(dmax, red);
+        for (int i = threadIdx.x; i < nz; i += NLPF_NT) {
+            Hp[pk(i, i)] += lam * (Hp[pk(i, i)] + 1e-14 * dmax);
+            Hp[pk(nz, i)] = g[(size_t)b * nz + i];
+        }
+        const bool ok = ldl_solve(nz, Hp, sm + P.o_dz);
+        for (int i = threadIdx.x; i < nz; i += NLPF_NT) dz_out[(size_t)b * nz + i] = ok ? -sm[P.o_dz + i] : 0.0;
+        if (threadIdx.x == 0) info_out[b] = ok ? 0 : 1;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// nlpf_solve: the whole damped Gauss-Newton / log-barrier iteration of one window per CTA.
+// Same decisions, in the same order, as oracle/nls.py:solve (the CPU checker).
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(NLPF_NT)
+solve_kernel(DevProb P, int B, double* __restrict__ z_io, const double* __restrict__ U,
+             const double* __restrict__ data, const double* __restrict__ xprior,
+             const double* __restrict__ wshift, nlpf_opts opt, double* __restrict__ cost_out,
+             int* __restrict__ iters_out, int* __restrict__ status_out) {
+    extern __shared__ double sm[];
+    const int tid = threadIdx.x;
+    const int nz = P.nz, K = P.K, nv = P.nv;
+    double* Hp = sm + P.o_H;
+    double* zs = sm + P.o_z;
+    double* zt = sm + P.o_zt;
+    double* g = sm + P.o_g;
+    double* ds = sm + P.o_ds;
+    double* dz = sm + P.o_dz;
+    double* red = sm + P.o_red;
+    stage_constants(P, sm);
+    const bool bounded = P.nb > 0;
+
+    for (int b = blockIdx.x; b < B; b += gridDim.x) {
+        __syncthreads();
+        for (int i = tid; i < nz; i += NLPF_NT) zs[i] = z_io[(size_t)b * nz + i];
+        __syncthreads();
+        if (bounded) {   // start strictly inside the bounds (IPOPT bound_push)
+            for (int t = tid; t < K * P.nb; t += NLPF_NT) {
+                const int k = t / P.nb, bb = t - k * P.nb;
+                const int idx = k * nv + P.bidx[bb];
+                double v = zs[idx];
+                if (P.blo[bb] > -1e300) v = fmax(v, P.blo[bb] + opt.bound_push);
+                if (P.bhi[bb] < 1e300) v = fmin(v, P.bhi[bb] - opt.bound_push);
+                zs[idx] = v;
+            }
+            __syncthreads();
+        }
+        WinPtr wp = window_ptrs(P, b, U, data, xprior, wshift);
+        double mu = bounded ? opt.mu0 : 0.0;
+        int iters = 0;
+        int status = NLPF_ST_MAXITER;
+        double lam = opt.lam0;
+        double J, merit, nse0;
+        eval_window<true>(P, sm, zs, wp, mu, J, merit, nse0);
+        if (!isfinite(merit)) {
+            status = NLPF_ST_NUMERIC;
+        } else {
+            while (true) {   // barrier stages
+                lam = opt.lam0;
+                int stage_steps = 0, floor_steps = 0;
+                status = NLPF_ST_MAXITER;
+                while (iters < opt.max_iter && stage_steps < opt.max_stage_iter) {
+                    // ||g||_inf and the damping diagonal
+                    double gm = 0.0, dm = 0.0;
+                    for (int i = tid; i < nz; i += NLPF_NT) {
+                        gm = fmax(gm, fabs(g[i]));
+                        const double d = Hp[pk(i, i)];
+                        ds[i] = d;
+                        dm = fmax(dm, d);
+                    }
+                    gm = block_max(gm, red);
+                    dm = block_max(dm, red);
+                    if (mu > opt.mu_min && stage_steps >= 1 && gm < 10.0 * mu) {
+                        status = NLPF_ST_CONVERGED;
+                        break;
+                    }
+                    bool accepted = false, at_floor = false;
+                    bool h_valid = true;      // Hp still holds H(z)
+                    double alpha = 1.0, Jt = J, mt = merit, dzmax = 0.0, nset = 0.0;
+                    while (lam <= 1e18) {
+                        if (!h_valid) {       // the factorisation overwrote H: rebuild it at z
+                            double Jd, md, nd;
+                            eval_window<true>(P, sm, zs, wp, mu, Jd, md, nd);
+                            h_valid = true;
+                        }
+                        for (int i = tid; i < nz; i += NLPF_NT) {
+                            Hp[pk(i, i)] = ds[i] + lam * (ds[i] + 1e-14 * dm);
+                            Hp[pk(nz, i)] = g[i];
+                        }
+                        h_valid = false;
+                        const bool ok = ldl_solve(nz, Hp, dz);
+                        if (ok) {
+                            // dz holds H^-1 g: the step is -dz.  fraction to the boundary:
+                            double a = 1.0, dmx = 0.0, finite = 0.0;
+                            for (int i = tid; i < nz; i += NLPF_NT) {
+                                dmx = fmax(dmx, fabs(dz[i]));
+                                if (!isfinite(dz[i])) finite = 1.0;
+                            }
+                            if (bounded) {
+                                for (int t = tid; t < K * P.nb; t += NLPF_NT) {
+                                    const int k = t / P.nb, bb = t - k * P.nb;
+                                    const int idx = k * nv + P.bidx[bb];
+                                    const double st = -dz[idx];
+                                    if (st < 0.0 && P.blo[bb] > -1e300) a = fmin(a, opt.tau_ftb * (zs[idx] - P.blo[bb]) / (-st));
+                                    if (st > 0.0 && P.bhi[bb] < 1e300) a = fmin(a, opt.tau_ftb * (P.bhi[bb] - zs[idx]) / st);
+                                }
+                                a = block_min(a, red);
+                            }
+                            dmx = block_max(dmx, red);
+                            finite = block_max(finite, red);
+                            if (finite == 0.0) {
+                                double pred = 0.0;
+                                for (int i = tid; i < nz; i += NLPF_NT) {
+                                    zt[i] = fma(-a, dz[i], zs[i]);
+                                    pred = fma(g[i], dz[i], pred);
+                                }
+                                pred = a * block_sum(pred, red);     // predicted decrease scale g^T H^-1 g
+                                __syncthreads();
+                                eval_window<false>(P, sm, zt, wp, mu, Jt, mt, nset);
+                                if (isfinite(mt) && mt < merit) {
+                                    accepted = true;
+                                    alpha = a;
+                                    dzmax = dmx;
+                                    break;
+                                }
+                                // rounding floor of the merit: no measurable decrease is predicted
+                                // (the Gauss-Newton step is still accurate because g is): take it, count it
+                                const double nb = nse0 + nset;
+                                if (isfinite(mt) && (mt - merit) <= nb && pred <= 4.0 * nb) {
+                                    at_floor = true;
+                                    accepted = true;
+                                    alpha = a;
+                                    dzmax = dmx;
+                                    break;
+                                }
+                            }
+                        }
+                        lam *= 10.0;
+                    }
+                    if (!accepted) {
+                        status = NLPF_ST_STALLED;
+                        if (!h_valid) {   // leave H, g consistent with z for a following stage
+                            double Jd, md, nd;
+                            eval_window<true>(P, sm, zs, wp, mu, Jd, md, nd);
+                        }
+                        break;
+                    }
+                    const double step = alpha * dzmax;
+                    double zm = 0.0;
+                    for (int i = tid; i < nz; i += NLPF_NT) {
+                        zs[i] = zt[i];
+                        zm = fmax(zm, fabs(zt[i]));
+                    }
+                    zm = block_max(zm, red);
+                    lam = fmax(lam / 10.0, 1e-12);
+                    ++iters;
+                    ++stage_steps;
+                    eval_window<true>(P, sm, zs, wp, mu, J, merit, nse0);
+                    if (step < opt.tol_step * (1.0 + zm)) {
+                        status = NLPF_ST_CONVERGED;
+                        break;
+                    }
+                    if (at_floor && ++floor_steps >= 5) {
+                        status = NLPF_ST_CONVERGED;
+                        break;
+                    }
+                }
+                if (!bounded || mu <= opt.mu_min || iters >= opt.max_iter) break;
+                mu = fmax(opt.mu_min, fmin(0.2 * mu, mu * sqrt(mu)));
+                eval_window<true>(P, sm, zs, wp, mu, J, merit, nse0);
+            }
+        }
+        for (int i = tid; i < nz; i += NLPF_NT) z_io[(size_t)b * nz + i] = zs[i];
+        if (tid == 0) {
+            cost_out[b] = J;
+            iters_out[b] = iters;
+            status_out[b] = status;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// nlpf_sample: x(t) = Phi(t) X, nlp.py:99-119
+// ------------------------------------------------------------------------------------------
+__global__ void sample_kernel(DevProb P, int B, const double* __restrict__ z, int nt,
+                              const double* __restrict__ PhiT, double* __restrict__ out) {
+    const size_t total = (size_t)B * nt * P.n;
+    for (size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
+        const int i = t % P.n;
+        const int it = (t / P.n) % nt;
+        const int b = t / ((size_t)P.n * nt);
+        const double* zb = z + (size_t)b * P.nz;
+        const int col = P.cmap[i];
+        double s = 0.0;
+        for (int j = 0; j < P.K; ++j) s = fma(PhiT[it * P.K + j], zb[j * P.nv + col], s);
+        out[t] = s;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// launchers (called from capi.cu)
+// ------------------------------------------------------------------------------------------
+static int grid_for(int B) { return B < 1 ? 1 : B; }
+
+extern "C" int nlpf_launch_assemble(nlpf_problem* p, int B, const double* z, const double* U, const double* data,
+                                    const double* xprior, const double* wshift, double mu, double* H_out,
+                                    double* g_out, double* cost_out, cudaStream_t st) {
+    assemble_kernel<<<grid_for(B), NLPF_NT, p->smem_bytes, st>>>(p->d, B, z, U, data, xprior, wshift, mu, H_out, g_out, cost_out);
+    return nlpf_check_cuda(cudaGetLastError(), "assemble_kernel launch");
+}
+
+extern "C" int nlpf_launch_factor_solve(nlpf_problem* p, int B, const double* H, const double* g, double lam,
+                                        double* dz_out, int* info_out, cudaStream_t st) {
+    factor_solve_kernel<<<grid_for(B), NLPF_NT, p->smem_bytes, st>>>(p->d, B, H, g, lam, dz_out, info_out);
+    return nlpf_check_cuda(cudaGetLastError(), "factor_solve_kernel launch");
+}
+
+extern "C" int nlpf_launch_solve(nlpf_problem* p, int B, double* z, const double* U, const double* data,
+                                 const double* xprior, const double* wshift, const nlpf_opts* o, double* cost_out,
+                                 int* iters_out, int* status_out, cudaStream_t st) {
+    solve_kernel<<<grid_for(B), NLPF_NT, p->smem_bytes, st>>>(p->d, B, z, U, data, xprior, wshift, *o, cost_out, iters_out, status_out);
+    return nlpf_check_cuda(cudaGetLastError(), "solve_kernel launch");
+}
+
+extern "C" int nlpf_launch_sample(nlpf_problem* p, int B, const double* z, int nt, const double* PhiT, double* out,
+                                  cudaStream_t st) {
+    const size_t total = (size_t)B * nt * p->d.n;
+    int blocks = (int)((total + 255) / 256);
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    if (blocks < 1) blocks = 1;
+    sample_kernel<<<blocks, 256, 0, st>>>(p->d, B, z, nt, PhiT, out);
+    return nlpf_check_cuda(cudaGetLastError(), "sample_kernel launch");
+}
+
+extern "C" int nlpf_set_smem_attrs(size_t bytes) {
+    cudaError_t e;
+    e = cudaFuncSetAttribute(assemble_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e != cudaSuccess) return nlpf_check_cuda(e, "smem attr assemble");
+    e = cudaFuncSetAttribute(factor_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e != cudaSuccess) return nlpf_check_cuda(e, "smem attr factor");
+    e = cudaFuncSetAttribute(solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e != cudaSuccess) return nlpf_check_cuda(e, "smem attr solve");
+    return 0;
+}

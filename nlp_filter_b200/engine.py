@@ -1,0 +1,254 @@
+"""Batched device entry points above the C ABI.
+
+`WindowProblem` wraps one `nlpf_problem` handle (a problem class); its methods take fp64 CUDA
+tensors (torch is used for device memory and streams only) and hand raw pointers to
+libnlpfilter.so.  `solve_windows_host` is the public end-to-end call for a batch of windows
+held in host (NumPy) buffers: pinned staging -> H2D -> whole-solve kernel -> D2H.
+
+Additions to the reference API, never changes: the reference solves one window per
+`NLP.solve()` call (nlp/nlp.py:76-83); these calls solve B independent windows of the same
+problem class at once.
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _capi
+from .desc import SolveOpts
+
+
+def _require_cuda():
+    if not torch.cuda.is_available():
+        raise _capi.NlpfError("no CUDA device: the estimator hot path has no CPU fallback")
+
+
+def _ptr(t):
+    if t is None:
+        return None
+    assert t.is_cuda and t.is_contiguous(), "device buffers must be contiguous CUDA tensors"
+    return ctypes.c_void_p(t.data_ptr())
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _f8(t, shape=None):
+    if t is None:
+        return None
+    if not (isinstance(t, torch.Tensor) and t.is_cuda):
+        t = torch.as_tensor(np.ascontiguousarray(t, dtype=np.float64)).cuda()
+    t = t.to(torch.float64).contiguous()
+    if shape is not None:
+        t = t.reshape(shape)
+    return t
+
+
+class WindowProblem(object):
+    """One problem class on the current CUDA device."""
+
+    def __init__(self, desc):
+        _require_cuda()
+        self.desc = desc.finalize()
+        self._lib = _capi.lib()
+        cdesc, keep = _capi.make_cdesc(desc)
+        h = ctypes.c_void_p()
+        _capi.check(self._lib.nlpf_problem_create(ctypes.byref(cdesc), ctypes.byref(h)))
+        self._h = h
+        self.nz = desc.nz
+        self.smem_bytes = int(self._lib.nlpf_problem_smem_bytes(h))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.nlpf_problem_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- kernels (1)+(2) ---------------------------------------------------------------------
+    def assemble(self, z, U=None, data=None, xprior=None, wshift=None, mu=0.0):
+        d = self.desc
+        z = _f8(z, (-1, d.nz))
+        B = z.shape[0]
+        U, data, xprior, wshift = _f8(U), _f8(data), _f8(xprior), _f8(wshift)
+        H = torch.empty((B, d.nz, d.nz), dtype=torch.float64, device=z.device)
+        g = torch.empty((B, d.nz), dtype=torch.float64, device=z.device)
+        cost = torch.empty((B, 2), dtype=torch.float64, device=z.device)
+        _capi.check(self._lib.nlpf_assemble(self._h, B, _ptr(z), _ptr(U), _ptr(data), _ptr(xprior), _ptr(wshift),
+                                            float(mu), _ptr(H), _ptr(g), _ptr(cost), _stream()))
+        return H, g, cost
+
+    # -- kernel (3) --------------------------------------------------------------------------
+    def factor_solve(self, H, g, lam=0.0):
+        d = self.desc
+        H = _f8(H, (-1, d.nz, d.nz))
+        g = _f8(g, (-1, d.nz))
+        B = H.shape[0]
+        dz = torch.empty((B, d.nz), dtype=torch.float64, device=H.device)
+        info = torch.empty((B,), dtype=torch.int32, device=H.device)
+        _capi.check(self._lib.nlpf_factor_solve(self._h, B, _ptr(H), _ptr(g), float(lam), _ptr(dz), _ptr(info), _stream()))
+        return dz, info
+
+    # -- whole solve -------------------------------------------------------------------------
+    def solve(self, z, U=None, data=None, xprior=None, wshift=None, opts=None, out=None):
+        """z (B, nz) CUDA tensor: initial guess in, minimiser out (in place).
+        Returns (z, cost, iters, status) device tensors; nothing is synchronised."""
+        d = self.desc
+        assert z.is_cuda and z.dtype == torch.float64 and z.is_contiguous()
+        B = z.shape[0]
+        copts = _capi.make_copts(opts or SolveOpts())
+        if out is None:
+            cost = torch.empty((B,), dtype=torch.float64, device=z.device)
+            iters = torch.empty((B,), dtype=torch.int32, device=z.device)
+            status = torch.empty((B,), dtype=torch.int32, device=z.device)
+        else:
+            cost, iters, status = out
+        _capi.check(self._lib.nlpf_solve(self._h, B, _ptr(z), _ptr(U), _ptr(data), _ptr(xprior), _ptr(wshift),
+                                         ctypes.byref(copts), _ptr(cost), _ptr(iters), _ptr(status), _stream()))
+        return z, cost, iters, status
+
+    def sample(self, z, PhiT):
+        d = self.desc
+        z = _f8(z, (-1, d.nz))
+        PhiT = _f8(PhiT, (-1, d.K))
+        B, nt = z.shape[0], PhiT.shape[0]
+        out = torch.empty((B, nt, d.n), dtype=torch.float64, device=z.device)
+        _capi.check(self._lib.nlpf_sample(self._h, B, _ptr(z), nt, _ptr(PhiT), _ptr(out), _stream()))
+        return out
+
+
+class HostBatch(object):
+    """Pinned host staging + device buffers for repeated end-to-end solves of B windows."""
+
+    def __init__(self, prob, B):
+        d = prob.desc
+        self.prob, self.B = prob, B
+        mk = lambda *s: torch.empty(s, dtype=torch.float64).pin_memory()
+        self.h_z = mk(B, d.nz)
+        self.h_U = mk(B, d.K, max(d.m, 1)) if d.m > 0 else None
+        self.h_data = mk(B, max(d.Ldata, 1))
+        self.h_xp = mk(B, d.n) if d.has_prior else None
+        dev = lambda t: torch.empty_like(t, device="cuda") if t is not None else None
+        self.d_z, self.d_U, self.d_data, self.d_xp = dev(self.h_z), dev(self.h_U), dev(self.h_data), dev(self.h_xp)
+        self.d_cost = torch.empty((B,), dtype=torch.float64, device="cuda")
+        self.d_iters = torch.empty((B,), dtype=torch.int32, device="cuda")
+        self.d_status = torch.empty((B,), dtype=torch.int32, device="cuda")
+        self.h_out = mk(B, d.nz)
+        self.h_cost = mk(B)
+        self.h_iters = torch.empty((B,), dtype=torch.int32).pin_memory()
+        self.h_status = torch.empty((B,), dtype=torch.int32).pin_memory()
+        self.h2d_bytes = sum(t.numel() * t.element_size() for t in (self.h_z, self.h_U, self.h_data, self.h_xp) if t is not None)
+        self.d2h_bytes = sum(t.numel() * t.element_size() for t in (self.h_out, self.h_cost, self.h_iters, self.h_status))
+
+    def load(self, z0, U=None, data=None, xprior=None):
+        self.h_z.copy_(torch.as_tensor(np.asarray(z0, dtype=np.float64).reshape(self.h_z.shape)))
+        if self.h_U is not None:
+            self.h_U.copy_(torch.as_tensor(np.asarray(U, dtype=np.float64).reshape(self.h_U.shape)))
+        if data is not None:
+            self.h_data.copy_(torch.as_tensor(np.asarray(data, dtype=np.float64).reshape(self.h_data.shape)))
+        if self.h_xp is not None:
+            self.h_xp.copy_(torch.as_tensor(np.asarray(xprior, dtype=np.float64).reshape(self.h_xp.shape)))
+
+    def run(self, opts=None):
+        """H2D of the staged inputs, solve, D2H of the estimates.  Asynchronous on the current
+        stream; call torch.cuda.synchronize() (or read after an event) before using h_out."""
+        self.d_z.copy_(self.h_z, non_blocking=True)
+        if self.h_U is not None:
+            self.d_U.copy_(self.h_U, non_blocking=True)
+        self.d_data.copy_(self.h_data, non_blocking=True)
+        if self.h_xp is not None:
+            self.d_xp.copy_(self.h_xp, non_blocking=True)
+        self.prob.solve(self.d_z, self.d_U, self.d_data, self.d_xp, None, opts,
+                        out=(self.d_cost, self.d_iters, self.d_status))
+        self.h_out.copy_(self.d_z, non_blocking=True)
+        self.h_cost.copy_(self.d_cost, non_blocking=True)
+        self.h_iters.copy_(self.d_iters, non_blocking=True)
+        self.h_status.copy_(self.d_status, non_blocking=True)
+
+
+def solve_windows_host(prob, z0, U=None, data=None, xprior=None, opts=None):
+    """Solve B windows held in NumPy arrays; returns (z, J, iters, status) as NumPy arrays."""
+    z0 = np.asarray(z0, dtype=np.float64).reshape(-1, prob.desc.nz)
+    hb = HostBatch(prob, z0.shape[0])
+    hb.load(z0, U, data, xprior)
+    hb.run(opts)
+    torch.cuda.synchronize()
+    return hb.h_out.numpy().copy(), hb.h_cost.numpy().copy(), hb.h_iters.numpy().copy(), hb.h_status.numpy().copy()
+
+
+# ---------------------------------------------------------------------------------------------
+# EKF and least squares
+# ---------------------------------------------------------------------------------------------
+EKF_GNSS5 = 0
+EKF_CAR9 = 1
+
+
+def ekf_run(model, mu, S, u, z, sat, nsat, Q, r, dt, par=None, want_traj=True):
+    """`steps` fused predict/update steps of B filters (utils/ekf.py:20-61).
+    mu (B,n), S (B,n,n), u (B,steps,m), z (B,steps,smax), sat (B,steps,smax,3), nsat (B,steps) int32,
+    Q (n,) diagonal.  mu and S are updated in place (device tensors); returns the mean trajectory."""
+    _require_cuda()
+    L = _capi.lib()
+    mu, S = _f8(mu), _f8(S)
+    B, n = mu.shape
+    u, z, sat = _f8(u), _f8(z), _f8(sat)
+    steps, smax = z.shape[1], z.shape[2]
+    nsat = torch.as_tensor(nsat).to(device=mu.device, dtype=torch.int32).contiguous()
+    Q = _f8(Q)
+    par_t = _f8(np.concatenate([np.asarray(par, float), np.zeros(16 - len(par))])) if par is not None else None
+    traj = torch.empty((B, steps, n), dtype=torch.float64, device=mu.device) if want_traj else None
+    _capi.check(L.nlpf_ekf_run(int(model), B, steps, smax, _ptr(mu), _ptr(S), _ptr(u), _ptr(z), _ptr(sat), _ptr(nsat),
+                               _ptr(Q), float(r), float(dt), _ptr(par_t), _ptr(traj), _stream()))
+    return mu, S, traj
+
+
+def ls_solve(sat, pr, nsat, x0=None, tcol=None, maxiter=100, tol=1e-7):
+    """Iterative GNSS least squares of B epochs (utils/leastsquares.py:19-42, 66-94).
+    sat (B,smax,3), pr (B,smax), nsat (B,) -> x (B, 4|5) = [x,y,z,b(,alpha)], iters (B,)."""
+    _require_cuda()
+    L = _capi.lib()
+    sat, pr = _f8(sat), _f8(pr)
+    B, smax = pr.shape
+    nsat = torch.as_tensor(nsat).to(device=sat.device, dtype=torch.int32).contiguous()
+    nu = 5 if tcol is not None else 4
+    x = torch.zeros((B, nu), dtype=torch.float64, device=sat.device) if x0 is None else _f8(x0, (B, nu)).clone()
+    tc = _f8(tcol) if tcol is not None else None
+    iters = torch.empty((B,), dtype=torch.int32, device=sat.device)
+    _capi.check(L.nlpf_ls_solve(B, smax, _ptr(sat), _ptr(pr), _ptr(nsat), _ptr(tc), _ptr(x), int(maxiter), float(tol),
+                                _ptr(iters), _stream()))
+    return x, iters
+
+
+def ls_vel(sat, satvel, prr, nsat, xpos):
+    """One-shot velocity / clock-drift solve (utils/leastsquares.py:45-63) -> (B,4) = [v, bdot]."""
+    _require_cuda()
+    L = _capi.lib()
+    sat, satvel, prr, xpos = _f8(sat), _f8(satvel), _f8(prr), _f8(xpos)
+    B, smax = prr.shape
+    nsat = torch.as_tensor(nsat).to(device=sat.device, dtype=torch.int32).contiguous()
+    out = torch.empty((B, 4), dtype=torch.float64, device=sat.device)
+    _capi.check(L.nlpf_ls_vel(B, smax, _ptr(sat), _ptr(satvel), _ptr(prr), _ptr(nsat), _ptr(xpos), _ptr(out), _stream()))
+    return out
+
+
+def fp64_peak_tflops(iters=20000, reps=5):
+    """Measured FP64 FMA throughput of the current device (roofline denominator)."""
+    _require_cuda()
+    L = _capi.lib()
+    sink = torch.zeros(4, dtype=torch.float64, device="cuda")
+    flops = ctypes.c_double()
+    best = 0.0
+    for i in range(reps + 2):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        _capi.check(L.nlpf_fp64_probe(int(iters), _ptr(sink), ctypes.byref(flops), _stream()))
+        e1.record()
+        torch.cuda.synchronize()
+        if i >= 2:
+            best = max(best, flops.value / (e0.elapsed_time(e1) * 1e-3) / 1e12)
+    return best

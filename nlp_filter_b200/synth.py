@@ -1,0 +1,100 @@
+"""Seeded synthetic batches of the benchmark shapes: per-window input
+buffers in exactly the layout the C ABI takes (z0, U, data, xprior as (B, ...) float64).
+
+  vdp_mhe_batch   Van der Pol MHE windows: RK4 truth, noisy full-state measurements at 50 epochs
+                  (estimation_example.py:10-45 pattern with dynamics.van_der_pol).
+  gnss_batch      stationary-receiver pseudorange windows, 51 epochs x 12 satellites, ENU frame
+                  (gnss_stationary.py:100-128).
+Everything is NumPy on the host; no device code here.
+"""
+import numpy as np
+
+from . import desc as D
+
+
+def _interp_rows(t_src, y_src, t_dst):
+    """Linear interpolation with linear extrapolation of (B, T) rows -> (B, len(t_dst))
+    (what scipy interp1d(fill_value='extrapolate') does in nlp.py:297,306)."""
+    t_src = np.asarray(t_src, float)
+    idx = np.clip(np.searchsorted(t_src, t_dst, side="right") - 1, 0, len(t_src) - 2)
+    t0, t1 = t_src[idx], t_src[idx + 1]
+    w = (t_dst - t0) / (t1 - t0)
+    return y_src[..., idx] * (1 - w) + y_src[..., idx + 1] * w
+
+
+def vdp_rhs(x0, x1, u):
+    return (1 - x1 ** 2) * x0 - x1 + u, x0        # nlp/dynamics.py:61-66
+
+
+def vdp_mhe_batch(desc, B, seed=2000):
+    rng = np.random.default_rng(seed)
+    T = desc.T
+    epochs = desc.epochs
+    x0 = np.stack([rng.normal(0.0, 0.25, B), rng.normal(1.0, 0.25, B)], 1)
+    phase = rng.uniform(0, 2 * np.pi, B)
+    ufun = lambda t: 0.5 * np.sin(t + phase)
+    dt = 0.01
+    nstep = int(round(T / dt))
+    xs = np.zeros((B, 2, nstep + 1))
+    xs[:, :, 0] = x0
+    a, b = x0[:, 0].copy(), x0[:, 1].copy()
+    for i in range(nstep):
+        t = i * dt
+        k1 = vdp_rhs(a, b, ufun(t))
+        k2 = vdp_rhs(a + 0.5 * dt * k1[0], b + 0.5 * dt * k1[1], ufun(t + 0.5 * dt))
+        k3 = vdp_rhs(a + 0.5 * dt * k2[0], b + 0.5 * dt * k2[1], ufun(t + 0.5 * dt))
+        k4 = vdp_rhs(a + dt * k3[0], b + dt * k3[1], ufun(t + dt))
+        a = a + dt / 6 * (k1[0] + 2 * k2[0] + 2 * k3[0] + k4[0])
+        b = b + dt / 6 * (k1[1] + 2 * k2[1] + 2 * k3[1] + k4[1])
+        xs[:, 0, i + 1], xs[:, 1, i + 1] = a, b
+    tt = np.arange(nstep + 1) * dt
+    truth = np.stack([_interp_rows(tt, xs[:, 0, :], epochs), _interp_rows(tt, xs[:, 1, :], epochs)], 1)  # B,2,E
+    rvar = 1.0 / desc.r_inv
+    y = truth + rng.normal(size=truth.shape) * np.sqrt(rvar)[None, :, None]
+    data = np.zeros((B, desc.Ldata))
+    for e in range(desc.E):
+        for i in range(2):
+            o = desc.roff[e * 2 + i]
+            data[:, o] = y[:, i, e]
+            data[:, o + 1] = desc.r_inv[i]
+    tn = desc.cpm.tau2t(desc.cpm.tau)
+    u_epochs = 0.5 * np.sin(epochs[None, :] + phase[:, None])
+    U = _interp_rows(epochs, u_epochs, tn)[:, :, None]                      # B,K,1
+    z0 = np.stack([_interp_rows(epochs, y[:, 0, :], tn), _interp_rows(epochs, y[:, 1, :], tn)], 2).reshape(B, -1)
+    return dict(z0=z0, U=np.ascontiguousarray(U), data=data, xprior=None, truth=truth, y=y)
+
+
+def gnss_batch(desc, B, seed=3000, n_sat=12, r_pr=100.0):
+    rng = np.random.default_rng(seed)
+    E, K = desc.E, desc.K
+    epochs = desc.epochs
+    pos = rng.normal(0.0, 5.0, (B, 3))
+    b0 = rng.uniform(-1e3, 1e3, B)
+    alpha = rng.normal(-190.0, 20.0, B)
+    # satellites on a shell above 10 deg elevation, slow linear motion
+    el = np.arcsin(rng.uniform(np.sin(np.deg2rad(10)), 1.0, (B, n_sat)))
+    az = rng.uniform(0, 2 * np.pi, (B, n_sat))
+    rad = rng.uniform(2.0e7, 2.6e7, (B, n_sat))
+    s0 = np.stack([rad * np.cos(el) * np.sin(az), rad * np.cos(el) * np.cos(az), rad * np.sin(el)], 2)  # B,S,3
+    sv = rng.normal(0.0, 1.5e3, (B, n_sat, 3))
+    sat = s0[:, None, :, :] + sv[:, None, :, :] * epochs[None, :, None, None]                           # B,E,S,3
+    rho = np.sqrt(np.sum((pos[:, None, None, :] - sat) ** 2, -1))
+    bias = b0[:, None] + alpha[:, None] * epochs[None, :]
+    pr = rho + bias[:, :, None] + rng.normal(0.0, np.sqrt(r_pr), rho.shape)
+    data = np.zeros((B, desc.Ldata))
+    off = desc.roff.reshape(E, n_sat)
+    for e in range(E):
+        for j in range(n_sat):
+            o = off[e, j]
+            data[:, o] = pr[:, e, j]
+            data[:, o + 1] = 1.0 / r_pr
+            data[:, o + 2:o + 5] = sat[:, e, j, :]
+    tn = desc.cpm.tau2t(desc.cpm.tau)
+    # initial guess: origin, clock bias/drift from the mean pseudorange misfit at the origin
+    mis = np.mean(pr - np.sqrt(np.sum(sat ** 2, -1)), 2)                      # B,E
+    a_g = (mis[:, -1] - mis[:, 0]) / (epochs[-1] - epochs[0])
+    z0 = np.zeros((B, K, 5))
+    z0[:, :, 3] = mis[:, :1] + a_g[:, None] * tn[None, :]
+    z0[:, :, 4] = a_g[:, None]
+    U = np.zeros((B, K, 3))
+    return dict(z0=z0.reshape(B, -1), U=U, data=data, xprior=None, pos=pos, b0=b0, alpha=alpha)

@@ -191,17 +191,25 @@ def meas_residuals(desc, z, win, jac=True):
 
 
 def _huber(W, qinv, delta):
-    """pseudo_huber_loss, cost_functions.py:25-31: value, half gradient, half curvature."""
+    """pseudo_huber_loss, cost_functions.py:25-31: value, half gradient, and the Gauss-Newton
+    curvature weight of the residual sqrt(loss)*sign(W), i.e. (d sqrt(loss)/dW)^2 =
+    q (s+1) / (2 s^2)  (equals q at W = 0, decays like q/(2s) for outliers)."""
     s = np.sqrt(1.0 + (W / delta) ** 2)
     val = 2.0 * qinv * delta ** 2 * (s - 1.0)
-    return val, qinv * W / s, qinv / s ** 3
+    return val, qinv * W / s, qinv * (s + 1.0) / (2.0 * s * s)
 
 
-def evaluate(desc, win, z, mu=0.0, want_grad=True):
+EPS = 2.220446049250313e-16
+
+
+def evaluate(desc, win, z, mu=0.0, want_grad=True, with_noise=False):
     """Objective J (reference definition), merit = J/2 + barrier, and -- when want_grad --
-    g = grad(merit), H = Gauss-Newton approximation of hess(merit)."""
+    g = grad(merit), H = Gauss-Newton approximation of hess(merit).  with_noise appends a
+    first-order bound on the rounding error of the merit (pseudoranges of 2e7 m minus predicted
+    ranges lose ~9 digits, so the merit cannot resolve millimetre steps; the gradient can)."""
     K, n, nv, nz = desc.K, desc.n, desc.nv, desc.nz
     J = 0.0
+    noise = 0.0
     g = np.zeros(nz)
     H = np.zeros((nz, nz))
     V = z[:K * nv].reshape(K, nv)
@@ -209,21 +217,28 @@ def evaluate(desc, win, z, mu=0.0, want_grad=True):
     if np.any(desc.qinv != 0.0):
         W, JW = defects(desc, z, win)
         cwq = desc.cw[:, None] * np.ones((1, n))
+        Vn, Xn, Un = _node_quantities(desc, z, win)
+        mag = np.abs(desc.Dt) @ np.abs(Xn) + np.abs(desc.Dt @ Xn - W - win.wshift)      # sum|D x| + |f|
         if desc.loss == D.LOSS_HUBER:
             val, hg, hh = _huber(W, desc.qinv[None, :], desc.delta)
             J += float(np.sum(cwq * val))
             wg = (cwq * hg).reshape(-1)
             wh = (cwq * hh).reshape(-1)
+            noise += float(np.sum(2.0 * np.abs(cwq * hg) * mag)) * EPS
         else:
             J += float(np.sum(cwq * desc.qinv[None, :] * W * W))
             wh = (cwq * desc.qinv[None, :]).reshape(-1)
             wg = wh * W.reshape(-1)
+            noise += float(np.sum(2.0 * np.abs(cwq * desc.qinv[None, :] * W) * mag)) * EPS
         if want_grad:
             g += JW.T @ wg
             H += JW.T @ (wh[:, None] * JW)
     # measurement residual cost
     r, w, Jr = meas_residuals(desc, z, win, jac=want_grad)
     J += float(np.sum(w * r * r))
+    if desc.M > 0:
+        yy = win.data[desc.roff]
+        noise += float(np.sum(2.0 * w * np.abs(r) * (2.0 * np.abs(yy) + np.abs(r)))) * EPS   # |y| + |h| <= 2|y| + |r|
     if want_grad and desc.M > 0:
         g += Jr.T @ (w * r)
         H += Jr.T @ (w[:, None] * Jr)
@@ -231,6 +246,7 @@ def evaluate(desc, win, z, mu=0.0, want_grad=True):
     if desc.has_prior:
         d0 = V[0, desc.cmap] - win.xprior
         J += float(np.sum(desc.pinv * d0 * d0))
+        noise += float(np.sum(2.0 * desc.pinv * np.abs(d0) * (np.abs(V[0, desc.cmap]) + np.abs(win.xprior)))) * EPS
         if want_grad:
             for i in range(n):
                 c = desc.cmap[i]
@@ -251,18 +267,19 @@ def evaluate(desc, win, z, mu=0.0, want_grad=True):
             if np.isfinite(desc.blo[b]):
                 s = z[ii] - desc.blo[b]
                 if np.any(s <= 0):
-                    return J, np.inf, g, H
+                    return (J, np.inf, g, H, noise) if with_noise else (J, np.inf, g, H)
                 merit -= mu * float(np.sum(np.log(s)))
                 g[ii] -= mu / s
                 H[ii, ii] += mu / s ** 2
             if np.isfinite(desc.bhi[b]):
                 s = desc.bhi[b] - z[ii]
                 if np.any(s <= 0):
-                    return J, np.inf, g, H
+                    return (J, np.inf, g, H, noise) if with_noise else (J, np.inf, g, H)
                 merit -= mu * float(np.sum(np.log(s)))
                 g[ii] += mu / s
                 H[ii, ii] += mu / s ** 2
-    return J, merit, g, H
+    noise = 0.5 * noise + EPS * abs(merit)
+    return (J, merit, g, H, noise) if with_noise else (J, merit, g, H)
 
 
 def _max_step(desc, z, dz, tau):
@@ -305,18 +322,20 @@ def solve(desc, win, z0, opts=None):
     iters = 0
     status = ST_MAXITER
     lam = opts.lam0
-    J, merit, g, H = evaluate(desc, win, z, mu)
+    J, merit, g, H, nz0 = evaluate(desc, win, z, mu, with_noise=True)
     if not np.isfinite(merit):
         return z, dict(J=J, iters=0, status=ST_NUMERIC, lam=lam, mu=mu)
     while True:
         lam = opts.lam0
         stage_steps = 0
+        floor_steps = 0
         status = ST_MAXITER
         while iters < opts.max_iter and stage_steps < opts.max_stage_iter:
             if mu > opts.mu_min and stage_steps >= 1 and np.max(np.abs(g)) < 10.0 * mu:
                 status = ST_CONVERGED
                 break
             accepted = False
+            floor = False
             dg = np.diag(H).copy()
             dg = dg + 1e-14 * np.max(dg)
             while lam <= 1e18:
@@ -329,8 +348,16 @@ def solve(desc, win, z0, opts=None):
                 if ok:
                     a = _max_step(desc, z, dz, opts.tau_ftb) if bounded else 1.0
                     zt = z + a * dz
-                    Jt, mt, _, _ = evaluate(desc, win, zt, mu, want_grad=False)
+                    Jt, mt, _, _, nzt = evaluate(desc, win, zt, mu, want_grad=False, with_noise=True)
                     if np.isfinite(mt) and mt < merit:
+                        accepted = True
+                        break
+                    # rounding floor of the merit: the predicted decrease is below what the merit
+                    # can resolve, and the merit did not rise by more than its rounding bound
+                    pred = -a * float(g @ dz)
+                    nb = nz0 + nzt
+                    if np.isfinite(mt) and (mt - merit) <= nb and pred <= 4.0 * nb:
+                        floor = True      # accept: the Gauss-Newton step is still accurate (g is)
                         accepted = True
                         break
                 lam *= 10.0
@@ -342,14 +369,19 @@ def solve(desc, win, z0, opts=None):
             lam = max(lam / 10.0, 1e-12)
             iters += 1
             stage_steps += 1
-            J, merit, g, H = evaluate(desc, win, z, mu)
+            J, merit, g, H, nz0 = evaluate(desc, win, z, mu, with_noise=True)
             if step < opts.tol_step * (1.0 + float(np.max(np.abs(z)))):
                 status = ST_CONVERGED
                 break
+            if floor:
+                floor_steps += 1
+                if floor_steps >= 5:
+                    status = ST_CONVERGED
+                    break
         if not bounded or mu <= opts.mu_min or iters >= opts.max_iter:
             break
         mu = max(opts.mu_min, min(0.2 * mu, mu ** 1.5))
-        J, merit, g, H = evaluate(desc, win, z, mu)
+        J, merit, g, H, nz0 = evaluate(desc, win, z, mu, with_noise=True)
     return z, dict(J=J, iters=iters, status=status, lam=lam, mu=mu)
 
 

@@ -1,0 +1,214 @@
+"""GPU parity tests of the NLS path (kernels 1+2, 3 and the whole solve) against the CPU oracle
+and the reference's stored IPOPT outputs.  All calls go through the C ABI (ctypes)."""
+import numpy as np
+import pytest
+
+from nlp_filter_b200 import desc as D
+from nlp_filter_b200 import shapes, synth
+from tests import helpers
+
+pytestmark = pytest.mark.gpu
+
+
+def _engine():
+    from nlp_filter_b200 import engine
+    return engine
+
+
+def _oracle():
+    from oracle import nls
+    return nls
+
+
+def _rel(a, b):
+    return np.max(np.abs(a - b)) / (np.max(np.abs(b)) + 1e-300)
+
+
+def _check_assemble(d, batch, zs, mu=0.0, tol=1e-11):
+    eng, nls = _engine(), _oracle()
+    prob = eng.WindowProblem(d)
+    B = zs.shape[0]
+    H, g, cost = prob.assemble(zs, batch.get("U"), batch["data"], batch.get("xprior"), None, mu)
+    H, g, cost = H.cpu().numpy(), g.cpu().numpy(), cost.cpu().numpy()
+    for b in range(B):
+        win = nls.Window(d, U=None if batch.get("U") is None else batch["U"][b], data=batch["data"][b],
+                         xprior=None if batch.get("xprior") is None else batch["xprior"][b])
+        J, merit, go, Ho = nls.evaluate(d, win, zs[b], mu)
+        assert abs(cost[b, 0] - J) <= tol * abs(J), (b, cost[b, 0], J)
+        assert abs(cost[b, 1] - merit) <= tol * abs(merit) + 1e-12
+        assert _rel(g[b], go) < tol, (b, _rel(g[b], go))
+        assert _rel(H[b], Ho) < tol, (b, _rel(H[b], Ho))
+        assert np.max(np.abs(H[b] - H[b].T)) == 0.0
+    prob.close()
+
+
+def test_assemble_vdp():
+    d = shapes.vdp_mhe()
+    bt = synth.vdp_mhe_batch(d, 8, seed=11)
+    rng = np.random.default_rng(1)
+    zs = bt["z0"] + 0.05 * rng.normal(size=bt["z0"].shape)
+    _check_assemble(d, bt, zs)
+
+
+def test_assemble_gnss():
+    d = shapes.gnss()
+    bt = synth.gnss_batch(d, 6, seed=12)
+    rng = np.random.default_rng(2)
+    zs = bt["z0"] + rng.normal(size=bt["z0"].shape)
+    _check_assemble(d, bt, zs, tol=1e-10)
+
+
+@pytest.mark.parametrize("loss", [D.LOSS_L2, D.LOSS_HUBER])
+def test_assemble_car_barrier(loss):
+    d = shapes.car(loss=loss)
+    g = helpers.car_golden()
+    B = 4
+    U, data = zip(*[helpers.car_window_inputs(d, g, float(t0)) for t0 in range(B)])
+    rng = np.random.default_rng(3)
+    zs = np.zeros((B, d.nz))
+    V = zs.reshape(B, d.K, d.nv)
+    V[:, :, 3] = 10.0
+    V[:, :, 7] = 200.0
+    zs += 0.1 * rng.normal(size=zs.shape)
+    bt = dict(U=np.array(U), data=np.array(data), xprior=np.tile(helpers.car_xhat0(g), (B, 1)))
+    _check_assemble(d, bt, zs, mu=0.1, tol=1e-10)
+    _check_assemble(d, bt, zs, mu=0.0, tol=1e-10)
+
+
+def test_assemble_two_receiver_masked_slots_and_folded_equality():
+    d = shapes.two_receiver()
+    bt = helpers.two_receiver_batch(d, 4)
+    rng = np.random.default_rng(4)
+    zs = bt["z0"] + 0.5 * rng.normal(size=bt["z0"].shape)
+    _check_assemble(d, bt, zs, tol=1e-10)
+
+
+def test_factor_solve_matches_lapack():
+    eng = _engine()
+    d = shapes.gnss()
+    prob = eng.WindowProblem(d)
+    rng = np.random.default_rng(5)
+    B, nz = 16, d.nz
+    A = rng.normal(size=(B, nz, nz + 5))
+    H = A @ A.transpose(0, 2, 1) + 1e-3 * np.eye(nz)
+    g = rng.normal(size=(B, nz))
+    for lam in (0.0, 1e-3, 10.0):
+        dz, info = prob.factor_solve(H, g, lam)
+        dz, info = dz.cpu().numpy(), info.cpu().numpy()
+        assert np.all(info == 0)
+        for b in range(B):
+            dg = np.diag(H[b]) + 1e-14 * np.max(np.diag(H[b]))
+            ref = -np.linalg.solve(H[b] + lam * np.diag(dg), g[b])
+            assert _rel(dz[b], ref) < 1e-9
+    # an indefinite matrix must be reported, not factorised
+    Hbad = H.copy()
+    Hbad[3] = -Hbad[3]
+    dz, info = prob.factor_solve(Hbad, g, 0.0)
+    info = info.cpu().numpy()
+    assert info[3] == 1 and info[2] == 0
+    prob.close()
+
+
+def _solve_both(d, bt, B, opts=None, tol=1e-6):
+    eng, nls = _engine(), _oracle()
+    prob = eng.WindowProblem(d)
+    z, J, iters, status = eng.solve_windows_host(prob, bt["z0"][:B], None if bt.get("U") is None else bt["U"][:B],
+                                                 bt["data"][:B], None if bt.get("xprior") is None else bt["xprior"][:B], opts)
+    assert np.all(status <= 1), status
+    worst = 0.0
+    for b in range(B):
+        win = nls.Window(d, U=None if bt.get("U") is None else bt["U"][b], data=bt["data"][b],
+                         xprior=None if bt.get("xprior") is None else bt["xprior"][b])
+        zo, info = nls.solve(d, win, bt["z0"][b], opts)
+        assert info["status"] <= 1
+        err = np.max(np.abs(z[b] - zo) / (1.0 + np.abs(zo)))
+        worst = max(worst, err)
+        assert err < tol, (b, err, info, iters[b])
+        assert abs(J[b] - info["J"]) <= 1e-9 * abs(info["J"])
+    prob.close()
+    return worst
+
+
+def test_solve_vdp_matches_oracle():
+    d = shapes.vdp_mhe()
+    bt = synth.vdp_mhe_batch(d, 24, seed=21)
+    _solve_both(d, bt, 24)
+
+
+def test_solve_gnss_matches_oracle_1mm():
+    d = shapes.gnss()
+    bt = synth.gnss_batch(d, 12, seed=22)
+    eng, nls = _engine(), _oracle()
+    prob = eng.WindowProblem(d)
+    z, J, iters, status = eng.solve_windows_host(prob, bt["z0"], bt["U"], bt["data"])
+    for b in range(12):
+        zo, info = nls.solve(d, nls.Window(d, U=bt["U"][b], data=bt["data"][b]), bt["z0"][b])
+        V, Vo = z[b].reshape(d.K, 5), zo.reshape(d.K, 5)
+        assert np.max(np.abs(V[:, :3] - Vo[:, :3])) < 1e-3          # GNSS positions within 1 mm
+        assert np.max(np.abs(V - Vo) / (1 + np.abs(Vo))) < 1e-6
+    prob.close()
+
+
+def test_solve_two_receiver_matches_oracle():
+    d = shapes.two_receiver()
+    bt = helpers.two_receiver_batch(d, 6)
+    _solve_both(d, bt, 6)
+
+
+@pytest.mark.parametrize("loss,key", [(D.LOSS_L2, "nlp_l2"), (D.LOSS_HUBER, "nlp_huber")])
+def test_car_chain_reproduces_stored_ipopt_outputs(loss, key):
+    """Receding-horizon chain of autonomous-car.py:232-288 (first 30 windows) against the
+    reference's stored IPOPT results: positions within 1 mm."""
+    eng = _engine()
+    d = shapes.car(loss=loss)
+    g = helpers.car_golden()
+    prob = eng.WindowProblem(d)
+    gold = g[key]
+    ts = np.linspace(0, 2.0, 10)
+    xhat0 = helpers.car_xhat0(g)
+    z = np.zeros((1, d.nz))
+    PhiDT = d.cpm.basisMatrix([1.0])
+    worst = np.zeros(7)
+    for step in range(30):
+        U, data = helpers.car_window_inputs(d, g, float(step))
+        z, J, iters, status = eng.solve_windows_host(prob, z, U[None], data[None], xhat0[None])
+        assert status[0] <= 1
+        est = helpers.car_extract(d, z[0], ts)
+        worst = np.maximum(worst, np.max(np.abs(est - gold[step * 10:(step + 1) * 10]), 0))
+        xhat0 = (PhiDT @ z[0].reshape(d.K, d.nv))[0]
+    assert np.all(worst[:3] < 1e-3), worst          # x, y, z within 1 mm of the pickle
+    assert worst[3] < 1e-3 and worst[4] < 1e-3 and np.all(worst[5:] < 5e-3), worst
+    prob.close()
+
+
+def test_sample_matches_basis_product():
+    eng = _engine()
+    d = shapes.gnss()
+    prob = eng.WindowProblem(d)
+    rng = np.random.default_rng(7)
+    z = rng.normal(size=(5, d.nz))
+    ts = np.linspace(0, d.T, 17)
+    Ph = d.cpm.basisMatrix(ts)
+    out = prob.sample(z, Ph).cpu().numpy()
+    ref = np.einsum("tk,bkn->btn", Ph, z.reshape(5, d.K, d.nv))
+    assert np.max(np.abs(out - ref)) < 1e-12 * np.max(np.abs(ref))
+    prob.close()
+
+
+def test_empty_measurement_set_and_error_paths():
+    eng = _engine()
+    from nlp_filter_b200 import _capi
+    d = shapes.vdp_mhe()
+    d.set_residuals([], [], np.zeros((0, D.NIDX), dtype=np.int32))
+    d.E = 0
+    d.Phi = np.zeros((0, d.K))
+    prob = eng.WindowProblem(d)          # dynamics cost only: still a valid problem
+    bt = dict(z0=np.ones((2, d.nz)), U=np.zeros((2, d.K, 1)), data=np.zeros((2, 1)))
+    _, _, c0 = prob.assemble(bt["z0"], bt["U"], bt["data"])
+    z, J, iters, status = eng.solve_windows_host(prob, bt["z0"], bt["U"], bt["data"])
+    assert np.all(np.isfinite(z)) and np.all(J < 1e-3 * c0.cpu().numpy()[:, 0])
+    prob.close()
+    bad = shapes.vdp_mhe()
+    bad.resize_nv(30)          # nz = 630 exceeds the shared-memory-resident limit
+    with pytest.raises(_capi.NlpfError):
+        eng.WindowProblem(bad)
