@@ -289,7 +289,7 @@ extern "C" int nlpf_problem_create(const nlpf_desc* D, nlpf_problem** out) {
     int o = 0;
     auto take = [&](int cnt) { int r = o; o += (cnt + 1) & ~1; return r; };
     P.o_H = take((nz + 1) * (nz + 2) / 2);
-    P.o_z = take(nz); P.o_zt = take(nz); P.o_g = take(nz); P.o_ds = take(nz); P.o_dz = take(nz);
+    P.o_z = take(nz); P.o_zt = take(nz); P.o_g = take(nz); P.o_ds = take(nz); P.o_dd = take(nz); P.o_dz = take(nz);
     P.o_f = take(K * n); P.o_lw = take(K * n); P.o_wh = take(K * n); P.o_slw = take(K * nv); P.o_whs = take(K * nv);
     const bool needF = !P.hconst;
     P.o_F = take(needF ? K * n * nv : 0);

@@ -6,6 +6,7 @@
 
 #define NLPF_NT 128            // threads per window CTA (4 warps: one per SM sub-partition)
 #define NLPF_NW (NLPF_NT / 32)
+#define NLPF_MIN_CTAS 8        // register cap 64/thread: 8 windows resident per SM (ncu: 128 regs limited it to 4)
 #define NLPF_NA_MAX 8          // active node-variable components a measurement set may touch
 #define NLPF_NG_MAX 8
 #define NLPF_N_MAX 12
@@ -51,7 +52,7 @@ struct DevProb {
     const uint32_t* tab;              // np  packed index -> j | a<<8 | l<<16 | b<<24 (255 = global)
     const uint16_t* ptab;             // npair  pair index -> j | l<<8
     // shared-memory layout, offsets in doubles
-    int o_H, o_z, o_zt, o_g, o_ds, o_dz, o_f, o_lw, o_wh, o_slw, o_F, o_GF, o_FF, o_whs;
+    int o_H, o_z, o_zt, o_g, o_ds, o_dd, o_dz, o_f, o_lw, o_wh, o_slw, o_F, o_GF, o_FF, o_whs;
     int o_Ve, o_G, o_q, o_Phi, o_Dt, o_red, smem_doubles;
 };
 

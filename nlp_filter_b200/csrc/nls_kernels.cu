@@ -648,6 +648,37 @@ __device__ void eval_window(const DevProb& P, double* sm, const double* zc, cons
             }
         }
     }
+    // ---- phase S: damping diagonal (Gauss-Newton diagonal, always positive) and the exact
+    //      second-order part of the dynamics cost  sum_i lw_ki * (-hess f_i(X_k))  for the models
+    //      that carry it (Gauss-Newton alone is only linearly convergent on large-defect windows) ----
+    if (FULL) {
+        __syncthreads();
+        double* dd = sm + P.o_dd;
+        for (int i = tid; i < nz; i += NLPF_NT) dd[i] = Hp[pk(i, i)];
+        if (P.has_dyncost && (P.dyn_id == NLPF_DYN_VDP || P.dyn_id == NLPF_DYN_BICYCLE)) {
+            __syncthreads();
+            for (int k = tid; k < K; k += NLPF_NT) {
+                const int o = k * nv;
+                if (P.dyn_id == NLPF_DYN_VDP) {
+                    // f0 = (1 - x1^2) x0 - x1 + u:  hess f0 = [[0, -2 x1], [-2 x1, -2 x0]]
+                    const int c0 = P.cmap[0], c1 = P.cmap[1];
+                    const double x0 = zc[o + c0], x1 = zc[o + c1];
+                    const double l0 = lw[k * n + 0];
+                    const int rhi = o + max(c0, c1), rlo = o + min(c0, c1);
+                    Hp[pk(rhi, rlo)] += l0 * 2.0 * x1;
+                    Hp[pk(o + c1, o + c1)] += l0 * 2.0 * x0;
+                } else {
+                    // f0 = v cos th, f1 = v sin th, th = x[2]
+                    const int c2 = P.cmap[2];
+                    const double u0 = (P.ucol[0] >= 0) ? zc[o + P.ucol[0]] : (wp.U ? wp.U[k * m + 0] : 0.0);
+                    const double v = 8.72649116358 * u0 - 0.856053299155;
+                    double s2, c2v;
+                    sincos(zc[o + c2], &s2, &c2v);
+                    Hp[pk(o + c2, o + c2)] += lw[k * n + 0] * v * c2v + lw[k * n + 1] * v * s2;
+                }
+            }
+        }
+    }
     // ---- phase I: reductions ----
     const double J = block_sum(cost, red);
     const double B = block_sum(bar, red);
@@ -791,7 +822,7 @@ factor_solve_kernel(DevProb P, int B, const double* __restrict__ H, const double
 // nlpf_solve: the whole damped Gauss-Newton / log-barrier iteration of one window per CTA.
 // Same decisions, in the same order, as oracle/nls.py:solve (the CPU checker).
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(NLPF_NT)
+__global__ void __launch_bounds__(NLPF_NT, NLPF_MIN_CTAS)
 solve_kernel(DevProb P, int B, double* __restrict__ z_io, const double* __restrict__ U,
              const double* __restrict__ data, const double* __restrict__ xprior,
              const double* __restrict__ wshift, nlpf_opts opt, double* __restrict__ cost_out,
@@ -805,6 +836,7 @@ solve_kernel(DevProb P, int B, double* __restrict__ z_io, const double* __restri
     double* g = sm + P.o_g;
     double* ds = sm + P.o_ds;
     double* dz = sm + P.o_dz;
+    double* dd = sm + P.o_dd;
     double* red = sm + P.o_red;
     stage_constants(P, sm);
     const bool bounded = P.nb > 0;
@@ -843,9 +875,8 @@ solve_kernel(DevProb P, int B, double* __restrict__ z_io, const double* __restri
                     double gm = 0.0, dm = 0.0;
                     for (int i = tid; i < nz; i += NLPF_NT) {
                         gm = fmax(gm, fabs(g[i]));
-                        const double d = Hp[pk(i, i)];
-                        ds[i] = d;
-                        dm = fmax(dm, d);
+                        ds[i] = Hp[pk(i, i)];
+                        dm = fmax(dm, dd[i]);
                     }
                     gm = block_max(gm, red);
                     dm = block_max(dm, red);
@@ -863,7 +894,7 @@ solve_kernel(DevProb P, int B, double* __restrict__ z_io, const double* __restri
                             h_valid = true;
                         }
                         for (int i = tid; i < nz; i += NLPF_NT) {
-                            Hp[pk(i, i)] = ds[i] + lam * (ds[i] + 1e-14 * dm);
+                            Hp[pk(i, i)] = ds[i] + lam * (dd[i] + 1e-14 * dm);
                             Hp[pk(nz, i)] = g[i];
                         }
                         h_valid = false;
@@ -1019,5 +1050,7 @@ extern "C" int nlpf_set_smem_attrs(size_t bytes) {
     if (e != cudaSuccess) return nlpf_check_cuda(e, "smem attr factor");
     e = cudaFuncSetAttribute(solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
     if (e != cudaSuccess) return nlpf_check_cuda(e, "smem attr solve");
+    e = cudaFuncSetAttribute(solve_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    if (e != cudaSuccess) return nlpf_check_cuda(e, "smem carveout solve");
     return 0;
 }
