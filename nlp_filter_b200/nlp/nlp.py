@@ -71,6 +71,8 @@ def _as_diag(M, n, what):
 class NLP(object):
     """NLP class"""
 
+    MAX_ITER = 3000
+
     def __init__(self, N):
         self.N = N
         self.var_names = []
@@ -199,6 +201,8 @@ class NLP(object):
         prob = self._problem_handle()
         dev = lambda a: None if a is None else torch.as_tensor(np.ascontiguousarray(a, dtype=np.float64).reshape(1, -1)).cuda()
         z = dev(z0)
+        if opts is None:            # a single problem may iterate as long as IPOPT would (its max_iter default is 3000)
+            opts = D.SolveOpts(max_iter=self.MAX_ITER, max_stage_iter=self.MAX_ITER)
         _, cost, iters, status = prob.solve(z, dev(U), dev(data), dev(xprior), dev(wshift), opts)
         torch.cuda.synchronize()
         return z.cpu().numpy()[0], dict(J=float(cost.item()), iters=int(iters.item()), status=int(status.item()))
