@@ -29,7 +29,7 @@ extern "C" int nlpf_launch_assemble(nlpf_problem*, int, const double*, const dou
 extern "C" int nlpf_launch_factor_solve(nlpf_problem*, int, const double*, const double*, double, double*, int*,
                                         cudaStream_t);
 extern "C" int nlpf_launch_solve(nlpf_problem*, int, double*, const double*, const double*, const double*,
-                                 const double*, const nlpf_opts*, double*, int*, int*, cudaStream_t);
+                                 const double*, const nlpf_opts*, double*, int*, int*, double*, cudaStream_t);
 extern "C" int nlpf_launch_sample(nlpf_problem*, int, const double*, int, const double*, double*, cudaStream_t);
 extern "C" int nlpf_set_smem_attrs(size_t bytes);
 
@@ -130,6 +130,8 @@ extern "C" int nlpf_problem_create(const nlpf_desc* D, nlpf_problem** out) {
 
     nlpf_problem* p = new nlpf_problem();
     memset(&p->d, 0, sizeof(DevProb));
+    p->scratch = nullptr;
+    p->scratch_doubles = 0;
     DevProb& P = p->d;
     P.K = K; P.n = n; P.m = m; P.nv = nv; P.ng = ng; P.nz = nz; P.np = nz * (nz + 1) / 2;
     P.dyn_id = D->dyn_id; P.loss = D->loss; P.has_prior = D->has_prior ? 1 : 0;
@@ -177,6 +179,8 @@ extern "C" int nlpf_problem_create(const nlpf_desc* D, nlpf_problem** out) {
     const int na = (int)act.size();
     if (na > NLPF_NA_MAX) { nlpf_set_error("measurements touch %d node components (limit %d)", na, NLPF_NA_MAX); delete p; return NLPF_E_ARG; }
     P.na = na; P.nat = na + ng;
+    P.lin_meas = (M > 0) ? 1 : 0;
+    for (int i = 0; i < M; ++i) if (D->rtype[i] != NLPF_RT_STATE) P.lin_meas = 0;
     std::vector<int> rtype_s(M), rloc_s((size_t)M * NLPF_NIDX, -1), roff_s(M), estart(E + 1, 0);
     for (int r = 0; r < M; ++r) {
         const int i = order[r];
@@ -255,6 +259,16 @@ extern "C" int nlpf_problem_create(const nlpf_desc* D, nlpf_problem** out) {
         for (int j = 0; j < K; ++j) for (int l = 0; l <= j; ++l) ptab[q++] = (uint16_t)(j | (l << 8));
     }
 
+    // LDL trailing-update work items: (row, 8-column segment) of the generic lower triangle with
+    // nz+1 rows, row-major, so that the items of a trailing triangle with s rows are a prefix
+    std::vector<uint16_t> seg_tab;
+    std::vector<int> seg_cnt(nz + 2, 0);
+    for (int di = 0; di <= nz; ++di) {
+        seg_cnt[di] = (int)seg_tab.size();
+        for (int dk0 = 0; dk0 <= di; dk0 += 8) seg_tab.push_back((uint16_t)(di | ((dk0 >> 3) << 8)));
+    }
+    seg_cnt[nz + 1] = (int)seg_tab.size();
+
     // ---- blob ----
     Blob B;
     std::vector<double> zero1(1, 0.0);
@@ -267,7 +281,7 @@ extern "C" int nlpf_problem_create(const nlpf_desc* D, nlpf_problem** out) {
                  obl = B.add(D->blo, sizeof(double) * D->nb), obh = B.add(D->bhi, sizeof(double) * D->nb),
                  oPh = B.add(D->Phi, sizeof(double) * E * K), ort = B.addv(rtype_s), orl = B.addv(rloc_s),
                  oro = B.addv(roff_s), oes = B.addv(estart), oac = B.addv(act), oHc = B.addv(Hc), oFc = B.addv(Fc),
-                 otb = B.addv(tab), opt = B.addv(ptab);
+                 otb = B.addv(tab), opt = B.addv(ptab), osg = B.addv(seg_tab), osc = B.addv(seg_cnt);
     B.add(zero1.data(), 16);
     p->blob_bytes = B.host.size();
     cudaGetDevice(&p->device);
@@ -284,6 +298,7 @@ extern "C" int nlpf_problem_create(const nlpf_desc* D, nlpf_problem** out) {
     P.rtype = (const int*)(base + ort); P.rloc = (const int*)(base + orl); P.roff = (const int*)(base + oro);
     P.estart = (const int*)(base + oes); P.act = (const int*)(base + oac); P.Hc = (const double*)(base + oHc);
     P.Fc = (const double*)(base + oFc); P.tab = (const uint32_t*)(base + otb); P.ptab = (const uint16_t*)(base + opt);
+    P.seg_tab = (const uint16_t*)(base + osg); P.seg_cnt = (const int*)(base + osc);
 
     // ---- shared-memory layout (doubles) ----
     int o = 0;
@@ -315,6 +330,7 @@ extern "C" int nlpf_problem_create(const nlpf_desc* D, nlpf_problem** out) {
 extern "C" int nlpf_problem_destroy(nlpf_problem* p) {
     if (!p) return NLPF_OK;
     cudaFree(p->blob);
+    if (p->scratch) cudaFree(p->scratch);
     delete p;
     return NLPF_OK;
 }
@@ -351,12 +367,17 @@ extern "C" int nlpf_solve(nlpf_problem* p, int B, double* z, const double* U, co
     int rc = check_batch(p, B, z, data);
     if (rc) return rc;
     if (!opts || !cost_out || !iters_out || !status_out) { nlpf_set_error("null opts/output buffer"); return NLPF_E_ARG; }
-    if (p->d.m > 0 && !U) {
-        bool need = false;
-        // host copy of ucol is not kept; a parameter control without a U buffer reads as zero
-        (void)need;
+    double* hlin = nullptr;
+    if (p->d.lin_meas) {        // per-window constant-H cache (not shared between concurrent calls on one handle)
+        const size_t need = (size_t)B * p->d.np;
+        if (need > p->scratch_doubles) {
+            if (p->scratch) { cudaStreamSynchronize((cudaStream_t)stream); cudaFree(p->scratch); p->scratch = nullptr; p->scratch_doubles = 0; }
+            if (nlpf_check_cuda(cudaMalloc((void**)&p->scratch, need * sizeof(double)), "cudaMalloc(constant-H cache)")) return NLPF_E_CUDA;
+            p->scratch_doubles = need;
+        }
+        hlin = p->scratch;
     }
-    return nlpf_launch_solve(p, B, z, U, data, xprior, wshift, opts, cost_out, iters_out, status_out, (cudaStream_t)stream);
+    return nlpf_launch_solve(p, B, z, U, data, xprior, wshift, opts, cost_out, iters_out, status_out, hlin, (cudaStream_t)stream);
 }
 
 extern "C" int nlpf_sample(nlpf_problem* p, int B, const double* z, int nt, const double* PhiT, double* out, void* stream) {

@@ -19,6 +19,7 @@
 struct DevProb {
     int K, n, m, nv, ng, nz, np;      // np = packed lower-triangle size nz(nz+1)/2
     int dyn_id, loss, has_prior, has_dyncost, has_nodecost;
+    int lin_meas;                     // 1: every residual is RT_STATE: its H contribution is constant per window
     int hconst;                       // 1: the dynamics part of H is constant (L2 loss, affine model)
     int fconst;                       // 1: dF/dv is constant (affine model)
     int nb, E, M, Ldata;
@@ -51,6 +52,8 @@ struct DevProb {
     const double* Fc;                 // n*nv constant dF/dv (affine models)
     const uint32_t* tab;              // np  packed index -> j | a<<8 | l<<16 | b<<24 (255 = global)
     const uint16_t* ptab;             // npair  pair index -> j | l<<8
+    const uint16_t* seg_tab;          // LDL trailing-update items of the generic triangle: di | (dk0/8)<<8
+    const int* seg_cnt;               // nz+2  number of items of a trailing triangle with s rows
     // shared-memory layout, offsets in doubles
     int o_H, o_z, o_zt, o_g, o_ds, o_dd, o_dz, o_f, o_lw, o_wh, o_slw, o_F, o_GF, o_FF, o_whs;
     int o_Ve, o_G, o_q, o_Phi, o_Dt, o_red, smem_doubles;
@@ -59,6 +62,8 @@ struct DevProb {
 struct nlpf_problem {
     DevProb d;
     void* blob;          // one device allocation holding every table
+    double* scratch;     // B x np constant-H cache of linear-measurement problems (grown on demand)
+    size_t scratch_doubles;
     size_t blob_bytes;
     size_t smem_bytes;
     int device;

@@ -345,6 +345,7 @@ struct WinPtr {
     const double* data;    // Ldata
     const double* xprior;  // n     or NULL
     const double* wshift;  // K*n   or NULL
+    double* hlin;          // np    constant H of this window (Hc + linear measurements) or NULL
 };
 
 __device__ __forceinline__ int pk(int r, int c) { return ((r * (r + 1)) >> 1) + c; }
@@ -355,9 +356,12 @@ __device__ __forceinline__ int pk(int r, int c) { return ((r * (r + 1)) >> 1) + 
 // Returns J and merit = J/2 + barrier (identical in every thread).  merit = +inf flags an
 // iterate outside the bounds or a non-finite objective.
 // ------------------------------------------------------------------------------------------
+// hmode: 0 = assemble everything; 1 = all measurements are linear (RT_STATE) and their constant
+// contribution to H is already folded into wp.hlin (built once per window by build_hlin): start
+// from it and skip the O(E K^2 na^2) accumulation (ncu: 24 % of the VDP kernel's samples).
 template <bool FULL>
 __device__ void eval_window(const DevProb& P, double* sm, const double* zc, const WinPtr& wp, double mu,
-                            double& J_out, double& merit_out, double& noise_out) {
+                            double& J_out, double& merit_out, double& noise_out, int hmode = 0) {
     const int tid = threadIdx.x;
     const int K = P.K, n = P.n, m = P.m, nv = P.nv, ng = P.ng, nz = P.nz, na = P.na, nat = P.nat;
     double* Hp = sm + P.o_H;
@@ -386,7 +390,8 @@ __device__ void eval_window(const DevProb& P, double* sm, const double* zc, cons
 
     // ---- phase A: H <- constant part, g <- 0 ----
     if (FULL) {
-        for (int p = tid; p < P.np; p += NLPF_NT) Hp[p] = P.Hc[p];
+        const double* H0 = (hmode == 1) ? wp.hlin : P.Hc;
+        for (int p = tid; p < P.np; p += NLPF_NT) Hp[p] = H0[p];
         for (int i = tid; i < nz; i += NLPF_NT) g[i] = 0.0;
     }
     // ---- phase B: node dynamics f (and dF/dv) ----
@@ -532,8 +537,10 @@ __device__ void eval_window(const DevProb& P, double* sm, const double* zc, cons
             for (int j = 0; j < K; ++j) s = fma(ph[j], zc[j * nv + col], s);
             Ve[t] = s;
         }
+        const bool accH = FULL && hmode == 0;
         if (FULL) {
-            for (int t = tid; t < ne * nat * nat; t += NLPF_NT) G[t] = 0.0;
+            if (accH)
+                for (int t = tid; t < ne * nat * nat; t += NLPF_NT) G[t] = 0.0;
             for (int t = tid; t < ne * nat; t += NLPF_NT) q[t] = 0.0;
         }
         __syncthreads();
@@ -557,7 +564,8 @@ __device__ void eval_window(const DevProb& P, double* sm, const double* zc, cons
                     for (int p = 0; p < nn; ++p) {
                         const double wg = w * gv[p];
                         qe[gl[p]] = fma(wg, r, qe[gl[p]]);
-                        for (int p2 = 0; p2 < nn; ++p2) Ge[gl[p] * nat + gl[p2]] = fma(wg, gv[p2], Ge[gl[p] * nat + gl[p2]]);
+                        if (accH)
+                            for (int p2 = 0; p2 < nn; ++p2) Ge[gl[p] * nat + gl[p2]] = fma(wg, gv[p2], Ge[gl[p] * nat + gl[p2]]);
                     }
                 }
             }
@@ -565,7 +573,7 @@ __device__ void eval_window(const DevProb& P, double* sm, const double* zc, cons
         if (FULL) {
             __syncthreads();
             // node-node blocks: H[(j,a),(l,b)] += sum_e phi_ej phi_el G_e[a][b]
-            const int nwork = P.npair * na;
+            const int nwork = accH ? P.npair * na : 0;
             for (int wk = tid; wk < nwork; wk += NLPF_NT) {
                 const int pr = wk / na, a = wk - pr * na;
                 const int pe = P.ptab[pr];
@@ -598,7 +606,7 @@ __device__ void eval_window(const DevProb& P, double* sm, const double* zc, cons
                 g[j * nv + P.act[a]] -= s;
             }
             // global unknowns: rows K*nv + gi
-            if (ng > 0) {
+            if (ng > 0 && accH) {
                 for (int t = tid; t < ng * K * na; t += NLPF_NT) {
                     const int gi = t / (K * na);
                     const int rem = t - gi * K * na;
@@ -697,27 +705,91 @@ __device__ void eval_window(const DevProb& P, double* sm, const double* zc, cons
 // On entry Hp holds the lower triangle of H (+ damping) and row nz holds g.  The elimination
 // leaves the unscaled factor (column j still multiplied by d_j) and, in row nz, L^-1 g; the
 // backward sweep then produces x = H^-1 g in xs.  Returns false when a pivot is not positive.
-// One block barrier per column; no square roots.
+//
+// Right-looking with panels of 4 columns (ncu of the column-at-a-time version: 33 % of the
+// kernel's stall samples sat behind its per-column barrier with <= nz of 128 threads busy):
+//   1. every thread factors the 4x4 diagonal block redundantly in registers (no barrier inside
+//      the panel), 2. one thread per row forms the panel entries w_i = A_i,J L11^-T,
+//   3. the trailing update A_ik -= sum_c (w_ic / d_c) w_kc is cut into (row, 8-column segment)
+//      items from a host-built table so that all 128 threads share it evenly; w_i stays in
+//      registers, 4 FMAs per 6 shared-memory accesses instead of 1 per 3.
+// Two barriers per 4 columns; no square roots.
 // ------------------------------------------------------------------------------------------
-__device__ bool ldl_solve(int nz, double* Hp, double* xs) {
+__device__ bool ldl_solve(const DevProb& P, int nz, double* Hp, double* xs) {
     const int tid = threadIdx.x;
-    const int rows = nz + 1;
     bool ok = true;
-    for (int j = 0; j < nz; ++j) {
+    for (int j0 = 0; j0 < nz; j0 += 4) {
+        const int pw = min(4, nz - j0);
         __syncthreads();
-        const double d = Hp[pk(j, j)];
-        if (!(d > 0.0) || !isfinite(d)) { ok = false; break; }   // uniform: every thread reads the same d
-        const double rd = 1.0 / d;
-        // trailing update of rows i > j (including the appended row), columns j < k <= i
-        const int rem = rows - (j + 1);
-        for (int ii = tid; ii < rem; ii += NLPF_NT) {
-            const int i = j + 1 + ii;
+        // ---- 1. diagonal block, redundantly per thread ----
+        double a[4][4], l[4][4], d[4], rd[4];
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+#pragma unroll
+            for (int c = 0; c <= r; ++c) a[r][c] = (r < pw) ? Hp[pk(j0 + r, j0 + c)] : (r == c ? 1.0 : 0.0);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            // w_rc = a_rc - sum_{q<c} w_rq l_cq  (stored back into a), d_c = w_cc
+#pragma unroll
+            for (int r = c; r < 4; ++r) {
+                double w = a[r][c];
+#pragma unroll
+                for (int q = 0; q < c; ++q) w = fma(-a[r][q], l[c][q], w);
+                a[r][c] = w;
+            }
+            d[c] = a[c][c];
+            rd[c] = 1.0 / d[c];
+#pragma unroll
+            for (int r = c + 1; r < 4; ++r) l[r][c] = a[r][c] * rd[c];
+        }
+        bool good = true;
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+            if (c < pw && (!(d[c] > 0.0) || !isfinite(d[c]))) good = false;
+        if (!good) { ok = false; break; }           // uniform: every thread factored the same block
+        const int j1 = j0 + pw;
+        // ---- 2. panel rows: w_i = a_i,J L11^-T (unscaled storage), one thread per row ----
+        for (int i = j1 + tid; i <= nz; i += NLPF_NT) {
+            double* Hi = Hp + ((i * (i + 1)) >> 1) + j0;
+            double w[4];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                if (c < pw) {
+                    double v = Hi[c];
+#pragma unroll
+                    for (int q = 0; q < c; ++q) v = fma(-w[q], l[c][q], v);
+                    w[c] = v;
+                    Hi[c] = v;
+                } else w[c] = 0.0;
+            }
+        }
+        __syncthreads();
+        if (tid == NLPF_NT - 1) {                    // the block itself, in the same storage convention; written
+#pragma unroll                                       // only after every thread has read it (nobody reads it again
+            for (int r = 0; r < 4; ++r)              // before the backward sweep)
+#pragma unroll
+                for (int c = 0; c <= r; ++c)
+                    if (r < pw) Hp[pk(j0 + r, j0 + c)] = a[r][c];
+        }
+        // ---- 3. trailing update over (row, 8-column segment) items ----
+        const int s = nz + 1 - j1;                   // rows j1 .. nz
+        const int nitem = P.seg_cnt[s];
+        for (int it = tid; it < nitem; it += NLPF_NT) {
+            const int e = P.seg_tab[it];
+            const int i = j1 + (e & 255);
+            const int k0 = j1 + ((e >> 8) << 3);
+            const int kend = min(min(k0 + 7, i), nz - 1);      // the appended row has no diagonal entry
             double* Hi = Hp + ((i * (i + 1)) >> 1);
-            const double lij = Hi[j] * rd;
-            const int kend = (i < nz) ? i : nz - 1;     // the appended row has no diagonal entry
-            for (int k = j + 1; k <= kend; ++k) {
-                const double hkj = Hp[pk(k, j)];
-                Hi[k] = fma(-lij, hkj, Hi[k]);
+            double li[4];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) li[c] = (c < pw) ? Hi[j0 + c] * rd[c] : 0.0;
+            for (int k = k0; k <= kend; ++k) {
+                const double* Hk = Hp + ((k * (k + 1)) >> 1) + j0;
+                double v = Hi[k];
+#pragma unroll
+                for (int c = 0; c < 4; ++c)
+                    if (c < pw) v = fma(-li[c], Hk[c], v);
+                Hi[k] = v;
             }
         }
     }
@@ -753,6 +825,7 @@ __device__ __forceinline__ WinPtr window_ptrs(const DevProb& P, int b, const dou
     wp.data = data ? data + (size_t)b * P.Ldata : nullptr;
     wp.xprior = xprior ? xprior + (size_t)b * P.n : nullptr;
     wp.wshift = wshift ? wshift + (size_t)b * P.K * P.n : nullptr;
+    wp.hlin = nullptr;
     return wp;
 }
 
@@ -812,10 +885,43 @@ factor_solve_kernel(DevProb P, int B, const double* __restrict__ H, const double
             Hp[pk(i, i)] += lam * (Hp[pk(i, i)] + 1e-14 * dmax);
             Hp[pk(nz, i)] = g[(size_t)b * nz + i];
         }
-        const bool ok = ldl_solve(nz, Hp, sm + P.o_dz);
+        const bool ok = ldl_solve(P, nz, Hp, sm + P.o_dz);
         for (int i = threadIdx.x; i < nz; i += NLPF_NT) dz_out[(size_t)b * nz + i] = ok ? -sm[P.o_dz + i] : 0.0;
         if (threadIdx.x == 0) info_out[b] = ok ? 0 : 1;
     }
+}
+
+// Hc + sum_e (phi_e phi_e^T) (x) diag(w_e) of one window whose residuals are all RT_STATE: constant
+// over the iterations, written once to the window's slot of the scratch buffer.
+__device__ void build_hlin(const DevProb& P, double* sm, const WinPtr& wp) {
+    const int tid = threadIdx.x;
+    const int K = P.K, nv = P.nv, na = P.na;
+    double* Hp = sm + P.o_H;
+    const double* Phi = sm + P.o_Phi;
+    double* wacc = sm + P.o_G;                   // E chunk x na weights
+    for (int p = tid; p < P.np; p += NLPF_NT) Hp[p] = P.Hc[p];
+    for (int c0 = 0; c0 < P.E; c0 += P.ec) {
+        const int ne = min(P.ec, P.E - c0);
+        __syncthreads();
+        for (int t = tid; t < ne * na; t += NLPF_NT) wacc[t] = 0.0;
+        __syncthreads();
+        for (int el = tid; el < ne; el += NLPF_NT)
+            for (int i = P.estart[c0 + el]; i < P.estart[c0 + el + 1]; ++i)
+                wacc[el * na + P.rloc[i * NLPF_NIDX]] += wp.data[P.roff[i] + 1];
+        __syncthreads();
+        for (int wk = tid; wk < P.npair * na; wk += NLPF_NT) {
+            const int pr = wk / na, a = wk - pr * na;
+            const int pe = P.ptab[pr];
+            const int j = pe & 255, l = pe >> 8;
+            double acc = 0.0;
+            for (int el = 0; el < ne; ++el) acc = fma(Phi[(c0 + el) * K + j] * Phi[(c0 + el) * K + l], wacc[el * na + a], acc);
+            const int r = j * nv + P.act[a], c = l * nv + P.act[a];
+            Hp[pk(r, c)] += acc;
+        }
+    }
+    __syncthreads();
+    for (int p = tid; p < P.np; p += NLPF_NT) wp.hlin[p] = Hp[p];
+    __syncthreads();
 }
 
 // ------------------------------------------------------------------------------------------
@@ -826,7 +932,7 @@ __global__ void __launch_bounds__(NLPF_NT, NLPF_MIN_CTAS)
 solve_kernel(DevProb P, int B, double* __restrict__ z_io, const double* __restrict__ U,
              const double* __restrict__ data, const double* __restrict__ xprior,
              const double* __restrict__ wshift, nlpf_opts opt, double* __restrict__ cost_out,
-             int* __restrict__ iters_out, int* __restrict__ status_out) {
+             int* __restrict__ iters_out, int* __restrict__ status_out, double* __restrict__ hlin) {
     extern __shared__ double sm[];
     const int tid = threadIdx.x;
     const int nz = P.nz, K = P.K, nv = P.nv;
@@ -857,12 +963,17 @@ solve_kernel(DevProb P, int B, double* __restrict__ z_io, const double* __restri
             __syncthreads();
         }
         WinPtr wp = window_ptrs(P, b, U, data, xprior, wshift);
+        const int hmode = (hlin != nullptr && P.lin_meas) ? 1 : 0;
+        if (hmode) {
+            wp.hlin = hlin + (size_t)b * P.np;
+            build_hlin(P, sm, wp);
+        }
         double mu = bounded ? opt.mu0 : 0.0;
         int iters = 0;
         int status = NLPF_ST_MAXITER;
         double lam = opt.lam0;
         double J, merit, nse0;
-        eval_window<true>(P, sm, zs, wp, mu, J, merit, nse0);
+        eval_window<true>(P, sm, zs, wp, mu, J, merit, nse0, hmode);
         if (!isfinite(merit)) {
             status = NLPF_ST_NUMERIC;
         } else {
@@ -890,7 +1001,7 @@ solve_kernel(DevProb P, int B, double* __restrict__ z_io, const double* __restri
                     while (lam <= 1e18) {
                         if (!h_valid) {       // the factorisation overwrote H: rebuild it at z
                             double Jd, md, nd;
-                            eval_window<true>(P, sm, zs, wp, mu, Jd, md, nd);
+                            eval_window<true>(P, sm, zs, wp, mu, Jd, md, nd, hmode);
                             h_valid = true;
                         }
                         for (int i = tid; i < nz; i += NLPF_NT) {
@@ -898,7 +1009,7 @@ solve_kernel(DevProb P, int B, double* __restrict__ z_io, const double* __restri
                             Hp[pk(nz, i)] = g[i];
                         }
                         h_valid = false;
-                        const bool ok = ldl_solve(nz, Hp, dz);
+                        const bool ok = ldl_solve(P, nz, Hp, dz);
                         if (ok) {
                             // dz holds H^-1 g: the step is -dz.  fraction to the boundary:
                             double a = 1.0, dmx = 0.0, finite = 0.0;
@@ -926,7 +1037,7 @@ solve_kernel(DevProb P, int B, double* __restrict__ z_io, const double* __restri
                                 }
                                 pred = a * block_sum(pred, red);     // predicted decrease scale g^T H^-1 g
                                 __syncthreads();
-                                eval_window<false>(P, sm, zt, wp, mu, Jt, mt, nset);
+                                eval_window<false>(P, sm, zt, wp, mu, Jt, mt, nset, hmode);
                                 if (isfinite(mt) && mt < merit) {
                                     accepted = true;
                                     alpha = a;
@@ -951,7 +1062,7 @@ solve_kernel(DevProb P, int B, double* __restrict__ z_io, const double* __restri
                         status = NLPF_ST_STALLED;
                         if (!h_valid) {   // leave H, g consistent with z for a following stage
                             double Jd, md, nd;
-                            eval_window<true>(P, sm, zs, wp, mu, Jd, md, nd);
+                            eval_window<true>(P, sm, zs, wp, mu, Jd, md, nd, hmode);
                         }
                         break;
                     }
@@ -965,7 +1076,7 @@ solve_kernel(DevProb P, int B, double* __restrict__ z_io, const double* __restri
                     lam = fmax(lam / 10.0, 1e-12);
                     ++iters;
                     ++stage_steps;
-                    eval_window<true>(P, sm, zs, wp, mu, J, merit, nse0);
+                    eval_window<true>(P, sm, zs, wp, mu, J, merit, nse0, hmode);
                     if (step < opt.tol_step * (1.0 + zm)) {
                         status = NLPF_ST_CONVERGED;
                         break;
@@ -977,7 +1088,7 @@ solve_kernel(DevProb P, int B, double* __restrict__ z_io, const double* __restri
                 }
                 if (!bounded || mu <= opt.mu_min || iters >= opt.max_iter) break;
                 mu = fmax(opt.mu_min, fmin(0.2 * mu, mu * sqrt(mu)));
-                eval_window<true>(P, sm, zs, wp, mu, J, merit, nse0);
+                eval_window<true>(P, sm, zs, wp, mu, J, merit, nse0, hmode);
             }
         }
         for (int i = tid; i < nz; i += NLPF_NT) z_io[(size_t)b * nz + i] = zs[i];
@@ -1027,8 +1138,8 @@ extern "C" int nlpf_launch_factor_solve(nlpf_problem* p, int B, const double* H,
 
 extern "C" int nlpf_launch_solve(nlpf_problem* p, int B, double* z, const double* U, const double* data,
                                  const double* xprior, const double* wshift, const nlpf_opts* o, double* cost_out,
-                                 int* iters_out, int* status_out, cudaStream_t st) {
-    solve_kernel<<<grid_for(B), NLPF_NT, p->smem_bytes, st>>>(p->d, B, z, U, data, xprior, wshift, *o, cost_out, iters_out, status_out);
+                                 int* iters_out, int* status_out, double* hlin, cudaStream_t st) {
+    solve_kernel<<<grid_for(B), NLPF_NT, p->smem_bytes, st>>>(p->d, B, z, U, data, xprior, wshift, *o, cost_out, iters_out, status_out, hlin);
     return nlpf_check_cuda(cudaGetLastError(), "solve_kernel launch");
 }
 
