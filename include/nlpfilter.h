@@ -169,6 +169,17 @@ int nlpf_ls_solve(int B, int smax, const double* sat, const double* pr, const in
 int nlpf_ls_vel(int B, int smax, const double* sat, const double* satvel, const double* prr,
                 const int* nsat, const double* x, double* out, void* stream);
 
+/* Row A9 (no reference counterpart; extension for multi-segment / long-horizon collocation):
+ * solve B SPD block-tridiagonal systems with diagonal blocks Dg[B][nblk][bs*bs], sub-diagonal
+ * blocks Lo[B][nblk][bs*bs] (Lo[.][0] ignored; A[i][i-1] = Lo[i], A[i-1][i] = Lo[i]^T), right-hand
+ * sides rhs[B][nblk][bs].  variant 0 = block Cholesky / Riccati recursion, 1 = block cyclic
+ * reduction.  x_out[B][nblk][bs]; info_out[B] 0 ok / 1 not positive definite.  bs <= 16. */
+int nlpf_blocktri_solve(int B, int nblk, int bs, const double* Dg, const double* Lo, const double* rhs,
+                        double* x_out, int* info_out, int variant, void* stream);
+
+/* shared memory (bytes) one window of this problem class needs in the whole-solve kernel */
+int nlpf_problem_smem_bytes(const nlpf_problem* p);
+
 /* FP64 FMA throughput probe used for the roofline denominator (bench.py): runs `iters`
  * dependent-chain-free DFMA per thread on a full grid, returns FLOP count in *flops_out. */
 int nlpf_fp64_probe(int iters, double* sink_dev, double* flops_out, void* stream);

@@ -40,7 +40,8 @@ class COpts(ctypes.Structure):
 
 EXPORTS = ("nlpf_version", "nlpf_last_error", "nlpf_device_count", "nlpf_problem_create",
            "nlpf_problem_destroy", "nlpf_problem_nz", "nlpf_assemble", "nlpf_factor_solve", "nlpf_solve",
-           "nlpf_sample", "nlpf_ekf_run", "nlpf_ls_solve", "nlpf_ls_vel", "nlpf_fp64_probe")
+           "nlpf_sample", "nlpf_ekf_run", "nlpf_ls_solve", "nlpf_ls_vel", "nlpf_fp64_probe", "nlpf_blocktri_solve",
+           "nlpf_problem_smem_bytes")
 
 _lib = None
 
@@ -70,6 +71,7 @@ def lib():
                                ctypes.c_double, ctypes.c_double, vp, vp, vp]
     L.nlpf_ls_solve.argtypes = [ctypes.c_int, ctypes.c_int, vp, vp, vp, vp, vp, ctypes.c_int, ctypes.c_double, vp, vp]
     L.nlpf_ls_vel.argtypes = [ctypes.c_int, ctypes.c_int, vp, vp, vp, vp, vp, vp, vp]
+    L.nlpf_blocktri_solve.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int, vp, vp, vp, vp, vp, ctypes.c_int, vp]
     L.nlpf_fp64_probe.argtypes = [ctypes.c_int, vp, ctypes.POINTER(ctypes.c_double), vp]
     for name in EXPORTS:
         getattr(L, name)

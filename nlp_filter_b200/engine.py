@@ -236,6 +236,23 @@ def ls_vel(sat, satvel, prr, nsat, xpos):
     return out
 
 
+BLOCKTRI_RICCATI = 0
+BLOCKTRI_CYCLIC = 1
+
+
+def blocktri_solve(Dg, Lo, rhs, variant=BLOCKTRI_RICCATI):
+    """Solve B SPD block-tridiagonal systems.  Dg, Lo (B, nblk, bs, bs),
+    rhs (B, nblk, bs) -> x (B, nblk, bs), info (B,)."""
+    _require_cuda()
+    L = _capi.lib()
+    Dg, Lo, rhs = _f8(Dg), _f8(Lo), _f8(rhs)
+    B, nblk, bs = rhs.shape
+    x = torch.empty_like(rhs)
+    info = torch.empty((B,), dtype=torch.int32, device=rhs.device)
+    _capi.check(L.nlpf_blocktri_solve(B, nblk, bs, _ptr(Dg), _ptr(Lo), _ptr(rhs), _ptr(x), _ptr(info), int(variant), _stream()))
+    return x, info
+
+
 def fp64_peak_tflops(iters=20000, reps=5):
     """Measured FP64 FMA throughput of the current device (roofline denominator)."""
     _require_cuda()
