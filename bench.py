@@ -29,12 +29,16 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 # algorithmic flop per Gauss-Newton iteration and compulsory bytes per window
-FLOP_PER_ITER = {"vdp": 146480.0, "gnss": 297342.0}
-BYTES_PER_WINDOW = {"vdp": 2104.0 + 360.0, "gnss": 25184.0 + 464.0}
+FLOP_PER_ITER = {"vdp": 146480.0, "gnss": 297342.0, "ekf": 9178.0, "ls": 806.0}
+BYTES_PER_WINDOW = {"vdp": 2104.0 + 360.0, "gnss": 25184.0 + 464.0, "ekf": 448.0, "ls": 416.0}
 WORKLOAD_DESC = {
     "vdp": "van_der_pol MHE windows (K=21 nodes, n=2, m=1, 50 full-state epochs, Q=1e-2 I, nz=42)",
     "gnss": "stationary-receiver GNSS MHE windows (K=11, n=5, m=3, 51 epochs x 12 pseudoranges, nz=55)",
+    "ekf": "5-state GNSS EKF (utils/ekf.py + utils/gnss.py), 256 filters x 64 predict/update steps, 12 satellites",
+    "ls": "iterative GNSS least squares (utils/leastsquares.py:19-42), 16384 independent epochs x 12 satellites, ECEF",
 }
+METRIC = {"vdp": ("solved_windows_per_sec", "windows/s"), "gnss": ("solved_windows_per_sec", "windows/s"),
+          "ekf": ("ekf_steps_per_sec", "filter-steps/s"), "ls": ("ls_epochs_per_sec", "epochs/s")}
 
 
 def make_problem(workload):
@@ -135,30 +139,199 @@ class ClockSampler(object):
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
+
+# ---------------------------------------------------------------------------------------------
+# secondary workloads: fused EKF and GNSS least squares (row A11)
+# ---------------------------------------------------------------------------------------------
+def make_ekf_inputs(Bf=256, steps=64, S=12, seed=4001):
+    rng = np.random.default_rng(seed)
+    pos = rng.normal(0, 5.0, (Bf, 3))
+    b0, al = rng.uniform(-1e3, 1e3, Bf), rng.normal(-190, 20, Bf)
+    el = np.arcsin(rng.uniform(np.sin(np.deg2rad(10)), 1.0, (Bf, S)))
+    az = rng.uniform(0, 2 * np.pi, (Bf, S))
+    rad = rng.uniform(2.0e7, 2.6e7, (Bf, S))
+    s0 = np.stack([rad * np.cos(el) * np.sin(az), rad * np.cos(el) * np.cos(az), rad * np.sin(el)], 2)
+    t = np.arange(1, steps + 1)
+    sat = s0[:, None, :, :] + rng.normal(0, 1e3, (Bf, 1, S, 3)) * t[None, :, None, None]
+    z = np.linalg.norm(pos[:, None, None, :] - sat, axis=3) + b0[:, None, None] + al[:, None, None] * t[None, :, None] \
+        + rng.normal(0, 10.0, (Bf, steps, S))
+    x0 = np.concatenate([pos + rng.normal(0, 3, (Bf, 3)), (b0 + 5)[:, None], (al + 1)[:, None]], 1)
+    return dict(x0=x0, S0=np.tile(np.eye(5), (Bf, 1, 1)), u=np.zeros((Bf, steps, 3)), z=z, sat=sat,
+                nsat=np.full((Bf, steps), S, dtype=np.int32), Q=np.array([0.0001, 0.0001, 0.0001, 0.1, 0.001]))
+
+
+def make_ls_inputs(B=16384, S=12, seed=4002):
+    rng = np.random.default_rng(seed)
+    p_ref = np.array([-2699899.3380952473, -4292848.690053425, 3855186.0888884724])
+    rx = p_ref[None, :] + rng.normal(0, 50.0, (B, 3))
+    dirs = rng.normal(size=(B, S, 3)) + 1.5 * (p_ref / np.linalg.norm(p_ref))[None, None, :]
+    dirs /= np.linalg.norm(dirs, axis=2, keepdims=True)
+    sat = rx[:, None, :] + dirs * rng.uniform(2.0e7, 2.5e7, (B, S, 1))
+    pr = np.linalg.norm(sat - rx[:, None, :], axis=2) + rng.uniform(-1e3, 1e3, B)[:, None] + rng.normal(0, 3.0, (B, S))
+    return dict(sat=sat, pr=pr, nsat=np.full(B, S, dtype=np.int32))
+
+
+def _cpu_ekf(i):
+    from oracle import ekf_ls
+    e = _CPU["ekf"]
+    ekf_ls.ekf_run(0, e["x0"][i], e["S0"][i], e["u"][i], e["z"][i], e["sat"][i], e["nsat"][i], e["Q"], 100.0, 1.0)
+    return e["z"].shape[1]
+
+
+def _cpu_ls(i):
+    from oracle import ekf_ls
+    l = _CPU["ls"]
+    return ekf_ls.iterative_ls(l["sat"][i], l["pr"][i])[2]
+
+
+def cpu_aux_per_sec(workload, n_units, cores):
+    """CPU restatement (oracle/ekf_ls.py) of the EKF / LS workload on `cores` processes; returns units/s."""
+    ctx = mp.get_context("fork")
+    if workload == "ekf":
+        _CPU["ekf"] = make_ekf_inputs(Bf=n_units)
+        fn, per = _cpu_ekf, _CPU["ekf"]["z"].shape[1]
+    else:
+        _CPU["ls"] = make_ls_inputs(B=n_units)
+        fn, per = _cpu_ls, 1
+    with ctx.Pool(cores) as pool:
+        pool.map(fn, range(min(n_units, cores)))
+        t0 = time.perf_counter()
+        pool.map(fn, range(n_units), chunksize=max(1, n_units // (cores * 4)))
+        dt = time.perf_counter() - t0
+    return n_units * per / dt
+
+
+def run_aux(args):
+    """EKF / LS lines (single GPU): same JSON shape as the headline line."""
+    cores = os.cpu_count() or 1
+    cpu_base = None
+    if not args.no_cpu_baseline:
+        n = args.cpu_windows or (64 if args.workload == "ekf" else 2048)
+        v = cpu_aux_per_sec(args.workload, n, cores)
+        cpu_base = {"value": v, "unit": METRIC[args.workload][1], "cores": cores, "kind": "port",
+                    "sample": "%d %s of the same synthetic workload, NumPy restatement oracle/ekf_ls.py, %d-process pool"
+                              % (n, "filters x 64 steps" if args.workload == "ekf" else "epochs", cores)}
+    import torch
+    from nlp_filter_b200 import engine
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the hot path has no CPU fallback")
+    torch.cuda.set_device(0)
+    dev = lambda a: torch.as_tensor(np.ascontiguousarray(a)).cuda()
+    pin = lambda a: torch.as_tensor(np.ascontiguousarray(a)).pin_memory()
+    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device="cuda")
+    peak_fp64 = engine.fp64_peak_tflops()
+    if args.workload == "ekf":
+        e = make_ekf_inputs()
+        Bf, steps = e["z"].shape[:2]
+        units = Bf * steps
+        d = {k: dev(e[k]) for k in ("x0", "S0", "u", "z", "sat", "Q")}
+        nsat = dev(e["nsat"])
+        h = {k: pin(e[k]) for k in ("x0", "S0", "u", "z", "sat")}
+        mu, S = torch.empty_like(d["x0"]), torch.empty_like(d["S0"])
+        h_out = torch.empty((Bf, steps, 5), dtype=torch.float64).pin_memory()
+
+        def step_device():
+            mu.copy_(d["x0"]); S.copy_(d["S0"])
+            return engine.ekf_run(engine.EKF_GNSS5, mu, S, d["u"], d["z"], d["sat"], nsat, d["Q"], 100.0, 1.0)[2]
+
+        def step_e2e():
+            for k in ("x0", "S0", "u", "z", "sat"):
+                d[k].copy_(h[k], non_blocking=True)
+            h_out.copy_(step_device(), non_blocking=True)
+        h2d = sum(h[k].numel() * 8 for k in h)
+        d2h = h_out.numel() * 8
+        iters_mean = 1.0
+    else:
+        l = make_ls_inputs()
+        units = l["pr"].shape[0]
+        d = {k: dev(l[k]) for k in ("sat", "pr")}
+        nsat = dev(l["nsat"])
+        h = {k: pin(l[k]) for k in ("sat", "pr")}
+        h_out = torch.empty((units, 4), dtype=torch.float64).pin_memory()
+        last = {}
+
+        def step_device():
+            x, it = engine.ls_solve(d["sat"], d["pr"], nsat)
+            last["it"] = it
+            return x
+
+        def step_e2e():
+            for k in ("sat", "pr"):
+                d[k].copy_(h[k], non_blocking=True)
+            h_out.copy_(step_device(), non_blocking=True)
+        h2d = sum(h[k].numel() * 8 for k in h)
+        d2h = h_out.numel() * 8
+
+    def timed(fn):
+        for _ in range(args.warmup):
+            flush.zero_(); fn()
+        torch.cuda.synchronize()
+        evs = []
+        for _ in range(args.steps):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); fn(); e1.record()
+            evs.append((e0, e1))
+        torch.cuda.synchronize()
+        return sum(a.elapsed_time(b) for a, b in evs)
+
+    sampler = ClockSampler(0)
+    sampler.start()
+    ms_dev = timed(step_device)
+    ms_e2e = timed(step_e2e)
+    clocks = sampler.stop()
+    if args.workload == "ls":
+        iters_mean = float(last["it"].to(torch.float64).mean().item())
+    ms_kernel = ms_dev / args.steps
+    flops = FLOP_PER_ITER[args.workload] * iters_mean * units
+    achieved = flops / (ms_kernel * 1e-3) / 1e12
+    metric, unit = METRIC[args.workload]
+    line = {"metric": metric, "value": units * args.steps / (ms_dev * 1e-3), "unit": unit, "n_gpus": 1, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": WORKLOAD_DESC[args.workload], "units_per_step": units,
+                       "l2": "256 MB buffer written between timed iterations", "mean_iterations": iters_mean},
+            "e2e": {"value": units * args.steps / (ms_e2e * 1e-3), "unit": unit, "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": args.steps,
+            "roofline": {"bound": "fp64", "kernel": "ekf_kernel" if args.workload == "ekf" else "ls_kernel<4>",
+                         "achieved": achieved, "peak": peak_fp64, "unit": "TFLOP/s", "frac": achieved / peak_fp64,
+                         "traffic": None, "kernel_ms": ms_kernel,
+                         "peak_source": "FP64 FMA probe measured in this run",
+                         "note": "latency-bound at this batch size (%d units): launch + dependent chains" % units},
+            "clocks": clocks}
+    if cpu_base is not None:
+        line["cpu_baseline"] = cpu_base
+    print(json.dumps(line))
+    return 0
+
 # ---------------------------------------------------------------------------------------------
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
     cores = os.cpu_count() or 1
-    n = args.cpu_windows or (256 if args.workload == "vdp" else 64)
+    n = args.cpu_windows or {"vdp": 256, "gnss": 64, "ekf": 64, "ls": 2048}[args.workload]
     vals = []
     for s in range(args.warmup + args.steps):
         t0 = time.perf_counter()
-        v, it = cpu_path_windows_per_sec(args.workload, n, cores, seed=2000 + s)
+        if args.workload in ("ekf", "ls"):
+            v, it = cpu_aux_per_sec(args.workload, n, cores), 0.0
+        else:
+            v, it = cpu_path_windows_per_sec(args.workload, n, cores, seed=2000 + s)
         if s >= args.warmup:
             vals.append((v, time.perf_counter() - t0, it))
     value = float(np.mean([v[0] for v in vals]))
     line = {
-        "impl": "reference", "metric": "solved_windows_per_sec", "value": value, "unit": "windows/s",
+        "impl": "reference", "metric": METRIC[args.workload][0], "value": value, "unit": METRIC[args.workload][1],
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * n / value, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
         "config": {"workload": WORKLOAD_DESC[args.workload], "windows_per_step": n},
-        "cpu_baseline": {"value": value, "unit": "windows/s", "cores": cores, "kind": "port",
-                         "sample": "%d windows per step of the same synthetic workload, NumPy restatement "
+        "cpu_baseline": {"value": value, "unit": METRIC[args.workload][1], "cores": cores, "kind": "port",
+                         "sample": "%d units per step of the same synthetic workload, NumPy restatement "
                                    "(oracle/nls.py) in a %d-process pool; CasADi/IPOPT not installable" % (n, cores)},
-        "e2e": {"value": value, "unit": "windows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "e2e": {"value": value, "unit": METRIC[args.workload][1], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
     return 0
@@ -324,7 +497,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="vdp", choices=["vdp", "gnss"])
+    ap.add_argument("--workload", default="vdp", choices=["vdp", "gnss", "ekf", "ls"])
     ap.add_argument("--windows", type=int, default=4096, help="windows per GPU per step")
     ap.add_argument("--cpu-windows", type=int, default=0, help="size of the CPU-path sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -332,6 +505,8 @@ def main():
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
         return run_reference(args)
+    if args.workload in ("ekf", "ls"):
+        return run_aux(args)
     return run_ours(args)
 
 

@@ -1,0 +1,100 @@
+"""BASELINE.json-size batches (4096 windows, 16384 LS epochs, 256 x 64 EKF steps) checked through
+size-independent properties: every window converges, re-solving from the solution is a fixed
+point, results do not depend on the window's position in the batch, the gradient vanishes at
+the returned point; plus oracle parity on a random subset."""
+import numpy as np
+import pytest
+
+from nlp_filter_b200 import shapes, synth
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("workload", ["vdp", "gnss"])
+def test_4096_windows_properties(workload):
+    import torch
+    from nlp_filter_b200 import engine
+    from oracle import nls
+    B = 4096
+    d = shapes.vdp_mhe() if workload == "vdp" else shapes.gnss()
+    bt = synth.vdp_mhe_batch(d, B, seed=2000) if workload == "vdp" else synth.gnss_batch(d, B, seed=3000)
+    prob = engine.WindowProblem(d)
+    z, J, iters, status = engine.solve_windows_host(prob, bt["z0"], bt["U"], bt["data"])
+    assert np.all(status <= 1), np.bincount(status)                 # every window solved
+    assert np.all(np.isfinite(z)) and np.max(iters) <= 60
+    # fixed point: restarting at the solution moves nothing
+    z2, J2, it2, st2 = engine.solve_windows_host(prob, z, bt["U"], bt["data"])
+    assert np.max(np.abs(z2 - z) / (1 + np.abs(z))) < 1e-8 and np.max(it2) <= 6
+    # stationarity: the gradient at the solution is at rounding level relative to its start value
+    _, g0, _ = prob.assemble(bt["z0"][:256], bt["U"][:256], bt["data"][:256])
+    _, g1, _ = prob.assemble(z[:256], bt["U"][:256], bt["data"][:256])
+    assert float(g1.abs().max()) < 1e-7 * float(g0.abs().max())
+    # position independence: a permuted batch gives bit-identical per-window results
+    perm = np.random.default_rng(0).permutation(B)
+    zp, Jp, _, _ = engine.solve_windows_host(prob, bt["z0"][perm], bt["U"][perm], bt["data"][perm])
+    assert np.array_equal(zp, z[perm]) and np.array_equal(Jp, J[perm])
+    # oracle parity on a random subset
+    for b in np.random.default_rng(1).choice(B, 12, replace=False):
+        zo, info = nls.solve(d, nls.Window(d, U=bt["U"][b], data=bt["data"][b]), bt["z0"][b])
+        assert np.max(np.abs(z[b] - zo) / (1 + np.abs(zo))) < 1e-6
+        if workload == "gnss":
+            assert np.max(np.abs(z[b].reshape(d.K, 5)[:, :3] - zo.reshape(d.K, 5)[:, :3])) < 1e-3     # 1 mm
+    prob.close()
+
+
+def test_16384_ls_epochs_properties():
+    """LS: solution is a fixed point of one more Gauss-Newton step and is translation-covariant."""
+    from nlp_filter_b200 import engine
+    from oracle import ekf_ls
+    rng = np.random.default_rng(5)
+    B, S = 16384, 12
+    p_ref = np.array([-2699899.3380952473, -4292848.690053425, 3855186.0888884724])
+    rx = p_ref[None, :] + rng.normal(0, 50.0, (B, 3))
+    dirs = rng.normal(size=(B, S, 3)) + 1.5 * (p_ref / np.linalg.norm(p_ref))[None, None, :]
+    dirs /= np.linalg.norm(dirs, axis=2, keepdims=True)
+    sat = rx[:, None, :] + dirs * rng.uniform(2.0e7, 2.5e7, (B, S, 1))
+    bias = rng.uniform(-1e3, 1e3, B)
+    pr = np.linalg.norm(sat - rx[:, None, :], axis=2) + bias[:, None] + rng.normal(0, 3.0, (B, S))
+    nsat = rng.integers(6, S + 1, B).astype(np.int32)
+    x, it = engine.ls_solve(sat, pr, nsat)
+    x, it = x.cpu().numpy(), it.cpu().numpy()
+    assert np.all(it <= 20) and np.all(np.isfinite(x)), (it.max(), np.isfinite(x).all())
+    assert np.median(np.linalg.norm(x[:, :3] - rx, axis=1)) < 15.0      # metres: 3 m range noise times the geometry factor
+    x2, it2 = engine.ls_solve(sat, pr, nsat, x0=x)                    # warm restart: converged already
+    assert np.max(np.abs(x2.cpu().numpy() - x)) < 1e-6 and np.all(it2.cpu().numpy() <= 3)
+    shift = np.array([1000.0, -2000.0, 500.0])                        # translate the whole geometry
+    xs, _ = engine.ls_solve(sat + shift, pr, nsat)
+    assert np.max(np.abs(xs.cpu().numpy()[:, :3] - (x[:, :3] + shift))) < 1e-5
+    for b in rng.choice(B, 16, replace=False):
+        xo, bo, _ = ekf_ls.iterative_ls(sat[b, :nsat[b]], pr[b, :nsat[b]])
+        assert np.max(np.abs(x[b] - np.append(xo, bo)) / (1 + np.abs(x[b]))) < 1e-9
+
+
+def test_256_filters_64_steps_against_oracle_subset():
+    from nlp_filter_b200 import engine
+    from oracle import ekf_ls
+    rng = np.random.default_rng(6)
+    Bf, steps, S = 256, 64, 12
+    Q = np.array([0.0001, 0.0001, 0.0001, 0.1, 0.001])
+    pos = rng.normal(0, 5.0, (Bf, 3))
+    b0, al = rng.uniform(-1e3, 1e3, Bf), rng.normal(-190, 20, Bf)
+    el = np.arcsin(rng.uniform(np.sin(np.deg2rad(10)), 1.0, (Bf, S)))
+    az = rng.uniform(0, 2 * np.pi, (Bf, S))
+    rad = rng.uniform(2.0e7, 2.6e7, (Bf, S))
+    s0 = np.stack([rad * np.cos(el) * np.sin(az), rad * np.cos(el) * np.cos(az), rad * np.sin(el)], 2)
+    t = np.arange(1, steps + 1)
+    sat = s0[:, None, :, :] + rng.normal(0, 1e3, (Bf, 1, S, 3)) * t[None, :, None, None]
+    z = np.linalg.norm(pos[:, None, None, :] - sat, axis=3) + b0[:, None, None] + al[:, None, None] * t[None, :, None] \
+        + rng.normal(0, 10.0, (Bf, steps, S))
+    nsat = rng.integers(4, S + 1, (Bf, steps)).astype(np.int32)
+    nsat[:, ::7] = 0                                                  # predict-only steps (ekf.py:32-38)
+    x0 = np.concatenate([pos + rng.normal(0, 3, (Bf, 3)), (b0 + 5)[:, None], (al + 1)[:, None]], 1)
+    u = np.zeros((Bf, steps, 3))
+    mu, S_, traj = engine.ekf_run(engine.EKF_GNSS5, x0, np.tile(np.eye(5), (Bf, 1, 1)), u, z, sat, nsat, Q, 100.0, 1.0)
+    traj = traj.cpu().numpy()
+    assert np.all(np.isfinite(traj))
+    assert np.median(np.linalg.norm(traj[:, -1, :3] - pos, axis=1)) < 5.0
+    for b in rng.choice(Bf, 8, replace=False):
+        ref, Sref = ekf_ls.ekf_run(0, x0[b], np.eye(5), u[b], z[b], sat[b], nsat[b], Q, 100.0, 1.0)
+        assert np.max(np.abs(traj[b] - ref) / (1 + np.abs(ref))) < 1e-9
+        assert np.max(np.abs(S_.cpu().numpy()[b] - Sref)) < 1e-9
