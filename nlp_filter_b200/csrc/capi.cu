@@ -6,6 +6,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -24,14 +25,19 @@ int nlpf_check_cuda(cudaError_t e, const char* what) {
     return NLPF_E_CUDA;
 }
 
-extern "C" int nlpf_launch_assemble(nlpf_problem*, int, const double*, const double*, const double*, const double*,
-                                    const double*, double, double*, double*, double*, cudaStream_t);
+extern "C" int nlpf_launch_assemble_gen(nlpf_problem*, int, const double*, const double*, const double*, const double*,
+                                        const double*, double, double*, double*, double*, cudaStream_t);
+extern "C" int nlpf_launch_assemble_pr(nlpf_problem*, int, const double*, const double*, const double*, const double*,
+                                       const double*, double, double*, double*, double*, cudaStream_t);
 extern "C" int nlpf_launch_factor_solve(nlpf_problem*, int, const double*, const double*, double, double*, int*,
                                         cudaStream_t);
-extern "C" int nlpf_launch_solve(nlpf_problem*, int, double*, const double*, const double*, const double*,
-                                 const double*, const nlpf_opts*, double*, int*, int*, double*, cudaStream_t);
+extern "C" int nlpf_launch_solve_gen(nlpf_problem*, int, double*, const double*, const double*, const double*,
+                                     const double*, const nlpf_opts*, double*, int*, int*, double*, cudaStream_t);
+extern "C" int nlpf_launch_solve_pr(nlpf_problem*, int, double*, const double*, const double*, const double*,
+                                    const double*, const nlpf_opts*, double*, int*, int*, double*, cudaStream_t);
 extern "C" int nlpf_launch_sample(nlpf_problem*, int, const double*, int, const double*, double*, cudaStream_t);
-extern "C" int nlpf_set_smem_attrs(size_t bytes);
+extern "C" int nlpf_set_smem_attrs_gen(size_t bytes);
+extern "C" int nlpf_set_smem_attrs_pr(size_t bytes);
 
 extern "C" int nlpf_version(void) { return NLPF_VERSION; }
 extern "C" const char* nlpf_last_error(void) { return g_err; }
@@ -160,7 +166,16 @@ extern "C" int nlpf_problem_create(const nlpf_desc* D, nlpf_problem** out) {
             nlpf_set_error("residual %d: range dimension must be 1..3", i); delete p; return NLPF_E_ARG;
         }
     }
-    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return D->repoch[a] < D->repoch[b]; });
+    // order: by epoch; inside an epoch pseudoranges first, grouped by their index quadruple (runs), then the rest
+    auto key = [&](int i, int s) { return D->rtype[i] == NLPF_RT_PR ? D->cmap[D->ridx[i * NLPF_NIDX + s]] : 0; };
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) {
+        if (D->repoch[a] != D->repoch[b]) return D->repoch[a] < D->repoch[b];
+        const int pa = D->rtype[a] == NLPF_RT_PR ? 0 : 1, pb = D->rtype[b] == NLPF_RT_PR ? 0 : 1;
+        if (pa != pb) return pa < pb;
+        if (pa == 1) return false;
+        for (int s = 0; s < 4; ++s) if (key(a, s) != key(b, s)) return key(a, s) < key(b, s);
+        return false;
+    });
     std::vector<int> colact(nv, 0);
     for (int i = 0; i < M; ++i) {
         int is_state[NLPF_NIDX], is_glob[NLPF_NIDX];
@@ -199,6 +214,25 @@ extern "C" int nlpf_problem_create(const nlpf_desc* D, nlpf_problem** out) {
         }
     }
     for (int e = 0; e < E; ++e) estart[e + 1] += estart[e];
+    // pseudorange runs per epoch
+    std::vector<int> gstart(E > 0 ? E : 1, 0), erun(E + 1, 0), run_start, run_len, run_loc;
+    for (int e = 0; e < E; ++e) {
+        erun[e] = (int)run_start.size();
+        int r = estart[e];
+        while (r < estart[e + 1] && rtype_s[r] == NLPF_RT_PR) {
+            int r2 = r + 1;
+            while (r2 < estart[e + 1] && rtype_s[r2] == NLPF_RT_PR &&
+                   std::equal(rloc_s.begin() + (size_t)r * NLPF_NIDX, rloc_s.begin() + (size_t)r * NLPF_NIDX + 4,
+                              rloc_s.begin() + (size_t)r2 * NLPF_NIDX)) ++r2;
+            run_start.push_back(r); run_len.push_back(r2 - r);
+            for (int s4 = 0; s4 < 4; ++s4) run_loc.push_back(rloc_s[(size_t)r * NLPF_NIDX + s4]);
+            r = r2;
+        }
+        gstart[e] = r;
+    }
+    erun[E] = (int)run_start.size();
+    p->use_pr = run_start.empty() ? 0 : 1;       // which instantiation of the window kernels serves this class
+    if (run_start.empty()) { run_start.push_back(0); run_len.push_back(0); run_loc.assign(4, 0); }
     // epochs per chunk: keep the per-chunk scratch (Ve, G, q) near 8 KB
     {
         const int per = P.nat * P.nat + P.nat + (na > 0 ? na : 1);
@@ -281,7 +315,8 @@ extern "C" int nlpf_problem_create(const nlpf_desc* D, nlpf_problem** out) {
                  obl = B.add(D->blo, sizeof(double) * D->nb), obh = B.add(D->bhi, sizeof(double) * D->nb),
                  oPh = B.add(D->Phi, sizeof(double) * E * K), ort = B.addv(rtype_s), orl = B.addv(rloc_s),
                  oro = B.addv(roff_s), oes = B.addv(estart), oac = B.addv(act), oHc = B.addv(Hc), oFc = B.addv(Fc),
-                 otb = B.addv(tab), opt = B.addv(ptab), osg = B.addv(seg_tab), osc = B.addv(seg_cnt);
+                 otb = B.addv(tab), opt = B.addv(ptab), osg = B.addv(seg_tab), osc = B.addv(seg_cnt),
+                 ogs = B.addv(gstart), oer = B.addv(erun), ors = B.addv(run_start), orn = B.addv(run_len), orc = B.addv(run_loc);
     B.add(zero1.data(), 16);
     p->blob_bytes = B.host.size();
     cudaGetDevice(&p->device);
@@ -299,6 +334,8 @@ extern "C" int nlpf_problem_create(const nlpf_desc* D, nlpf_problem** out) {
     P.estart = (const int*)(base + oes); P.act = (const int*)(base + oac); P.Hc = (const double*)(base + oHc);
     P.Fc = (const double*)(base + oFc); P.tab = (const uint32_t*)(base + otb); P.ptab = (const uint16_t*)(base + opt);
     P.seg_tab = (const uint16_t*)(base + osg); P.seg_cnt = (const int*)(base + osc);
+    P.gstart = (const int*)(base + ogs); P.erun = (const int*)(base + oer); P.run_start = (const int*)(base + ors);
+    P.run_len = (const int*)(base + orn); P.run_loc = (const int*)(base + orc);
 
     // ---- shared-memory layout (doubles) ----
     int o = 0;
@@ -313,8 +350,12 @@ extern "C" int nlpf_problem_create(const nlpf_desc* D, nlpf_problem** out) {
     P.o_Ve = take(P.ec * (na > 0 ? na : 1));
     P.o_G = take(P.ec * P.nat * P.nat);
     P.o_q = take(P.ec * P.nat);
-    P.o_Phi = take(E * K);
-    P.o_Dt = take(K * K);
+    {   // class constants staged in shared memory (default) or read through L1 (NLPF_CONST_SMEM=0: experiments)
+        const char* ev = getenv("NLPF_CONST_SMEM");
+        P.const_smem = ev ? atoi(ev) : 1;
+    }
+    P.o_Phi = take(P.const_smem ? E * K : 0);
+    P.o_Dt = take(P.const_smem ? K * K : 0);
     P.o_red = take(8);
     P.smem_doubles = o;
     p->smem_bytes = (size_t)o * sizeof(double);
@@ -322,7 +363,7 @@ extern "C" int nlpf_problem_create(const nlpf_desc* D, nlpf_problem** out) {
         nlpf_set_error("problem needs %zu bytes of shared memory per window (limit 232448)", p->smem_bytes);
         cudaFree(p->blob); delete p; return NLPF_E_ARG;
     }
-    if (nlpf_set_smem_attrs(227 * 1024) != NLPF_OK) { cudaFree(p->blob); delete p; return NLPF_E_CUDA; }
+    if (nlpf_set_smem_attrs_gen(227 * 1024) != NLPF_OK || nlpf_set_smem_attrs_pr(227 * 1024) != NLPF_OK) { cudaFree(p->blob); delete p; return NLPF_E_CUDA; }
     *out = p;
     return NLPF_OK;
 }
@@ -352,7 +393,7 @@ extern "C" int nlpf_assemble(nlpf_problem* p, int B, const double* z, const doub
     int rc = check_batch(p, B, z, data);
     if (rc) return rc;
     if (!H_out || !g_out || !cost_out) { nlpf_set_error("null output buffer"); return NLPF_E_ARG; }
-    return nlpf_launch_assemble(p, B, z, U, data, xprior, wshift, mu, H_out, g_out, cost_out, (cudaStream_t)stream);
+    return (p->use_pr ? nlpf_launch_assemble_pr : nlpf_launch_assemble_gen)(p, B, z, U, data, xprior, wshift, mu, H_out, g_out, cost_out, (cudaStream_t)stream);
 }
 
 extern "C" int nlpf_factor_solve(nlpf_problem* p, int B, const double* H, const double* g, double lam, double* dz_out,
@@ -377,7 +418,7 @@ extern "C" int nlpf_solve(nlpf_problem* p, int B, double* z, const double* U, co
         }
         hlin = p->scratch;
     }
-    return nlpf_launch_solve(p, B, z, U, data, xprior, wshift, opts, cost_out, iters_out, status_out, hlin, (cudaStream_t)stream);
+    return (p->use_pr ? nlpf_launch_solve_pr : nlpf_launch_solve_gen)(p, B, z, U, data, xprior, wshift, opts, cost_out, iters_out, status_out, hlin, (cudaStream_t)stream);
 }
 
 extern "C" int nlpf_sample(nlpf_problem* p, int B, const double* z, int nt, const double* PhiT, double* out, void* stream) {

@@ -6,7 +6,9 @@
 
 #define NLPF_NT 128            // threads per window CTA (4 warps: one per SM sub-partition)
 #define NLPF_NW (NLPF_NT / 32)
+#ifndef NLPF_MIN_CTAS
 #define NLPF_MIN_CTAS 8        // register cap 64/thread: 8 windows resident per SM (ncu: 128 regs limited it to 4)
+#endif
 #define NLPF_NA_MAX 8          // active node-variable components a measurement set may touch
 #define NLPF_NG_MAX 8
 #define NLPF_N_MAX 12
@@ -19,6 +21,7 @@
 struct DevProb {
     int K, n, m, nv, ng, nz, np;      // np = packed lower-triangle size nz(nz+1)/2
     int dyn_id, loss, has_prior, has_dyncost, has_nodecost;
+    int const_smem;                   // 1: Phi and Dt staged in shared memory, 0: read through L1
     int lin_meas;                     // 1: every residual is RT_STATE: its H contribution is constant per window
     int hconst;                       // 1: the dynamics part of H is constant (L2 loss, affine model)
     int fconst;                       // 1: dF/dv is constant (affine model)
@@ -47,6 +50,11 @@ struct DevProb {
     const int* rloc;                  // M*8 local indices: <na active comp, >=na global, -1 unused
     const int* roff;                  // M
     const int* estart;                // E+1
+    const int* gstart;                // E    first residual of epoch e that is not part of a pseudorange run
+    const int* erun;                  // E+1  runs of epoch e: [erun[e], erun[e+1])
+    const int* run_start;             // nrun first residual of the run
+    const int* run_len;               // nrun
+    const int* run_loc;               // nrun*4 local indices x,y,z,b shared by the run
     const int* act;                   // na  -> node-variable column
     const double* Hc;                 // np  constant part of H (packed lower, row-major)
     const double* Fc;                 // n*nv constant dF/dv (affine models)
@@ -66,6 +74,7 @@ struct nlpf_problem {
     size_t scratch_doubles;
     size_t blob_bytes;
     size_t smem_bytes;
+    int use_pr;          // 1: problem has pseudorange runs -> *_pr kernels
     int device;
 };
 

@@ -16,6 +16,21 @@
 #include "common.cuh"
 #include <math.h>
 
+// This file is compiled twice (nls_kernels_gen.cu, nls_kernels_pr.cu): NLPF_PR_RUNS = 1 adds the
+// lane-group / register-accumulation path for pseudorange runs.  Keeping it out of the other
+// instantiation matters: with the 64-register cap its 14 accumulators cost the van der Pol
+// kernel 21 % (measured) although that problem class has no pseudoranges at all.
+#ifndef NLPF_PR_RUNS
+#error "include through nls_kernels_gen.cu / nls_kernels_pr.cu"
+#endif
+#if NLPF_PR_RUNS
+#define VN(name) name##_pr
+#else
+#define VN(name) name##_gen
+#endif
+
+namespace VN(nlpf_ns) {      // both instantiations define the same helper names
+
 // ------------------------------------------------------------------------------------------
 // block-wide reductions; every thread returns the same value (same summation order)
 // ------------------------------------------------------------------------------------------
@@ -377,8 +392,8 @@ __device__ void eval_window(const DevProb& P, double* sm, const double* zc, cons
     double* Ve = sm + P.o_Ve;
     double* G = sm + P.o_G;
     double* q = sm + P.o_q;
-    const double* Phi = sm + P.o_Phi;
-    const double* Dt = sm + P.o_Dt;
+    const double* Phi = P.const_smem ? sm + P.o_Phi : P.Phi;
+    const double* Dt = P.const_smem ? sm + P.o_Dt : P.Dt;
     double* red = sm + P.o_red;
     const bool dyn_h = FULL && !P.hconst;            // H has a state-dependent dynamics part
     const bool need_F = dyn_h;                       // ... which needs dF/dv per node in shared memory
@@ -544,7 +559,113 @@ __device__ void eval_window(const DevProb& P, double* sm, const double* zc, cons
             for (int t = tid; t < ne * nat; t += NLPF_NT) q[t] = 0.0;
         }
         __syncthreads();
-        for (int el = tid; el < ne; el += NLPF_NT) {
+#if NLPF_PR_RUNS
+        // Residuals of the chunk.  A group of LG lanes shares one epoch: pseudorange "runs" (consecutive
+        // RT_PR residuals with the same index quadruple -- the bulk of every GNSS problem) are split
+        // over the lanes, accumulated in registers (4 gradient + 10 outer-product values) and
+        // combined with LG-wide shuffles; the lane that owns the epoch adds them to G_e / q_e.
+        // (ncu, thread-per-epoch version: 24 % of the GNSS kernel's samples waited at the barrier
+        // behind 42 busy threads of 128.)  Other residual types go through meas_eval on the owner lane.
+        {
+            const int LG = (ne <= NLPF_NT / 4) ? 4 : ((ne <= NLPF_NT / 2) ? 2 : 1);
+            const int sub = tid & (LG - 1);
+            const int ngrp = NLPF_NT / LG;
+            for (int el0 = 0; el0 < ne; el0 += ngrp) {
+                const int el = el0 + tid / LG;
+                const bool live = el < ne;                      // whole groups are live or not (shuffles stay converged)
+                const double* xe = Ve + (live ? el : 0) * na;
+                double* Ge = G + (live ? el : 0) * nat * nat;
+                double* qe = q + (live ? el : 0) * nat;
+                const int e = c0 + (live ? el : 0);
+                const int rbeg = live ? P.erun[e] : 0;
+                const int nr = live ? P.erun[e + 1] - rbeg : 0;
+                int nrmax = nr;                                 // same trip count for the whole warp: the shuffles
+                for (int o = 16; o > 0; o >>= 1) nrmax = max(nrmax, __shfl_xor_sync(0xffffffffu, nrmax, o));   // below need it converged
+                for (int kr = 0; kr < nrmax; ++kr) {
+                    const bool act = kr < nr;
+                    const int rn = rbeg + (act ? kr : 0);
+                    const int i0 = act ? P.run_start[rn] : 0, i1 = act ? i0 + P.run_len[rn] : 0;
+                    const int l0 = act ? P.run_loc[4 * rn] : 0, l1 = act ? P.run_loc[4 * rn + 1] : 0;
+                    const int l2 = act ? P.run_loc[4 * rn + 2] : 0, l3 = act ? P.run_loc[4 * rn + 3] : 0;
+                    const double x0 = lval(l0, xe, glob, na), x1 = lval(l1, xe, glob, na), x2 = lval(l2, xe, glob, na);
+                    const double xb = lval(l3, xe, glob, na);
+                    double a0 = 0, a1 = 0, a2 = 0, a3 = 0;                       // sum w r grad
+                    double g00 = 0, g10 = 0, g11 = 0, g20 = 0, g21 = 0, g22 = 0, g30 = 0, g31 = 0, g32 = 0, g33 = 0;
+                    for (int i = i0 + sub; i < i1; i += LG) {
+                        const double* rec = wp.data + P.roff[i];
+                        const double w = rec[1];
+                        if (w == 0.0) continue;                 // masked slot: skipped, never 0 * NaN
+                        const double d0 = x0 - rec[2], d1 = x1 - rec[3], d2 = x2 - rec[4];
+                        const double rho = sqrt(d0 * d0 + d1 * d1 + d2 * d2);
+                        const double r = rec[0] - (rho + xb);
+                        cost += w * r * r;
+                        nse += 2.0 * w * fabs(r) * (2.0 * fabs(rec[0]) + fabs(r));
+                        if (FULL) {
+                            const double ir = 1.0 / rho;
+                            const double e0 = d0 * ir, e1 = d1 * ir, e2 = d2 * ir;
+                            const double wr = w * r;
+                            a0 = fma(wr, e0, a0); a1 = fma(wr, e1, a1); a2 = fma(wr, e2, a2); a3 += wr;
+                            if (accH) {
+                                const double w0 = w * e0, w1 = w * e1, w2 = w * e2;
+                                g00 = fma(w0, e0, g00); g10 = fma(w1, e0, g10); g11 = fma(w1, e1, g11);
+                                g20 = fma(w2, e0, g20); g21 = fma(w2, e1, g21); g22 = fma(w2, e2, g22);
+                                g30 += w0; g31 += w1; g32 += w2; g33 += w;
+                            }
+                        }
+                    }
+                    if (FULL) {
+                        for (int o = LG >> 1; o > 0; o >>= 1) {
+                            a0 += __shfl_xor_sync(0xffffffffu, a0, o); a1 += __shfl_xor_sync(0xffffffffu, a1, o);
+                            a2 += __shfl_xor_sync(0xffffffffu, a2, o); a3 += __shfl_xor_sync(0xffffffffu, a3, o);
+                            if (accH) {
+                                g00 += __shfl_xor_sync(0xffffffffu, g00, o); g10 += __shfl_xor_sync(0xffffffffu, g10, o);
+                                g11 += __shfl_xor_sync(0xffffffffu, g11, o); g20 += __shfl_xor_sync(0xffffffffu, g20, o);
+                                g21 += __shfl_xor_sync(0xffffffffu, g21, o); g22 += __shfl_xor_sync(0xffffffffu, g22, o);
+                                g30 += __shfl_xor_sync(0xffffffffu, g30, o); g31 += __shfl_xor_sync(0xffffffffu, g31, o);
+                                g32 += __shfl_xor_sync(0xffffffffu, g32, o); g33 += __shfl_xor_sync(0xffffffffu, g33, o);
+                            }
+                        }
+                        if (sub == 0 && act) {
+                            qe[l0] += a0; qe[l1] += a1; qe[l2] += a2; qe[l3] += a3;
+                            if (accH) {
+                                // symmetric 4x4 block scattered to (l_p, l_q); += so that coinciding indices add up
+                                Ge[l0 * nat + l0] += g00;
+                                Ge[l1 * nat + l0] += g10; Ge[l0 * nat + l1] += g10; Ge[l1 * nat + l1] += g11;
+                                Ge[l2 * nat + l0] += g20; Ge[l0 * nat + l2] += g20; Ge[l2 * nat + l1] += g21; Ge[l1 * nat + l2] += g21;
+                                Ge[l2 * nat + l2] += g22;
+                                Ge[l3 * nat + l0] += g30; Ge[l0 * nat + l3] += g30; Ge[l3 * nat + l1] += g31; Ge[l1 * nat + l3] += g31;
+                                Ge[l3 * nat + l2] += g32; Ge[l2 * nat + l3] += g32; Ge[l3 * nat + l3] += g33;
+                            }
+                        }
+                    }
+                }
+                if (sub == 0 && live) {          // residuals of other types: owner lane, general path
+                    const int i1 = P.estart[e + 1];
+                    for (int i = P.gstart[e]; i < i1; ++i) {
+                        const double* rec = wp.data + P.roff[i];
+                        const double w = rec[1];
+                        if (w == 0.0) continue;
+                        int gl[8];
+                        double gv[8];
+                        double h;
+                        const int nn = meas_eval(P.rtype[i], P.rloc + i * NLPF_NIDX, rec, xe, glob, na, h, gl, gv);
+                        const double r = rec[0] - h;
+                        cost += w * r * r;
+                        nse += 2.0 * w * fabs(r) * (2.0 * fabs(rec[0]) + fabs(r));
+                        if (FULL) {
+                            for (int p = 0; p < nn; ++p) {
+                                const double wg = w * gv[p];
+                                qe[gl[p]] = fma(wg, r, qe[gl[p]]);
+                                if (accH)
+                                    for (int p2 = 0; p2 < nn; ++p2) Ge[gl[p] * nat + gl[p2]] = fma(wg, gv[p2], Ge[gl[p] * nat + gl[p2]]);
+                            }
+                        }
+                    }
+                }
+            }
+        }
+#else
+        for (int el = tid; el < ne; el += NLPF_NT) {          // thread per epoch, every residual through meas_eval
             const double* xe = Ve + el * na;
             double* Ge = G + el * nat * nat;
             double* qe = q + el * nat;
@@ -570,6 +691,7 @@ __device__ void eval_window(const DevProb& P, double* sm, const double* zc, cons
                 }
             }
         }
+#endif
         if (FULL) {
             __syncthreads();
             // node-node blocks: H[(j,a),(l,b)] += sum_e phi_ej phi_el G_e[a][b]
@@ -814,6 +936,7 @@ __device__ bool ldl_solve(const DevProb& P, int nz, double* Hp, double* xs) {
 // shared-memory staging common to the kernels
 // ------------------------------------------------------------------------------------------
 __device__ void stage_constants(const DevProb& P, double* sm) {
+    if (!P.const_smem) return;
     for (int i = threadIdx.x; i < P.E * P.K; i += NLPF_NT) sm[P.o_Phi + i] = P.Phi[i];
     for (int i = threadIdx.x; i < P.K * P.K; i += NLPF_NT) sm[P.o_Dt + i] = P.Dt[i];
 }
@@ -833,7 +956,7 @@ __device__ __forceinline__ WinPtr window_ptrs(const DevProb& P, int b, const dou
 // nlpf_assemble: evaluation only (tests, ncu)
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(NLPF_NT)
-assemble_kernel(DevProb P, int B, const double* __restrict__ z, const double* __restrict__ U,
+VN(assemble_kernel)(DevProb P, int B, const double* __restrict__ z, const double* __restrict__ U,
                 const double* __restrict__ data, const double* __restrict__ xprior,
                 const double* __restrict__ wshift, double mu, double* __restrict__ H_out,
                 double* __restrict__ g_out, double* __restrict__ cost_out) {
@@ -861,6 +984,7 @@ assemble_kernel(DevProb P, int B, const double* __restrict__ z, const double* __
     }
 }
 
+#if !NLPF_PR_RUNS
 // ------------------------------------------------------------------------------------------
 // nlpf_factor_solve: kernel (3) alone
 // ------------------------------------------------------------------------------------------
@@ -891,13 +1015,15 @@ factor_solve_kernel(DevProb P, int B, const double* __restrict__ H, const double
     }
 }
 
+#endif
+
 // Hc + sum_e (phi_e phi_e^T) (x) diag(w_e) of one window whose residuals are all RT_STATE: constant
 // over the iterations, written once to the window's slot of the scratch buffer.
 __device__ void build_hlin(const DevProb& P, double* sm, const WinPtr& wp) {
     const int tid = threadIdx.x;
     const int K = P.K, nv = P.nv, na = P.na;
     double* Hp = sm + P.o_H;
-    const double* Phi = sm + P.o_Phi;
+    const double* Phi = P.const_smem ? sm + P.o_Phi : P.Phi;
     double* wacc = sm + P.o_G;                   // E chunk x na weights
     for (int p = tid; p < P.np; p += NLPF_NT) Hp[p] = P.Hc[p];
     for (int c0 = 0; c0 < P.E; c0 += P.ec) {
@@ -929,7 +1055,7 @@ __device__ void build_hlin(const DevProb& P, double* sm, const WinPtr& wp) {
 // Same decisions, in the same order, as oracle/nls.py:solve (the CPU checker).
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(NLPF_NT, NLPF_MIN_CTAS)
-solve_kernel(DevProb P, int B, double* __restrict__ z_io, const double* __restrict__ U,
+VN(solve_kernel)(DevProb P, int B, double* __restrict__ z_io, const double* __restrict__ U,
              const double* __restrict__ data, const double* __restrict__ xprior,
              const double* __restrict__ wshift, nlpf_opts opt, double* __restrict__ cost_out,
              int* __restrict__ iters_out, int* __restrict__ status_out, double* __restrict__ hlin) {
@@ -1100,6 +1226,7 @@ solve_kernel(DevProb P, int B, double* __restrict__ z_io, const double* __restri
     }
 }
 
+#if !NLPF_PR_RUNS
 // ------------------------------------------------------------------------------------------
 // nlpf_sample: x(t) = Phi(t) X, nlp.py:99-119
 // ------------------------------------------------------------------------------------------
@@ -1118,31 +1245,40 @@ __global__ void sample_kernel(DevProb P, int B, const double* __restrict__ z, in
     }
 }
 
+#endif
+
+}  // namespace
+using namespace VN(nlpf_ns);
+
 // ------------------------------------------------------------------------------------------
 // launchers (called from capi.cu)
 // ------------------------------------------------------------------------------------------
 static int grid_for(int B) { return B < 1 ? 1 : B; }
 
-extern "C" int nlpf_launch_assemble(nlpf_problem* p, int B, const double* z, const double* U, const double* data,
+extern "C" int VN(nlpf_launch_assemble)(nlpf_problem* p, int B, const double* z, const double* U, const double* data,
                                     const double* xprior, const double* wshift, double mu, double* H_out,
                                     double* g_out, double* cost_out, cudaStream_t st) {
-    assemble_kernel<<<grid_for(B), NLPF_NT, p->smem_bytes, st>>>(p->d, B, z, U, data, xprior, wshift, mu, H_out, g_out, cost_out);
+    VN(assemble_kernel)<<<grid_for(B), NLPF_NT, p->smem_bytes, st>>>(p->d, B, z, U, data, xprior, wshift, mu, H_out, g_out, cost_out);
     return nlpf_check_cuda(cudaGetLastError(), "assemble_kernel launch");
 }
 
+#if !NLPF_PR_RUNS
 extern "C" int nlpf_launch_factor_solve(nlpf_problem* p, int B, const double* H, const double* g, double lam,
                                         double* dz_out, int* info_out, cudaStream_t st) {
     factor_solve_kernel<<<grid_for(B), NLPF_NT, p->smem_bytes, st>>>(p->d, B, H, g, lam, dz_out, info_out);
     return nlpf_check_cuda(cudaGetLastError(), "factor_solve_kernel launch");
 }
 
-extern "C" int nlpf_launch_solve(nlpf_problem* p, int B, double* z, const double* U, const double* data,
+#endif
+
+extern "C" int VN(nlpf_launch_solve)(nlpf_problem* p, int B, double* z, const double* U, const double* data,
                                  const double* xprior, const double* wshift, const nlpf_opts* o, double* cost_out,
                                  int* iters_out, int* status_out, double* hlin, cudaStream_t st) {
-    solve_kernel<<<grid_for(B), NLPF_NT, p->smem_bytes, st>>>(p->d, B, z, U, data, xprior, wshift, *o, cost_out, iters_out, status_out, hlin);
+    VN(solve_kernel)<<<grid_for(B), NLPF_NT, p->smem_bytes, st>>>(p->d, B, z, U, data, xprior, wshift, *o, cost_out, iters_out, status_out, hlin);
     return nlpf_check_cuda(cudaGetLastError(), "solve_kernel launch");
 }
 
+#if !NLPF_PR_RUNS
 extern "C" int nlpf_launch_sample(nlpf_problem* p, int B, const double* z, int nt, const double* PhiT, double* out,
                                   cudaStream_t st) {
     const size_t total = (size_t)B * nt * p->d.n;
@@ -1153,15 +1289,19 @@ extern "C" int nlpf_launch_sample(nlpf_problem* p, int B, const double* z, int n
     return nlpf_check_cuda(cudaGetLastError(), "sample_kernel launch");
 }
 
-extern "C" int nlpf_set_smem_attrs(size_t bytes) {
+#endif
+
+extern "C" int VN(nlpf_set_smem_attrs)(size_t bytes) {
     cudaError_t e;
-    e = cudaFuncSetAttribute(assemble_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    e = cudaFuncSetAttribute(VN(assemble_kernel), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
     if (e != cudaSuccess) return nlpf_check_cuda(e, "smem attr assemble");
+#if !NLPF_PR_RUNS
     e = cudaFuncSetAttribute(factor_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
     if (e != cudaSuccess) return nlpf_check_cuda(e, "smem attr factor");
-    e = cudaFuncSetAttribute(solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+#endif
+    e = cudaFuncSetAttribute(VN(solve_kernel), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
     if (e != cudaSuccess) return nlpf_check_cuda(e, "smem attr solve");
-    e = cudaFuncSetAttribute(solve_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    e = cudaFuncSetAttribute(VN(solve_kernel), cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     if (e != cudaSuccess) return nlpf_check_cuda(e, "smem carveout solve");
     return 0;
 }
