@@ -356,7 +356,7 @@ extern "C" int nlpf_problem_create(const nlpf_desc* D, nlpf_problem** out) {
     }
     P.o_Phi = take(P.const_smem ? E * K : 0);
     P.o_Dt = take(P.const_smem ? K * K : 0);
-    P.o_red = take(8);
+    P.o_red = take(32);
     P.smem_doubles = o;
     p->smem_bytes = (size_t)o * sizeof(double);
     if (p->smem_bytes > 227 * 1024) {

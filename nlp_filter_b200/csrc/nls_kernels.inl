@@ -80,6 +80,37 @@ __device__ double block_min(double v, double* red) {
     return s;
 }
 
+// Several reductions behind one pair of barriers (the per-value versions above cost 2 barriers
+// each; an evaluation needs J, barrier, rounding bound and the out-of-bounds flag together).
+// v[0..NS) are summed, v[NS..NS+NM) are maximised; results overwrite v in every thread.
+template <int NS, int NM>
+__device__ void block_reduce(double* v, double* red) {
+#pragma unroll
+    for (int k = 0; k < NS; ++k) v[k] = warp_sum(v[k]);
+#pragma unroll
+    for (int k = 0; k < NM; ++k) v[NS + k] = warp_max(v[NS + k]);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+        for (int k = 0; k < NS + NM; ++k) red[(threadIdx.x >> 5) * (NS + NM) + k] = v[k];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < NS; ++k) {
+        double s = 0.0;
+#pragma unroll
+        for (int i = 0; i < NLPF_NW; ++i) s += red[i * (NS + NM) + k];
+        v[k] = s;
+    }
+#pragma unroll
+    for (int k = 0; k < NM; ++k) {
+        double s = red[NS + k];
+#pragma unroll
+        for (int i = 1; i < NLPF_NW; ++i) s = fmax(s, red[i * (NS + NM) + NS + k]);
+        v[NS + k] = s;
+    }
+}
+
 // ------------------------------------------------------------------------------------------
 // Kernel (1a): continuous-time models f(x,u) and dF/dv, nlp/dynamics.py.
 // Fk is the n x nv Jacobian w.r.t. the node variables (state columns through cmap, unknown
@@ -411,7 +442,14 @@ __device__ void eval_window(const DevProb& P, double* sm, const double* zc, cons
     }
     // ---- phase B: node dynamics f (and dF/dv) ----
     if (P.has_dyncost) {
-        for (int k = tid; k < K; k += NLPF_NT) {
+        // affine models whose H part is constant need no per-node pass: thread (k,i) of phase C forms
+        // f_ki = c0_i + A_i. x_k + B_i. u_k itself (ncu: 8 % of the GNSS kernel waited here for 11 busy threads)
+#if NLPF_PR_RUNS
+        const bool affine_inline = P.fconst && !need_F;
+#else
+        const bool affine_inline = false;      // kept out of this instantiation: it cost the van der Pol kernel 10 % (register allocation)
+#endif
+        for (int k = affine_inline ? K : tid; k < K; k += NLPF_NT) {
             double x[NLPF_N_MAX], u[NLPF_M_MAX], f[NLPF_N_MAX];
             for (int i = 0; i < n; ++i) x[i] = zc[k * nv + P.cmap[i]];
             for (int i = 0; i < m; ++i)
@@ -422,13 +460,24 @@ __device__ void eval_window(const DevProb& P, double* sm, const double* zc, cons
             dyn_eval(P, x, u, f, need_F, Fk);
             for (int i = 0; i < n; ++i) fbuf[k * n + i] = f[i];
         }
-        __syncthreads();
+        if (!affine_inline) __syncthreads();
         // ---- phase C: defects W, weights ----
         for (int t = tid; t < K * n; t += NLPF_NT) {
             const int k = t / n, i = t - k * n;
             const int col = P.cmap[i];
-            double W = -fbuf[t];
-            double mag = fabs(fbuf[t]);
+            double fki;
+            if (affine_inline) {
+                fki = P.c0[i];
+                for (int j = 0; j < n; ++j) fki = fma(P.A[i * n + j], zc[k * nv + P.cmap[j]], fki);
+                for (int j = 0; j < m; ++j) {
+                    const double uj = (P.ucol[j] >= 0) ? zc[k * nv + P.ucol[j]] : (wp.U ? wp.U[k * m + j] : 0.0);
+                    fki = fma(P.Bm[i * m + j], uj, fki);
+                }
+            } else {
+                fki = fbuf[t];
+            }
+            double W = -fki;
+            double mag = fabs(fki);
             for (int j = 0; j < K; ++j) {
                 const double dx = Dt[k * K + j] * zc[j * nv + col];
                 W += dx;
@@ -696,27 +745,57 @@ __device__ void eval_window(const DevProb& P, double* sm, const double* zc, cons
             __syncthreads();
             // node-node blocks: H[(j,a),(l,b)] += sum_e phi_ej phi_el G_e[a][b]
             const int nwork = accH ? P.npair * na : 0;
-            for (int wk = tid; wk < nwork; wk += NLPF_NT) {
-                const int pr = wk / na, a = wk - pr * na;
-                const int pe = P.ptab[pr];
-                const int j = pe & 255, l = pe >> 8;
-                double acc[NLPF_NA_MAX];
-#pragma unroll
-                for (int b = 0; b < NLPF_NA_MAX; ++b) acc[b] = 0.0;
-                for (int el = 0; el < ne; ++el) {
-                    const double* ph = Phi + (c0 + el) * K;
-                    const double pp = ph[j] * ph[l];
-                    const double* Ga = G + (el * nat + a) * nat;
-#pragma unroll
-                    for (int b = 0; b < NLPF_NA_MAX; ++b)
-                        if (b < na) acc[b] = fma(pp, Ga[b], acc[b]);
+            if (NLPF_PR_RUNS && na == 4 && nat == 4) {
+                // the pseudorange case (x, y, z, clock): exact trip counts, 16-byte loads of the G_e rows
+                // (ncu: the predicated 8-wide version of this loop was 14 % of the GNSS kernel's instructions)
+                for (int wk = tid; wk < nwork; wk += NLPF_NT) {
+                    const int pr = wk >> 2, a = wk & 3;
+                    const int pe = P.ptab[pr];
+                    const int j = pe & 255, l = pe >> 8;
+                    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+                    const double* ph = Phi + c0 * K;
+                    const double2* Ga = reinterpret_cast<const double2*>(G + a * 4);
+                    for (int el = 0; el < ne; ++el) {
+                        const double pp = ph[j] * ph[l];
+                        const double2 g01 = Ga[0], g23 = Ga[1];
+                        a0 = fma(pp, g01.x, a0);
+                        a1 = fma(pp, g01.y, a1);
+                        a2 = fma(pp, g23.x, a2);
+                        a3 = fma(pp, g23.y, a3);
+                        ph += K;
+                        Ga += 8;                     // next epoch: 16 doubles
+                    }
+                    const int r = j * nv + P.act[a];
+                    const int cb = l * nv;
+                    const int c0_ = cb + P.act[0], c1_ = cb + P.act[1], c2_ = cb + P.act[2], c3_ = cb + P.act[3];
+                    if (c0_ <= r) Hp[pk(r, c0_)] += a0;
+                    if (c1_ <= r) Hp[pk(r, c1_)] += a1;
+                    if (c2_ <= r) Hp[pk(r, c2_)] += a2;
+                    if (c3_ <= r) Hp[pk(r, c3_)] += a3;
                 }
-                const int r = j * nv + P.act[a];
+            } else {
+                for (int wk = tid; wk < nwork; wk += NLPF_NT) {
+                    const int pr = wk / na, a = wk - pr * na;
+                    const int pe = P.ptab[pr];
+                    const int j = pe & 255, l = pe >> 8;
+                    double acc[NLPF_NA_MAX];
 #pragma unroll
-                for (int b = 0; b < NLPF_NA_MAX; ++b) {
-                    if (b < na) {
-                        const int c = l * nv + P.act[b];
-                        if (c <= r) Hp[pk(r, c)] += acc[b];
+                    for (int b = 0; b < NLPF_NA_MAX; ++b) acc[b] = 0.0;
+                    for (int el = 0; el < ne; ++el) {
+                        const double* ph = Phi + (c0 + el) * K;
+                        const double pp = ph[j] * ph[l];
+                        const double* Ga = G + (el * nat + a) * nat;
+#pragma unroll
+                        for (int b = 0; b < NLPF_NA_MAX; ++b)
+                            if (b < na) acc[b] = fma(pp, Ga[b], acc[b]);
+                    }
+                    const int r = j * nv + P.act[a];
+#pragma unroll
+                    for (int b = 0; b < NLPF_NA_MAX; ++b) {
+                        if (b < na) {
+                            const int c = l * nv + P.act[b];
+                            if (c <= r) Hp[pk(r, c)] += acc[b];
+                        }
                     }
                 }
             }
@@ -810,10 +889,9 @@ __device__ void eval_window(const DevProb& P, double* sm, const double* zc, cons
         }
     }
     // ---- phase I: reductions ----
-    const double J = block_sum(cost, red);
-    const double B = block_sum(bar, red);
-    const double NS = block_sum(nse, red);
-    const double anybad = block_max(bad ? 1.0 : 0.0, red);
+    double rv[4] = {cost, bar, nse, bad ? 1.0 : 0.0};
+    block_reduce<3, 1>(rv, red);
+    const double J = rv[0], B = rv[1], NS = rv[2], anybad = rv[3];
     double merit = 0.5 * J + B;
     if (anybad > 0.0 || !isfinite(merit)) merit = INFINITY;
     J_out = J;
@@ -1115,8 +1193,12 @@ VN(solve_kernel)(DevProb P, int B, double* __restrict__ z_io, const double* __re
                         ds[i] = Hp[pk(i, i)];
                         dm = fmax(dm, dd[i]);
                     }
-                    gm = block_max(gm, red);
-                    dm = block_max(dm, red);
+                    {
+                        double rv[2] = {gm, dm};
+                        block_reduce<0, 2>(rv, red);
+                        gm = rv[0];
+                        dm = rv[1];
+                    }
                     if (mu > opt.mu_min && stage_steps >= 1 && gm < 10.0 * mu) {
                         status = NLPF_ST_CONVERGED;
                         break;
@@ -1151,17 +1233,20 @@ VN(solve_kernel)(DevProb P, int B, double* __restrict__ z_io, const double* __re
                                     if (st < 0.0 && P.blo[bb] > -1e300) a = fmin(a, opt.tau_ftb * (zs[idx] - P.blo[bb]) / (-st));
                                     if (st > 0.0 && P.bhi[bb] < 1e300) a = fmin(a, opt.tau_ftb * (P.bhi[bb] - zs[idx]) / st);
                                 }
-                                a = block_min(a, red);
                             }
-                            dmx = block_max(dmx, red);
-                            finite = block_max(finite, red);
+                            double pred = 0.0;                       // predicted decrease scale g^T H^-1 g
+                            for (int i = tid; i < nz; i += NLPF_NT) pred = fma(g[i], dz[i], pred);
+                            {
+                                double rv[4] = {pred, -a, dmx, finite};      // min(a) = -max(-a)
+                                block_reduce<1, 3>(rv, red);
+                                pred = rv[0];
+                                a = -rv[1];
+                                dmx = rv[2];
+                                finite = rv[3];
+                            }
+                            pred *= a;
                             if (finite == 0.0) {
-                                double pred = 0.0;
-                                for (int i = tid; i < nz; i += NLPF_NT) {
-                                    zt[i] = fma(-a, dz[i], zs[i]);
-                                    pred = fma(g[i], dz[i], pred);
-                                }
-                                pred = a * block_sum(pred, red);     // predicted decrease scale g^T H^-1 g
+                                for (int i = tid; i < nz; i += NLPF_NT) zt[i] = fma(-a, dz[i], zs[i]);
                                 __syncthreads();
                                 eval_window<false>(P, sm, zt, wp, mu, Jt, mt, nset, hmode);
                                 if (isfinite(mt) && mt < merit) {
