@@ -192,7 +192,7 @@ extern "C" int nlpf_problem_create(const nlpf_desc* D, nlpf_problem** out) {
     std::vector<int> act, actinv(nv, -1);
     for (int a = 0; a < nv; ++a) if (colact[a]) { actinv[a] = (int)act.size(); act.push_back(a); }
     const int na = (int)act.size();
-    if (na > NLPF_NA_MAX) { nlpf_set_error("measurements touch %d node components (limit %d)", na, NLPF_NA_MAX); delete p; return NLPF_E_ARG; }
+    if (na > NLPF_NV_MAX) { nlpf_set_error("measurements touch %d node components (limit %d)", na, NLPF_NV_MAX); delete p; return NLPF_E_ARG; }
     P.na = na; P.nat = na + ng;
     P.lin_meas = (M > 0) ? 1 : 0;
     for (int i = 0; i < M; ++i) if (D->rtype[i] != NLPF_RT_STATE) P.lin_meas = 0;

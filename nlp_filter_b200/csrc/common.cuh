@@ -9,7 +9,7 @@
 #ifndef NLPF_MIN_CTAS
 #define NLPF_MIN_CTAS 8        // register cap 64/thread: 8 windows resident per SM (ncu: 128 regs limited it to 4)
 #endif
-#define NLPF_NA_MAX 8          // active node-variable components a measurement set may touch
+#define NLPF_NA_MAX 8          // components b handled per work item of the H accumulation (register block)
 #define NLPF_NG_MAX 8
 #define NLPF_N_MAX 12
 #define NLPF_M_MAX 6

@@ -774,8 +774,11 @@ __device__ void eval_window(const DevProb& P, double* sm, const double* zc, cons
                     if (c3_ <= r) Hp[pk(r, c3_)] += a3;
                 }
             } else {
-                for (int wk = tid; wk < nwork; wk += NLPF_NT) {
-                    const int pr = wk / na, a = wk - pr * na;
+                // work item = (node pair, component a, block of up to NLPF_NA_MAX components b)
+                const int nbb = (na + NLPF_NA_MAX - 1) / NLPF_NA_MAX;
+                for (int wk = tid; wk < nwork * nbb; wk += NLPF_NT) {
+                    const int w2 = wk / nbb, b0 = (wk - w2 * nbb) * NLPF_NA_MAX;
+                    const int pr = w2 / na, a = w2 - pr * na;
                     const int pe = P.ptab[pr];
                     const int j = pe & 255, l = pe >> 8;
                     double acc[NLPF_NA_MAX];
@@ -784,16 +787,16 @@ __device__ void eval_window(const DevProb& P, double* sm, const double* zc, cons
                     for (int el = 0; el < ne; ++el) {
                         const double* ph = Phi + (c0 + el) * K;
                         const double pp = ph[j] * ph[l];
-                        const double* Ga = G + (el * nat + a) * nat;
+                        const double* Ga = G + (el * nat + a) * nat + b0;
 #pragma unroll
                         for (int b = 0; b < NLPF_NA_MAX; ++b)
-                            if (b < na) acc[b] = fma(pp, Ga[b], acc[b]);
+                            if (b0 + b < na) acc[b] = fma(pp, Ga[b], acc[b]);
                     }
                     const int r = j * nv + P.act[a];
 #pragma unroll
                     for (int b = 0; b < NLPF_NA_MAX; ++b) {
-                        if (b < na) {
-                            const int c = l * nv + P.act[b];
+                        if (b0 + b < na) {
+                            const int c = l * nv + P.act[b0 + b];
                             if (c <= r) Hp[pk(r, c)] += acc[b];
                         }
                     }

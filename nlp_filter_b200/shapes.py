@@ -167,3 +167,45 @@ def two_receiver(N=10, T=5.0, n_sat=10, fold_equality=True):
             ix.append(_idx(5, 6, 7, 8))
     d.set_residuals(rt, ep, ix)
     return d.finalize()
+
+
+def multi_receiver(N=15, T=63.0, n_epochs=64, n_sat=11):
+    """multi-receiver.py:62-99 shape: K=16, n=8, m=0, three global unknowns XA; per epoch
+    pseudorange + pseudorange-rate per satellite and one planar range to XA."""
+    d = _base(N, T, 8, 0, np.linspace(0, T, n_epochs))
+    A = np.zeros((8, 8))
+    for i in range(4):
+        A[i, 4 + i] = 1.0
+    affine(d, A, np.zeros((8, 1)))
+    d.ng = 3
+    d.qinv = 1.0 / np.array([0.01, 0.01, 0.01, 0.01, 1., 1., 0.01, 0.01])
+    rt, ep, ix = [], [], []
+    for e in range(n_epochs):
+        for j in range(n_sat):
+            rt.append(D.RT_PR); ep.append(e); ix.append(_idx(0, 1, 2, 3))
+            rt.append(D.RT_PRR); ep.append(e); ix.append(_idx(0, 1, 2, 4, 5, 6, 7))
+        rt.append(D.RT_RANGE_PT); ep.append(e); ix.append(_idx(0, 1, 0, 0, 1, -1, 2))
+    d.set_residuals(rt, ep, ix)
+    return d.finalize()
+
+
+def generic_model(dyn_id, n, m, K=7, T=3.0, n_epochs=9, extra=()):
+    """Small problem around any kernel dynamics model with full-state measurements of every
+    component (+ optional extra residual rows): used by the parity tests of the model library."""
+    d = _base(K - 1, T, n, m, np.linspace(0, T, n_epochs))
+    d.dyn_id = dyn_id
+    d.dyn_par[:6] = CAR_PARAMS
+    if dyn_id == D.DYN_QUADCOPTER:
+        d.dyn_par[:4] = [1.3, 0.02, 0.03, 0.04]
+    if dyn_id == D.DYN_AFFINE:
+        rng = np.random.default_rng(99)
+        d.A, d.Bm, d.c0 = rng.normal(size=(n, n)), rng.normal(size=(n, max(m, 1))), rng.normal(size=n)
+    d.qinv = 1.0 + np.arange(n) * 0.5
+    rt, ep, ix = [], [], []
+    for e in range(n_epochs):
+        for i in range(n):
+            rt.append(D.RT_STATE); ep.append(e); ix.append(_idx(i))
+        for (t, idx) in extra:
+            rt.append(t); ep.append(e); ix.append(_idx(*idx))
+    d.set_residuals(rt, ep, ix)
+    return d.finalize()
