@@ -36,6 +36,10 @@ extern "C" int nlpf_launch_solve_gen(nlpf_problem*, int, double*, const double*,
 extern "C" int nlpf_launch_solve_pr(nlpf_problem*, int, double*, const double*, const double*, const double*,
                                     const double*, const nlpf_opts*, double*, int*, int*, double*, cudaStream_t);
 extern "C" int nlpf_launch_sample(nlpf_problem*, int, const double*, int, const double*, double*, cudaStream_t);
+extern "C" int nlpf_ws_variant(int K, int N, int M, int E, int NM, int dyn);
+extern "C" int nlpf_ws_launch(int variant, nlpf_problem* p, int B, double* z, const double* U, const double* data,
+                              const nlpf_opts* o, double* cost_out, int* iters_out, int* status_out, double* hlin,
+                              int* counter, cudaStream_t st);
 extern "C" int nlpf_set_smem_attrs_gen(size_t bytes);
 extern "C" int nlpf_set_smem_attrs_pr(size_t bytes);
 
@@ -293,6 +297,30 @@ extern "C" int nlpf_problem_create(const nlpf_desc* D, nlpf_problem** out) {
         for (int j = 0; j < K; ++j) for (int l = 0; l <= j; ++l) ptab[q++] = (uint16_t)(j | (l << 8));
     }
 
+    // transposed basis and the uniform linear-measurement layout (warp-per-window kernel)
+    std::vector<double> PhiT((size_t)K * (E > 0 ? E : 1), 0.0);
+    for (int e = 0; e < E; ++e) for (int j = 0; j < K; ++j) PhiT[(size_t)j * E + e] = D->Phi[(size_t)e * K + j];
+    std::vector<int> mslot(n, -1);
+    p->ws_variant = -1;
+    p->counter = nullptr;
+    if (P.lin_meas && E > 0 && M % E == 0) {
+        const int NM = M / E;
+        bool uniform = true;
+        for (int e = 0; e < E && uniform; ++e) {
+            if (estart[e + 1] - estart[e] != NM) uniform = false;
+            for (int s2 = 0; s2 < NM && uniform; ++s2)
+                if (rloc_s[(size_t)(e * NM + s2) * NLPF_NIDX] != rloc_s[(size_t)s2 * NLPF_NIDX]) uniform = false;
+        }
+        bool ident = (nv == n) && (ng == 0);
+        for (int i = 0; i < n; ++i) if (D->cmap[i] != i) ident = false;
+        bool upar = true;
+        for (int i = 0; i < m; ++i) if (D->ucol[i] >= 0) upar = false;
+        if (uniform) for (int s2 = 0; s2 < NM; ++s2) mslot[act[rloc_s[(size_t)s2 * NLPF_NIDX]]] = s2;
+        if (uniform && ident && upar && D->loss == NLPF_LOSS_L2 && D->nb == 0 && !P.has_prior && !P.has_nodecost &&
+            P.has_dyncost && !getenv("NLPF_NO_WARP_KERNEL"))
+            p->ws_variant = nlpf_ws_variant(K, n, m, E, NM, D->dyn_id);
+    }
+
     // LDL trailing-update work items: (row, 8-column segment) of the generic lower triangle with
     // nz+1 rows, row-major, so that the items of a trailing triangle with s rows are a prefix
     std::vector<uint16_t> seg_tab;
@@ -316,7 +344,7 @@ extern "C" int nlpf_problem_create(const nlpf_desc* D, nlpf_problem** out) {
                  oPh = B.add(D->Phi, sizeof(double) * E * K), ort = B.addv(rtype_s), orl = B.addv(rloc_s),
                  oro = B.addv(roff_s), oes = B.addv(estart), oac = B.addv(act), oHc = B.addv(Hc), oFc = B.addv(Fc),
                  otb = B.addv(tab), opt = B.addv(ptab), osg = B.addv(seg_tab), osc = B.addv(seg_cnt),
-                 ogs = B.addv(gstart), oer = B.addv(erun), ors = B.addv(run_start), orn = B.addv(run_len), orc = B.addv(run_loc);
+                 oPT = B.addv(PhiT), oms = B.addv(mslot), ogs = B.addv(gstart), oer = B.addv(erun), ors = B.addv(run_start), orn = B.addv(run_len), orc = B.addv(run_loc);
     B.add(zero1.data(), 16);
     p->blob_bytes = B.host.size();
     cudaGetDevice(&p->device);
@@ -334,6 +362,7 @@ extern "C" int nlpf_problem_create(const nlpf_desc* D, nlpf_problem** out) {
     P.estart = (const int*)(base + oes); P.act = (const int*)(base + oac); P.Hc = (const double*)(base + oHc);
     P.Fc = (const double*)(base + oFc); P.tab = (const uint32_t*)(base + otb); P.ptab = (const uint16_t*)(base + opt);
     P.seg_tab = (const uint16_t*)(base + osg); P.seg_cnt = (const int*)(base + osc);
+    P.PhiT = (const double*)(base + oPT); P.mslot = (const int*)(base + oms);
     P.gstart = (const int*)(base + ogs); P.erun = (const int*)(base + oer); P.run_start = (const int*)(base + ors);
     P.run_len = (const int*)(base + orn); P.run_loc = (const int*)(base + orc);
 
@@ -372,6 +401,7 @@ extern "C" int nlpf_problem_destroy(nlpf_problem* p) {
     if (!p) return NLPF_OK;
     cudaFree(p->blob);
     if (p->scratch) cudaFree(p->scratch);
+    if (p->counter) cudaFree(p->counter);
     delete p;
     return NLPF_OK;
 }
@@ -408,6 +438,18 @@ extern "C" int nlpf_solve(nlpf_problem* p, int B, double* z, const double* U, co
     int rc = check_batch(p, B, z, data);
     if (rc) return rc;
     if (!opts || !cost_out || !iters_out || !status_out) { nlpf_set_error("null opts/output buffer"); return NLPF_E_ARG; }
+    if (p->ws_variant >= 0 && !xprior && !wshift && (p->d.m == 0 || U)) {
+        // small linear-measurement class: warp-per-window kernel (its own constant-H cache and work counter)
+        const size_t need = (size_t)B * p->d.np;
+        if (need > p->scratch_doubles) {
+            if (p->scratch) { cudaStreamSynchronize((cudaStream_t)stream); cudaFree(p->scratch); p->scratch = nullptr; p->scratch_doubles = 0; }
+            if (nlpf_check_cuda(cudaMalloc((void**)&p->scratch, need * sizeof(double)), "cudaMalloc(constant-H cache)")) return NLPF_E_CUDA;
+            p->scratch_doubles = need;
+        }
+        if (!p->counter && nlpf_check_cuda(cudaMalloc((void**)&p->counter, sizeof(int)), "cudaMalloc(work counter)")) return NLPF_E_CUDA;
+        return nlpf_ws_launch(p->ws_variant, p, B, z, U, data, opts, cost_out, iters_out, status_out, p->scratch, p->counter,
+                              (cudaStream_t)stream);
+    }
     double* hlin = nullptr;
     if (p->d.lin_meas) {        // per-window constant-H cache (not shared between concurrent calls on one handle)
         const size_t need = (size_t)B * p->d.np;

@@ -46,6 +46,8 @@ struct DevProb {
     const double* blo;
     const double* bhi;
     const double* Phi;                // E*K
+    const double* PhiT;               // K*E (transposed copy: coalesced when lanes run over epochs)
+    const int* mslot;                 // n  slot of state component a in every epoch's record set, or -1 (uniform linear measurements)
     const int* rtype;                 // M (sorted by epoch)
     const int* rloc;                  // M*8 local indices: <na active comp, >=na global, -1 unused
     const int* roff;                  // M
@@ -75,6 +77,8 @@ struct nlpf_problem {
     size_t blob_bytes;
     size_t smem_bytes;
     int use_pr;          // 1: problem has pseudorange runs -> *_pr kernels
+    int ws_variant;      // >= 0: small linear-measurement class served by the warp-per-window kernel
+    int* counter;        // device work counter of the warp-per-window kernel
     int device;
 };
 

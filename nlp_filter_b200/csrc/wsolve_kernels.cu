@@ -1,0 +1,494 @@
+// wsolve_kernels.cu -- warp-per-window whole-solve kernel for SMALL estimation windows whose
+// measurements are linear (RT_STATE of a fixed set of components at every epoch): the van der
+// Pol MHE shape of BASELINE.json configs[1] and the estimation_example.py pattern.
+//
+// Why a second kernel (profiles/r1_vdp_kernel_full.json, CTA-per-window kernel): ~27 k useful
+// FMAs per iteration were buried under 40 k warp instructions -- runtime sizes and index tables,
+// 128 threads of which <= 42 had work in most phases, ~70 block barriers per iteration, a
+// 64-register cap.  Here every size is a template parameter (loops unroll, indices fold), one
+// warp owns one window (only __syncwarp), windows are handed out through an atomic counter (no
+// tail behind slow windows), and 16 warps/SM leave 128 registers per thread.
+//
+// Same algorithm and decisions as solve_kernel (nls_kernels.inl) and oracle/nls.py:
+// damped Gauss-Newton with the exact second-order dynamics term, LDL^T with the right-hand side
+// appended, rounding-bound step acceptance.  Restrictions (checked on the host, anything else
+// goes to the general kernel): L2 loss, no bounds, no arrival cost, no global unknowns, identity
+// cmap, parameter controls, every epoch measures the same NM components.
+#include "common.cuh"
+#include <math.h>
+
+#define WS_WARPS 4
+
+namespace {
+
+__device__ __forceinline__ double wsum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ double wmax(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+__device__ __forceinline__ constexpr int pk(int r, int c) { return ((r * (r + 1)) >> 1) + c; }
+
+// ---- models (nlp/dynamics.py), compile-time sized; F is the N x N Jacobian, row-major ----
+template <int DYN, int N, int M>
+__device__ __forceinline__ void ws_dyn(const DevProb& P, const double* x, const double* u, double* f, double* F) {
+#pragma unroll
+    for (int i = 0; i < N * N; ++i) F[i] = 0.0;
+    if (DYN == NLPF_DYN_VDP) {                         // dynamics.py:61-66
+        f[0] = (1.0 - x[1] * x[1]) * x[0] - x[1] + u[0];
+        f[1] = x[0];
+        F[0] = 1.0 - x[1] * x[1];
+        F[1] = -2.0 * x[0] * x[1] - 1.0;
+        F[N] = 1.0;
+    } else {                                           // affine: f = A x + B u + c0
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            double s = P.c0[i];
+#pragma unroll
+            for (int j = 0; j < N; ++j) {
+                s = fma(P.A[i * N + j], x[j], s);
+                F[i * N + j] = P.A[i * N + j];
+            }
+#pragma unroll
+            for (int j = 0; j < M; ++j) s = fma(P.Bm[i * M + j], u[j], s);
+            f[i] = s;
+        }
+    }
+}
+
+template <int K, int N, int M, int E, int NM>
+struct WsLayout {
+    static constexpr int NZ = K * N;
+    static constexpr int NP = NZ * (NZ + 1) / 2;
+    static constexpr int NR = E * NM;                  // residuals
+    static constexpr int ev(int x) { return (x + 1) & ~1; }
+    static constexpr int oH = 0;
+    static constexpr int oZ = oH + ev(NP + NZ);
+    static constexpr int oZT = oZ + ev(NZ);
+    static constexpr int oG = oZT + ev(NZ);
+    static constexpr int oDZ = oG + ev(NZ);
+    static constexpr int oDS = oDZ + ev(NZ);
+    static constexpr int oDD = oDS + ev(NZ);
+    static constexpr int oLW = oDD + ev(NZ);
+    static constexpr int oFB = oLW + ev(NZ);
+    static constexpr int oF = oFB + ev(NZ);
+    static constexpr int oGF = oF + ev(K * N * N);
+    static constexpr int oFF = oGF + ev(K * N * N);
+    static constexpr int oQ = oFF + ev(K * N * N);
+    static constexpr int PER_WARP = oQ + ev(NR);
+    static constexpr int oDt = WS_WARPS * PER_WARP;    // shared by the CTA
+    static constexpr int TOTAL = oDt + ev(K * K);
+};
+
+// objective J, its first-order rounding bound and (FULL) H (packed, shared memory), g
+template <int K, int N, int M, int E, int NM, int DYN, bool FULL>
+__device__ __forceinline__ void ws_eval(const DevProb& P, double* sm, const double* Dt, const double* zc,
+                                        const double* Ug, const double* dg, const double* hlin,
+                                        double& J_out, double& noise_out) {
+    typedef WsLayout<K, N, M, E, NM> L;
+    constexpr int NZ = L::NZ;
+    const int lane = threadIdx.x & 31;
+    double* Hp = sm + L::oH;
+    double* g = sm + L::oG;
+    double* lw = sm + L::oLW;
+    double* fb = sm + L::oFB;
+    double* Fm = sm + L::oF;
+    double* GF = sm + L::oGF;
+    double* FF = sm + L::oFF;
+    double* qv = sm + L::oQ;
+    double cost = 0.0, nse = 0.0;
+
+    if (FULL) {
+        for (int p = lane; p < L::NP; p += 32) Hp[p] = hlin[p];      // constant part + linear measurements
+    }
+    // node dynamics
+    for (int k = lane; k < K; k += 32) {
+        double x[N], u[M > 0 ? M : 1], f[N], F[N * N];
+#pragma unroll
+        for (int i = 0; i < N; ++i) x[i] = zc[k * N + i];
+#pragma unroll
+        for (int i = 0; i < M; ++i) u[i] = Ug[k * M + i];
+        ws_dyn<DYN, N, M>(P, x, u, f, F);
+#pragma unroll
+        for (int i = 0; i < N; ++i) fb[k * N + i] = f[i];
+        if (FULL) {
+#pragma unroll
+            for (int i = 0; i < N * N; ++i) Fm[k * N * N + i] = F[i];
+        }
+    }
+    __syncwarp();
+    // defects W_ki = sum_j Dt_kj x_ji - f_ki, weights
+    for (int t = lane; t < NZ; t += 32) {
+        const int k = t / N, i = t - k * N;
+        const double fki = fb[t];
+        double W = -fki, mag = fabs(fki);
+#pragma unroll
+        for (int j = 0; j < K; ++j) {
+            const double dx = Dt[k * K + j] * zc[j * N + i];
+            W += dx;
+            mag += fabs(dx);
+        }
+        const double cq = P.cw[k] * P.qinv[i];
+        cost = fma(cq * W, W, cost);
+        lw[t] = cq * W;
+        nse += 2.0 * fabs(cq * W) * mag;
+    }
+    __syncwarp();
+    if (FULL) {
+        // per-node blocks GF = Lambda F, FF = F^T Lambda F; gradient of the dynamics cost
+        for (int t = lane; t < K * N * N; t += 32) {
+            const int k = t / (N * N), rem = t - k * N * N, a = rem / N, b = rem - a * N;
+            const double* Fk = Fm + k * N * N;
+            GF[t] = P.cw[k] * P.qinv[a] * Fk[a * N + b];
+            double s = 0.0;
+#pragma unroll
+            for (int i = 0; i < N; ++i) s = fma(Fk[i * N + a] * (P.cw[k] * P.qinv[i]), Fk[i * N + b], s);
+            FF[t] = s;
+        }
+        for (int t = lane; t < NZ; t += 32) {
+            const int j = t / N, a = t - j * N;
+            double s = 0.0;
+#pragma unroll
+            for (int k = 0; k < K; ++k) s = fma(Dt[k * K + j], lw[k * N + a], s);
+#pragma unroll
+            for (int i = 0; i < N; ++i) s = fma(-Fm[j * N * N + i * N + a], lw[j * N + i], s);
+            g[t] = s;
+        }
+        __syncwarp();
+        // H += -Dt_jl GF_j[b][a] - Dt_lj GF_l[a][b] (+ FF_j on the diagonal blocks), per node pair
+        for (int pr = lane; pr < K * (K + 1) / 2; pr += 32) {
+            const int pe = P.ptab[pr];
+            const int j = pe & 255, l = pe >> 8;
+            const double djl = Dt[j * K + l], dlj = Dt[l * K + j];
+#pragma unroll
+            for (int a = 0; a < N; ++a)
+#pragma unroll
+                for (int b = 0; b < N; ++b) {
+                    if (j == l && b > a) continue;
+                    double s = -djl * GF[j * N * N + b * N + a] - dlj * GF[l * N * N + a * N + b];
+                    if (j == l) s += FF[j * N * N + a * N + b];
+                    Hp[pk(j * N + a, l * N + b)] += s;
+                }
+        }
+        __syncwarp();
+    }
+    // measurements: residual t = e*NM + s measures component mc[s] at epoch e (record [y, w] at roff[t])
+    for (int t = lane; t < L::NR; t += 32) {
+        const int e = t / NM, s = t - e * NM;
+        const int c = P.act[P.rloc[t * NLPF_NIDX]];
+        const double* rec = dg + P.roff[t];
+        const double w = rec[1];
+        double v = 0.0;
+#pragma unroll
+        for (int j = 0; j < K; ++j) v = fma(P.PhiT[j * E + e], zc[j * N + c], v);
+        const double r = (w != 0.0) ? rec[0] - v : 0.0;
+        cost = fma(w * r, r, cost);
+        nse += 2.0 * w * fabs(r) * (2.0 * fabs(rec[0]) + fabs(r));
+        if (FULL) qv[t] = w * r;
+        (void)s;
+    }
+    if (FULL) {
+        __syncwarp();
+        for (int t = lane; t < NZ; t += 32) {
+            const int j = t / N, a = t - j * N;
+            const int s = P.mslot[a];                      // slot of component a in an epoch's record set, or -1
+            if (s >= 0) {
+                double acc = 0.0;
+#pragma unroll 10
+                for (int e = 0; e < E; ++e) acc = fma(P.Phi[e * K + j], qv[e * NM + s], acc);
+                g[t] -= acc;
+            }
+        }
+        __syncwarp();
+        // Gauss-Newton diagonal for the damping, then the exact second-order dynamics term
+        double* dd = sm + L::oDD;
+        for (int i = lane; i < NZ; i += 32) dd[i] = Hp[pk(i, i)];
+        if (DYN == NLPF_DYN_VDP) {
+            __syncwarp();
+            for (int k = lane; k < K; k += 32) {           // hess f0 = [[0, -2 x1], [-2 x1, -2 x0]]
+                const double x0 = zc[k * N], x1 = zc[k * N + 1], l0 = lw[k * N];
+                Hp[pk(k * N + 1, k * N)] += l0 * 2.0 * x1;
+                Hp[pk(k * N + 1, k * N + 1)] += l0 * 2.0 * x0;
+            }
+        }
+    }
+    J_out = wsum(cost);
+    noise_out = 2.220446049250313e-16 * (0.5 * wsum(nse) + 0.5 * fabs(J_out));
+    __syncwarp();
+}
+
+// LDL^T of the packed matrix with the right-hand side appended as row NZ (see nls_kernels.inl:
+// ldl_solve); warp version: panels of 4 columns, redundant 4x4 factorisation per lane, (row,
+// 8-column segment) items from the host-built table.
+template <int NZ>
+__device__ __forceinline__ bool ws_ldl(const DevProb& P, double* Hp, double* xs) {
+    const int lane = threadIdx.x & 31;
+    bool ok = true;
+#pragma unroll 1
+    for (int j0 = 0; j0 < NZ; j0 += 4) {
+        const int pw = (NZ - j0 < 4) ? NZ - j0 : 4;
+        __syncwarp();
+        double a[4][4], l[4][4], d[4], rd[4];
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+#pragma unroll
+            for (int c = 0; c <= r; ++c) a[r][c] = (r < pw) ? Hp[pk(j0 + r, j0 + c)] : (r == c ? 1.0 : 0.0);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+#pragma unroll
+            for (int r = c; r < 4; ++r) {
+                double w = a[r][c];
+#pragma unroll
+                for (int q = 0; q < c; ++q) w = fma(-a[r][q], l[c][q], w);
+                a[r][c] = w;
+            }
+            d[c] = a[c][c];
+            rd[c] = 1.0 / d[c];
+#pragma unroll
+            for (int r = c + 1; r < 4; ++r) l[r][c] = a[r][c] * rd[c];
+        }
+        bool good = true;
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+            if (c < pw && (!(d[c] > 0.0) || !isfinite(d[c]))) good = false;
+        if (!good) { ok = false; break; }
+        const int j1 = j0 + pw;
+        for (int i = j1 + lane; i <= NZ; i += 32) {
+            double* Hi = Hp + pk(i, j0);
+            double w[4];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                if (c < pw) {
+                    double v = Hi[c];
+#pragma unroll
+                    for (int q = 0; q < c; ++q) v = fma(-w[q], l[c][q], v);
+                    w[c] = v;
+                    Hi[c] = v;
+                } else w[c] = 0.0;
+            }
+        }
+        __syncwarp();
+        if (lane == 31) {
+#pragma unroll
+            for (int r = 0; r < 4; ++r)
+#pragma unroll
+                for (int c = 0; c <= r; ++c)
+                    if (r < pw) Hp[pk(j0 + r, j0 + c)] = a[r][c];
+        }
+        const int nitem = P.seg_cnt[NZ + 1 - j1];
+        for (int it = lane; it < nitem; it += 32) {
+            const int e = P.seg_tab[it];
+            const int i = j1 + (e & 255);
+            const int k0 = j1 + ((e >> 8) << 3);
+            int kend = k0 + 7;
+            if (kend > i) kend = i;
+            if (kend > NZ - 1) kend = NZ - 1;
+            double* Hi = Hp + pk(i, 0);
+            double li[4];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) li[c] = (c < pw) ? Hi[j0 + c] * rd[c] : 0.0;
+            for (int k = k0; k <= kend; ++k) {
+                const double* Hk = Hp + pk(k, j0);
+                double v = Hi[k];
+#pragma unroll
+                for (int c = 0; c < 4; ++c)
+                    if (c < pw) v = fma(-li[c], Hk[c], v);
+                Hi[k] = v;
+            }
+        }
+    }
+    __syncwarp();
+    if (!ok) return false;
+    double* u = Hp + pk(NZ, 0);
+    for (int j = NZ - 1; j >= 0; --j) {
+        const double* Hj = Hp + pk(j, 0);
+        const double xj = u[j] / Hj[j];
+        for (int i = lane; i < j; i += 32) u[i] = fma(-Hj[i], xj, u[i]);
+        if (lane == 0) xs[j] = xj;
+        __syncwarp();
+    }
+    return true;
+}
+
+template <int K, int N, int M, int E, int NM, int DYN>
+__global__ void __launch_bounds__(WS_WARPS * 32, 4)
+wsolve_kernel(const __grid_constant__ DevProb P, int B, double* __restrict__ z_io, const double* __restrict__ U,
+              const double* __restrict__ data, nlpf_opts opt, double* __restrict__ cost_out, int* __restrict__ iters_out,
+              int* __restrict__ status_out, double* __restrict__ hlin_all, int* __restrict__ counter) {
+    typedef WsLayout<K, N, M, E, NM> L;
+    constexpr int NZ = L::NZ;
+    extern __shared__ double smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double* Dt = smem + L::oDt;
+    for (int i = threadIdx.x; i < K * K; i += WS_WARPS * 32) Dt[i] = P.Dt[i];
+    __syncthreads();
+    double* sm = smem + warp * L::PER_WARP;
+    double* Hp = sm + L::oH;
+    double* zs = sm + L::oZ;
+    double* zt = sm + L::oZT;
+    double* g = sm + L::oG;
+    double* dz = sm + L::oDZ;
+    double* ds = sm + L::oDS;
+    double* dd = sm + L::oDD;
+
+    while (true) {
+        int b = 0;
+        if (lane == 0) b = atomicAdd(counter, 1);
+        b = __shfl_sync(0xffffffffu, b, 0);
+        if (b >= B) break;
+        const double* Ug = U + (size_t)b * K * (M > 0 ? M : 1);
+        const double* dg = data + (size_t)b * P.Ldata;
+        double* hlin = hlin_all + (size_t)b * L::NP;
+        for (int i = lane; i < NZ; i += 32) zs[i] = z_io[(size_t)b * NZ + i];
+        // constant H of this window: Hc + sum_e (phi_e phi_e^T) (x) diag(w_e)
+        for (int p = lane; p < L::NP; p += 32) Hp[p] = P.Hc[p];
+        __syncwarp();
+        for (int pr = lane; pr < K * (K + 1) / 2; pr += 32) {
+            const int pe = P.ptab[pr];
+            const int j = pe & 255, l = pe >> 8;
+            double acc[NM];
+#pragma unroll
+            for (int s = 0; s < NM; ++s) acc[s] = 0.0;
+#pragma unroll 5
+            for (int e = 0; e < E; ++e) {
+                const double pp = P.Phi[e * K + j] * P.Phi[e * K + l];
+#pragma unroll
+                for (int s = 0; s < NM; ++s) acc[s] = fma(pp, dg[P.roff[e * NM + s] + 1], acc[s]);
+            }
+#pragma unroll
+            for (int s = 0; s < NM; ++s) {
+                const int c = P.act[P.rloc[s * NLPF_NIDX]];
+                Hp[pk(j * N + c, l * N + c)] += acc[s];
+            }
+        }
+        __syncwarp();
+        for (int p = lane; p < L::NP; p += 32) hlin[p] = Hp[p];
+        __syncwarp();
+
+        int iters = 0, status = NLPF_ST_MAXITER, floor_steps = 0;
+        double lam = opt.lam0, J, nse0;
+        ws_eval<K, N, M, E, NM, DYN, true>(P, sm, Dt, zs, Ug, dg, hlin, J, nse0);
+        double merit = 0.5 * J;
+        if (!isfinite(merit)) {
+            status = NLPF_ST_NUMERIC;
+        } else {
+            while (iters < opt.max_iter) {
+                double dm = 0.0;
+                for (int i = lane; i < NZ; i += 32) {
+                    ds[i] = Hp[pk(i, i)];
+                    dm = fmax(dm, dd[i]);
+                }
+                dm = wmax(dm);
+                bool accepted = false, at_floor = false, h_valid = true;
+                double Jt = J, nset = 0.0, dzmax = 0.0;
+                while (lam <= 1e18) {
+                    if (!h_valid) {
+                        double Jd, nd;
+                        ws_eval<K, N, M, E, NM, DYN, true>(P, sm, Dt, zs, Ug, dg, hlin, Jd, nd);
+                        h_valid = true;
+                    }
+                    for (int i = lane; i < NZ; i += 32) {
+                        Hp[pk(i, i)] = ds[i] + lam * (dd[i] + 1e-14 * dm);
+                        Hp[pk(NZ, i)] = g[i];
+                    }
+                    h_valid = false;
+                    const bool ok = ws_ldl<NZ>(P, Hp, dz);
+                    if (ok) {
+                        double dmx = 0.0, fin = 0.0, pred = 0.0;
+                        for (int i = lane; i < NZ; i += 32) {
+                            dmx = fmax(dmx, fabs(dz[i]));
+                            if (!isfinite(dz[i])) fin = 1.0;
+                            pred = fma(g[i], dz[i], pred);
+                            zt[i] = zs[i] - dz[i];
+                        }
+                        dmx = wmax(dmx);
+                        fin = wmax(fin);
+                        pred = wsum(pred);
+                        __syncwarp();
+                        if (fin == 0.0) {
+                            ws_eval<K, N, M, E, NM, DYN, false>(P, sm, Dt, zt, Ug, dg, hlin, Jt, nset);
+                            const double mt = 0.5 * Jt;
+                            if (isfinite(mt) && mt < merit) { accepted = true; dzmax = dmx; break; }
+                            const double nb = nse0 + nset;
+                            if (isfinite(mt) && (mt - merit) <= nb && pred <= 4.0 * nb) {
+                                accepted = true; at_floor = true; dzmax = dmx; break;
+                            }
+                        }
+                    }
+                    lam *= 10.0;
+                }
+                if (!accepted) {
+                    status = NLPF_ST_STALLED;
+                    break;
+                }
+                double zm = 0.0;
+                for (int i = lane; i < NZ; i += 32) {
+                    zs[i] = zt[i];
+                    zm = fmax(zm, fabs(zt[i]));
+                }
+                zm = wmax(zm);
+                lam = fmax(lam / 10.0, 1e-12);
+                ++iters;
+                __syncwarp();
+                ws_eval<K, N, M, E, NM, DYN, true>(P, sm, Dt, zs, Ug, dg, hlin, J, nse0);
+                merit = 0.5 * J;
+                if (dzmax < opt.tol_step * (1.0 + zm)) { status = NLPF_ST_CONVERGED; break; }
+                if (at_floor && ++floor_steps >= 5) { status = NLPF_ST_CONVERGED; break; }
+            }
+        }
+        for (int i = lane; i < NZ; i += 32) z_io[(size_t)b * NZ + i] = zs[i];
+        if (lane == 0) {
+            cost_out[b] = J;
+            iters_out[b] = iters;
+            status_out[b] = status;
+        }
+        __syncwarp();
+    }
+}
+
+template <int K, int N, int M, int E, int NM, int DYN>
+int ws_launch(nlpf_problem* p, int B, double* z, const double* U, const double* data, const nlpf_opts* o,
+              double* cost_out, int* iters_out, int* status_out, double* hlin, int* counter, cudaStream_t st) {
+    typedef WsLayout<K, N, M, E, NM> L;
+    auto kern = wsolve_kernel<K, N, M, E, NM, DYN>;
+    const size_t smem = sizeof(double) * L::TOTAL;
+    static bool attr = false;
+    if (!attr) {
+        if (nlpf_check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "wsolve smem attr")) return NLPF_E_CUDA;
+        cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        attr = true;
+    }
+    if (nlpf_check_cuda(cudaMemsetAsync(counter, 0, sizeof(int), st), "wsolve counter reset")) return NLPF_E_CUDA;
+    int per_sm = (int)((227 * 1024) / (smem + 1024));
+    if (per_sm < 1) per_sm = 1;
+    if (per_sm > 4) per_sm = 4;
+    int grid = 148 * per_sm;
+    const int need = (B + WS_WARPS - 1) / WS_WARPS;
+    if (grid > need) grid = need;
+    kern<<<grid, WS_WARPS * 32, smem, st>>>(p->d, B, z, U, data, *o, cost_out, iters_out, status_out, hlin, counter);
+    return nlpf_check_cuda(cudaGetLastError(), "wsolve_kernel launch");
+}
+
+}  // namespace
+
+// instantiated shapes: (K, N, M, E, NM, DYN).  Returns the variant index or -1.
+extern "C" int nlpf_ws_variant(int K, int N, int M, int E, int NM, int dyn) {
+    if (K == 21 && N == 2 && M == 1 && E == 50 && NM == 2 && dyn == NLPF_DYN_VDP) return 0;      // van der Pol MHE (BASELINE configs[1])
+    if (K == 21 && N == 2 && M == 2 && E == 50 && NM == 2 && dyn == NLPF_DYN_AFFINE) return 1;   // estimation_example.py
+    return -1;
+}
+
+extern "C" int nlpf_ws_launch(int variant, nlpf_problem* p, int B, double* z, const double* U, const double* data,
+                              const nlpf_opts* o, double* cost_out, int* iters_out, int* status_out, double* hlin,
+                              int* counter, cudaStream_t st) {
+    switch (variant) {
+        case 0: return ws_launch<21, 2, 1, 50, 2, NLPF_DYN_VDP>(p, B, z, U, data, o, cost_out, iters_out, status_out, hlin, counter, st);
+        case 1: return ws_launch<21, 2, 2, 50, 2, NLPF_DYN_AFFINE>(p, B, z, U, data, o, cost_out, iters_out, status_out, hlin, counter, st);
+    }
+    nlpf_set_error("unknown warp-solve variant %d", variant);
+    return NLPF_E_ARG;
+}
