@@ -225,7 +225,7 @@ __device__ __forceinline__ void ws_eval(const DevProb& P, double* sm, const doub
 // ldl_solve); warp version: panels of 4 columns, redundant 4x4 factorisation per lane, (row,
 // 8-column segment) items from the host-built table.
 template <int NZ>
-__device__ __forceinline__ bool ws_ldl(const DevProb& P, double* Hp, double* xs) {
+__device__ __forceinline__ bool ws_ldl(const DevProb& P, double* Hp, double* xs, double* rdv) {
     const int lane = threadIdx.x & 31;
     bool ok = true;
 #pragma unroll 1
@@ -274,10 +274,12 @@ __device__ __forceinline__ bool ws_ldl(const DevProb& P, double* Hp, double* xs)
         __syncwarp();
         if (lane == 31) {
 #pragma unroll
-            for (int r = 0; r < 4; ++r)
+            for (int r = 0; r < 4; ++r) {
 #pragma unroll
                 for (int c = 0; c <= r; ++c)
                     if (r < pw) Hp[pk(j0 + r, j0 + c)] = a[r][c];
+                if (r < pw) rdv[j0 + r] = rd[r];           // reciprocal pivots for the backward sweep
+            }
         }
         const int nitem = P.seg_cnt[NZ + 1 - j1];
         for (int it = lane; it < nitem; it += 32) {
@@ -303,12 +305,37 @@ __device__ __forceinline__ bool ws_ldl(const DevProb& P, double* Hp, double* xs)
     }
     __syncwarp();
     if (!ok) return false;
+    // backward sweep, four unknowns per step: every lane solves the 4x4 triangle redundantly in
+    // registers (x_j = (u_j - sum_{k>j in block} Hraw[k][j] x_k) / d_j), then the lanes share the update
+    // u_i -= sum_c Hraw[j_c][i] x_c of the rows above.  (The one-unknown-per-step version with a
+    // division was 14 % of the kernel's stall samples.)
     double* u = Hp + pk(NZ, 0);
-    for (int j = NZ - 1; j >= 0; --j) {
-        const double* Hj = Hp + pk(j, 0);
-        const double xj = u[j] / Hj[j];
-        for (int i = lane; i < j; i += 32) u[i] = fma(-Hj[i], xj, u[i]);
-        if (lane == 0) xs[j] = xj;
+#pragma unroll 1
+    for (int jb = NZ; jb > 0; jb -= 4) {
+        const int j0 = (jb >= 4) ? jb - 4 : 0;
+        const int pw = jb - j0;
+        double x[4];
+#pragma unroll
+        for (int r = 3; r >= 0; --r) {
+            if (r < pw) {
+                double v = u[j0 + r];
+#pragma unroll
+                for (int q = 3; q > r; --q)
+                    if (q < pw) v = fma(-Hp[pk(j0 + q, j0 + r)], x[q], v);
+                x[r] = v * rdv[j0 + r];
+            } else x[r] = 0.0;
+        }
+        __syncwarp();
+        for (int i = lane; i < j0; i += 32) {
+            double v = u[i];
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+                if (c < pw) v = fma(-Hp[pk(j0 + c, i)], x[c], v);
+            u[i] = v;
+        }
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+            if (lane == c && c < pw) xs[j0 + c] = x[c];
         __syncwarp();
     }
     return true;
@@ -346,6 +373,8 @@ wsolve_kernel(const __grid_constant__ DevProb P, int B, double* __restrict__ z_i
         for (int i = lane; i < NZ; i += 32) zs[i] = z_io[(size_t)b * NZ + i];
         // constant H of this window: Hc + sum_e (phi_e phi_e^T) (x) diag(w_e)
         for (int p = lane; p < L::NP; p += 32) Hp[p] = P.Hc[p];
+        double* wts = sm + L::oQ;                          // measurement weights of this window
+        for (int t = lane; t < L::NR; t += 32) wts[t] = dg[P.roff[t] + 1];
         __syncwarp();
         for (int pr = lane; pr < K * (K + 1) / 2; pr += 32) {
             const int pe = P.ptab[pr];
@@ -357,7 +386,7 @@ wsolve_kernel(const __grid_constant__ DevProb P, int B, double* __restrict__ z_i
             for (int e = 0; e < E; ++e) {
                 const double pp = P.Phi[e * K + j] * P.Phi[e * K + l];
 #pragma unroll
-                for (int s = 0; s < NM; ++s) acc[s] = fma(pp, dg[P.roff[e * NM + s] + 1], acc[s]);
+                for (int s = 0; s < NM; ++s) acc[s] = fma(pp, wts[e * NM + s], acc[s]);
             }
 #pragma unroll
             for (int s = 0; s < NM; ++s) {
@@ -396,7 +425,7 @@ wsolve_kernel(const __grid_constant__ DevProb P, int B, double* __restrict__ z_i
                         Hp[pk(NZ, i)] = g[i];
                     }
                     h_valid = false;
-                    const bool ok = ws_ldl<NZ>(P, Hp, dz);
+                    const bool ok = ws_ldl<NZ>(P, Hp, dz, sm + L::oFB);
                     if (ok) {
                         double dmx = 0.0, fin = 0.0, pred = 0.0;
                         for (int i = lane; i < NZ; i += 32) {
