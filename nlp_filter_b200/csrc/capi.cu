@@ -36,7 +36,7 @@ extern "C" int nlpf_launch_solve_gen(nlpf_problem*, int, double*, const double*,
 extern "C" int nlpf_launch_solve_pr(nlpf_problem*, int, double*, const double*, const double*, const double*,
                                     const double*, const nlpf_opts*, double*, int*, int*, double*, cudaStream_t);
 extern "C" int nlpf_launch_sample(nlpf_problem*, int, const double*, int, const double*, double*, cudaStream_t);
-extern "C" int nlpf_ws_variant(int K, int N, int M, int E, int NM, int dyn);
+extern "C" int nlpf_ws_variant(int K, int N, int M, int E, int NM, int dyn, int meas);
 extern "C" int nlpf_ws_launch(int variant, nlpf_problem* p, int B, double* z, const double* U, const double* data,
                               const nlpf_opts* o, double* cost_out, int* iters_out, int* status_out, double* hlin,
                               int* counter, cudaStream_t st);
@@ -303,22 +303,37 @@ extern "C" int nlpf_problem_create(const nlpf_desc* D, nlpf_problem** out) {
     std::vector<int> mslot(n, -1);
     p->ws_variant = -1;
     p->counter = nullptr;
-    if (P.lin_meas && E > 0 && M % E == 0) {
-        const int NM = M / E;
-        bool uniform = true;
-        for (int e = 0; e < E && uniform; ++e) {
-            if (estart[e + 1] - estart[e] != NM) uniform = false;
-            for (int s2 = 0; s2 < NM && uniform; ++s2)
-                if (rloc_s[(size_t)(e * NM + s2) * NLPF_NIDX] != rloc_s[(size_t)s2 * NLPF_NIDX]) uniform = false;
-        }
+    {
         bool ident = (nv == n) && (ng == 0);
         for (int i = 0; i < n; ++i) if (D->cmap[i] != i) ident = false;
         bool upar = true;
         for (int i = 0; i < m; ++i) if (D->ucol[i] >= 0) upar = false;
-        if (uniform) for (int s2 = 0; s2 < NM; ++s2) mslot[act[rloc_s[(size_t)s2 * NLPF_NIDX]]] = s2;
-        if (uniform && ident && upar && D->loss == NLPF_LOSS_L2 && D->nb == 0 && !P.has_prior && !P.has_nodecost &&
-            P.has_dyncost && !getenv("NLPF_NO_WARP_KERNEL"))
-            p->ws_variant = nlpf_ws_variant(K, n, m, E, NM, D->dyn_id);
+        const bool plain = ident && upar && D->loss == NLPF_LOSS_L2 && D->nb == 0 && !P.has_prior && !P.has_nodecost &&
+                           P.has_dyncost && !getenv("NLPF_NO_WARP_KERNEL");
+        if (E > 0 && M > 0 && M % E == 0) {
+            const int NM = M / E;
+            bool uniform = true;                    // every epoch carries the same record set, in the same order
+            for (int e = 0; e < E && uniform; ++e) {
+                if (estart[e + 1] - estart[e] != NM) uniform = false;
+                for (int s2 = 0; s2 < NM && uniform; ++s2) {
+                    if (rtype_s[e * NM + s2] != rtype_s[s2]) uniform = false;
+                    for (int q = 0; q < 4 && uniform; ++q)
+                        if (rloc_s[(size_t)(e * NM + s2) * NLPF_NIDX + q] != rloc_s[(size_t)s2 * NLPF_NIDX + q] &&
+                            (q == 0 || rtype_s[s2] == NLPF_RT_PR)) uniform = false;
+                }
+            }
+            if (uniform && P.lin_meas) {
+                for (int s2 = 0; s2 < NM; ++s2) mslot[act[rloc_s[(size_t)s2 * NLPF_NIDX]]] = s2;
+                if (plain) p->ws_variant = nlpf_ws_variant(K, n, m, E, NM, D->dyn_id, 0);
+            } else if (uniform && plain) {
+                bool allpr = true;                  // one pseudorange run per epoch with a single index quadruple
+                for (int r = 0; r < M; ++r) if (rtype_s[r] != NLPF_RT_PR) allpr = false;
+                for (int s2 = 1; s2 < NM && allpr; ++s2)
+                    for (int q = 0; q < 4; ++q)
+                        if (rloc_s[(size_t)s2 * NLPF_NIDX + q] != rloc_s[q]) allpr = false;
+                if (allpr) p->ws_variant = nlpf_ws_variant(K, n, m, E, NM, D->dyn_id, 1);
+            }
+        }
     }
 
     // LDL trailing-update work items: (row, 8-column segment) of the generic lower triangle with

@@ -17,7 +17,6 @@
 #include "common.cuh"
 #include <math.h>
 
-#define WS_WARPS 4
 
 namespace {
 
@@ -60,8 +59,20 @@ __device__ __forceinline__ void ws_dyn(const DevProb& P, const double* x, const 
     }
 }
 
-template <int K, int N, int M, int E, int NM>
+// compile-time description of one problem class
+template <int K_, int N_, int M_, int E_, int NM_, int DYN_, int MEAS_, int WARPS_>
+struct WsCfg {
+    static constexpr int K = K_, N = N_, M = M_, E = E_;
+    static constexpr int NM = NM_;          // records per epoch: measured components (MEAS 0) or satellite slots (MEAS 1)
+    static constexpr int DYN = DYN_;
+    static constexpr int MEAS = MEAS_;      // 0: RT_STATE of a fixed component set, 1: RT_PR with one index quadruple
+    static constexpr int WARPS = WARPS_;    // windows (warps) per CTA
+    static constexpr bool HCONST = (DYN_ == NLPF_DYN_AFFINE);   // dynamics part of H constant (in Hc)
+};
+
+template <class C>
 struct WsLayout {
+    static constexpr int K = C::K, N = C::N, E = C::E, NM = C::NM;
     static constexpr int NZ = K * N;
     static constexpr int NP = NZ * (NZ + 1) / 2;
     static constexpr int NR = E * NM;                  // residuals
@@ -76,20 +87,23 @@ struct WsLayout {
     static constexpr int oLW = oDD + ev(NZ);
     static constexpr int oFB = oLW + ev(NZ);
     static constexpr int oF = oFB + ev(NZ);
-    static constexpr int oGF = oF + ev(K * N * N);
-    static constexpr int oFF = oGF + ev(K * N * N);
-    static constexpr int oQ = oFF + ev(K * N * N);
-    static constexpr int PER_WARP = oQ + ev(NR);
-    static constexpr int oDt = WS_WARPS * PER_WARP;    // shared by the CTA
+    static constexpr int NBLK = C::HCONST ? 0 : K * N * N;       // per-node Jacobian blocks only for nonlinear models
+    static constexpr int oGF = oF + ev(NBLK);
+    static constexpr int oFF = oGF + ev(NBLK);
+    static constexpr int oQ = oFF + ev(NBLK);
+    static constexpr int NQ = (C::MEAS == 0) ? NR : E * 14;      // w*r per residual, or [G_e (10) | q_e (4)] per epoch
+    static constexpr int PER_WARP = oQ + ev(NQ);
+    static constexpr int oDt = C::WARPS * PER_WARP;    // shared by the CTA
     static constexpr int TOTAL = oDt + ev(K * K);
 };
 
 // objective J, its first-order rounding bound and (FULL) H (packed, shared memory), g
-template <int K, int N, int M, int E, int NM, int DYN, bool FULL>
+template <class C, bool FULL>
 __device__ __forceinline__ void ws_eval(const DevProb& P, double* sm, const double* Dt, const double* zc,
-                                        const double* Ug, const double* dg, const double* hlin,
+                                        const double* Ug, const double* dg, const double* h0,
                                         double& J_out, double& noise_out) {
-    typedef WsLayout<K, N, M, E, NM> L;
+    typedef WsLayout<C> L;
+    constexpr int K = C::K, N = C::N, M = C::M, E = C::E, NM = C::NM, DYN = C::DYN;
     constexpr int NZ = L::NZ;
     const int lane = threadIdx.x & 31;
     double* Hp = sm + L::oH;
@@ -103,7 +117,7 @@ __device__ __forceinline__ void ws_eval(const DevProb& P, double* sm, const doub
     double cost = 0.0, nse = 0.0;
 
     if (FULL) {
-        for (int p = lane; p < L::NP; p += 32) Hp[p] = hlin[p];      // constant part + linear measurements
+        for (int p = lane; p < L::NP; p += 32) Hp[p] = h0[p];        // constant part (+ linear measurements)
     }
     // node dynamics
     for (int k = lane; k < K; k += 32) {
@@ -115,7 +129,7 @@ __device__ __forceinline__ void ws_eval(const DevProb& P, double* sm, const doub
         ws_dyn<DYN, N, M>(P, x, u, f, F);
 #pragma unroll
         for (int i = 0; i < N; ++i) fb[k * N + i] = f[i];
-        if (FULL) {
+        if (FULL && !C::HCONST) {
 #pragma unroll
             for (int i = 0; i < N * N; ++i) Fm[k * N * N + i] = F[i];
         }
@@ -139,70 +153,181 @@ __device__ __forceinline__ void ws_eval(const DevProb& P, double* sm, const doub
     }
     __syncwarp();
     if (FULL) {
-        // per-node blocks GF = Lambda F, FF = F^T Lambda F; gradient of the dynamics cost
-        for (int t = lane; t < K * N * N; t += 32) {
-            const int k = t / (N * N), rem = t - k * N * N, a = rem / N, b = rem - a * N;
-            const double* Fk = Fm + k * N * N;
-            GF[t] = P.cw[k] * P.qinv[a] * Fk[a * N + b];
-            double s = 0.0;
+        if (!C::HCONST) {
+            // per-node blocks GF = Lambda F, FF = F^T Lambda F
+            for (int t = lane; t < K * N * N; t += 32) {
+                const int k = t / (N * N), rem = t - k * N * N, a = rem / N, b = rem - a * N;
+                const double* Fk = Fm + k * N * N;
+                GF[t] = P.cw[k] * P.qinv[a] * Fk[a * N + b];
+                double s = 0.0;
 #pragma unroll
-            for (int i = 0; i < N; ++i) s = fma(Fk[i * N + a] * (P.cw[k] * P.qinv[i]), Fk[i * N + b], s);
-            FF[t] = s;
+                for (int i = 0; i < N; ++i) s = fma(Fk[i * N + a] * (P.cw[k] * P.qinv[i]), Fk[i * N + b], s);
+                FF[t] = s;
+            }
         }
+        // gradient of the dynamics cost: g_(j,a) = sum_k Dt_kj lw_ka - sum_i F_j[i][a] lw_ji
         for (int t = lane; t < NZ; t += 32) {
             const int j = t / N, a = t - j * N;
             double s = 0.0;
 #pragma unroll
             for (int k = 0; k < K; ++k) s = fma(Dt[k * K + j], lw[k * N + a], s);
+            if (C::HCONST) {
 #pragma unroll
-            for (int i = 0; i < N; ++i) s = fma(-Fm[j * N * N + i * N + a], lw[j * N + i], s);
+                for (int i = 0; i < N; ++i) s = fma(-P.A[i * N + a], lw[j * N + i], s);
+            } else {
+#pragma unroll
+                for (int i = 0; i < N; ++i) s = fma(-Fm[j * N * N + i * N + a], lw[j * N + i], s);
+            }
             g[t] = s;
         }
         __syncwarp();
-        // H += -Dt_jl GF_j[b][a] - Dt_lj GF_l[a][b] (+ FF_j on the diagonal blocks), per node pair
-        for (int pr = lane; pr < K * (K + 1) / 2; pr += 32) {
-            const int pe = P.ptab[pr];
-            const int j = pe & 255, l = pe >> 8;
-            const double djl = Dt[j * K + l], dlj = Dt[l * K + j];
+        if (!C::HCONST) {
+            // H += -Dt_jl GF_j[b][a] - Dt_lj GF_l[a][b] (+ FF_j on the diagonal blocks), per node pair
+            for (int pr = lane; pr < K * (K + 1) / 2; pr += 32) {
+                const int pe = P.ptab[pr];
+                const int j = pe & 255, l = pe >> 8;
+                const double djl = Dt[j * K + l], dlj = Dt[l * K + j];
 #pragma unroll
-            for (int a = 0; a < N; ++a)
+                for (int a = 0; a < N; ++a)
 #pragma unroll
-                for (int b = 0; b < N; ++b) {
-                    if (j == l && b > a) continue;
-                    double s = -djl * GF[j * N * N + b * N + a] - dlj * GF[l * N * N + a * N + b];
-                    if (j == l) s += FF[j * N * N + a * N + b];
-                    Hp[pk(j * N + a, l * N + b)] += s;
-                }
+                    for (int b = 0; b < N; ++b) {
+                        if (j == l && b > a) continue;
+                        double s = -djl * GF[j * N * N + b * N + a] - dlj * GF[l * N * N + a * N + b];
+                        if (j == l) s += FF[j * N * N + a * N + b];
+                        Hp[pk(j * N + a, l * N + b)] += s;
+                    }
+            }
+            __syncwarp();
         }
-        __syncwarp();
     }
-    // measurements: residual t = e*NM + s measures component mc[s] at epoch e (record [y, w] at roff[t])
-    for (int t = lane; t < L::NR; t += 32) {
-        const int e = t / NM, s = t - e * NM;
-        const int c = P.act[P.rloc[t * NLPF_NIDX]];
-        const double* rec = dg + P.roff[t];
-        const double w = rec[1];
-        double v = 0.0;
+    if (C::MEAS == 0) {
+        // linear measurements: residual t = e*NM + s measures one state component at epoch e (record [y, w])
+        for (int t = lane; t < L::NR; t += 32) {
+            const int e = t / NM;
+            const int c = P.act[P.rloc[t * NLPF_NIDX]];
+            const double* rec = dg + P.roff[t];
+            const double w = rec[1];
+            double v = 0.0;
 #pragma unroll
-        for (int j = 0; j < K; ++j) v = fma(P.PhiT[j * E + e], zc[j * N + c], v);
-        const double r = (w != 0.0) ? rec[0] - v : 0.0;
-        cost = fma(w * r, r, cost);
-        nse += 2.0 * w * fabs(r) * (2.0 * fabs(rec[0]) + fabs(r));
-        if (FULL) qv[t] = w * r;
-        (void)s;
-    }
-    if (FULL) {
-        __syncwarp();
-        for (int t = lane; t < NZ; t += 32) {
-            const int j = t / N, a = t - j * N;
-            const int s = P.mslot[a];                      // slot of component a in an epoch's record set, or -1
-            if (s >= 0) {
-                double acc = 0.0;
+            for (int j = 0; j < K; ++j) v = fma(P.PhiT[j * E + e], zc[j * N + c], v);
+            const double r = (w != 0.0) ? rec[0] - v : 0.0;
+            cost = fma(w * r, r, cost);
+            nse += 2.0 * w * fabs(r) * (2.0 * fabs(rec[0]) + fabs(r));
+            if (FULL) qv[t] = w * r;
+        }
+        if (FULL) {
+            __syncwarp();
+            for (int t = lane; t < NZ; t += 32) {
+                const int j = t / N, a = t - j * N;
+                const int s = P.mslot[a];                  // slot of component a in an epoch's record set, or -1
+                if (s >= 0) {
+                    double acc = 0.0;
 #pragma unroll 10
-                for (int e = 0; e < E; ++e) acc = fma(P.Phi[e * K + j], qv[e * NM + s], acc);
-                g[t] -= acc;
+                    for (int e = 0; e < E; ++e) acc = fma(P.Phi[e * K + j], qv[e * NM + s], acc);
+                    g[t] -= acc;
+                }
             }
         }
+    } else {
+        // pseudoranges (measurements.py:56-70): one lane per epoch, NM satellite slots, components
+        // (c0,c1,c2 | cb); G_e = sum w grad grad^T (10 unique) and q_e = sum w r grad in registers
+        const int c0 = P.act[P.run_loc[0]], c1 = P.act[P.run_loc[1]], c2 = P.act[P.run_loc[2]], cb = P.act[P.run_loc[3]];
+        for (int e = lane; e < E; e += 32) {
+            double x0 = 0.0, x1 = 0.0, x2 = 0.0, xb = 0.0;
+#pragma unroll
+            for (int j = 0; j < K; ++j) {
+                const double ph = P.PhiT[j * E + e];
+                x0 = fma(ph, zc[j * N + c0], x0);
+                x1 = fma(ph, zc[j * N + c1], x1);
+                x2 = fma(ph, zc[j * N + c2], x2);
+                xb = fma(ph, zc[j * N + cb], xb);
+            }
+            double a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+            double g00 = 0, g10 = 0, g11 = 0, g20 = 0, g21 = 0, g22 = 0, g30 = 0, g31 = 0, g32 = 0, g33 = 0;
+#pragma unroll 2
+            for (int s = 0; s < NM; ++s) {
+                const double* rec = dg + P.roff[e * NM + s];
+                const double w = rec[1];
+                if (w == 0.0) continue;                     // masked slot: skipped, never 0 * NaN
+                const double d0 = x0 - rec[2], d1 = x1 - rec[3], d2 = x2 - rec[4];
+                const double rho = sqrt(d0 * d0 + d1 * d1 + d2 * d2);
+                const double r = rec[0] - (rho + xb);
+                cost = fma(w * r, r, cost);
+                nse += 2.0 * w * fabs(r) * (2.0 * fabs(rec[0]) + fabs(r));
+                if (FULL) {
+                    const double ir = 1.0 / rho;
+                    const double e0 = d0 * ir, e1 = d1 * ir, e2 = d2 * ir;
+                    const double wr = w * r;
+                    a0 = fma(wr, e0, a0); a1 = fma(wr, e1, a1); a2 = fma(wr, e2, a2); a3 += wr;
+                    const double w0 = w * e0, w1 = w * e1, w2 = w * e2;
+                    g00 = fma(w0, e0, g00); g10 = fma(w1, e0, g10); g11 = fma(w1, e1, g11);
+                    g20 = fma(w2, e0, g20); g21 = fma(w2, e1, g21); g22 = fma(w2, e2, g22);
+                    g30 += w0; g31 += w1; g32 += w2; g33 += w;
+                }
+            }
+            if (FULL) {
+                double* Ge = qv + e * 14;
+                Ge[0] = g00; Ge[1] = g10; Ge[2] = g11; Ge[3] = g20; Ge[4] = g21; Ge[5] = g22;
+                Ge[6] = g30; Ge[7] = g31; Ge[8] = g32; Ge[9] = g33;
+                Ge[10] = a0; Ge[11] = a1; Ge[12] = a2; Ge[13] = a3;
+            }
+        }
+        if (FULL) {
+            __syncwarp();
+            // gradient: g_(j,c_a) -= sum_e phi_ej q_e[a]
+            for (int t = lane; t < K * 4; t += 32) {
+                const int j = t >> 2, a = t & 3;
+                double acc = 0.0;
+#pragma unroll 3
+                for (int e = 0; e < E; ++e) acc = fma(P.Phi[e * K + j], qv[e * 14 + 10 + a], acc);
+                const int c = (a == 0) ? c0 : (a == 1) ? c1 : (a == 2) ? c2 : cb;
+                g[j * N + c] -= acc;
+            }
+            // H_(j,a),(l,b) += sum_e phi_ej phi_el G_e[a][b]: two lanes share a node pair (epoch halves),
+            // 10 unique values per pair (G_e symmetric), combined with one shuffle
+            constexpr int NPAIR = K * (K + 1) / 2;
+            constexpr int EH = (E + 1) / 2;
+            for (int it0 = 0; it0 < 2 * NPAIR; it0 += 32) {
+                const int it = it0 + lane;
+                const bool on = it < 2 * NPAIR;
+                const int pe = P.ptab[on ? (it >> 1) : 0];
+                const int j = pe & 255, l = pe >> 8;
+                const int eb = (it & 1) * EH, ee = (it & 1) ? E : EH;
+                double h[10];
+#pragma unroll
+                for (int q = 0; q < 10; ++q) h[q] = 0.0;
+                if (on) {
+                    for (int e = eb; e < ee; ++e) {
+                        const double pp = P.Phi[e * K + j] * P.Phi[e * K + l];
+                        const double* Ge = qv + e * 14;
+#pragma unroll
+                        for (int q = 0; q < 10; ++q) h[q] = fma(pp, Ge[q], h[q]);
+                    }
+                }
+#pragma unroll
+                for (int q = 0; q < 10; ++q) h[q] += __shfl_xor_sync(0xffffffffu, h[q], 1);
+                if (on && !(it & 1)) {
+                    const int cc[4] = {c0, c1, c2, cb};
+                    int q = 0;
+#pragma unroll
+                    for (int a = 0; a < 4; ++a)
+#pragma unroll
+                        for (int b = 0; b <= a; ++b, ++q) {
+                            // (a,b) and, off the diagonal of G, its mirror (b,a); inside a diagonal node block only
+                            // the entry of the lower triangle exists
+                            const int r1 = j * N + cc[a], k1 = l * N + cc[b];
+                            if (k1 <= r1) Hp[pk(r1, k1)] += h[q];
+                            if (a != b) {
+                                const int r2 = j * N + cc[b], k2 = l * N + cc[a];
+                                if (k2 <= r2 && !(j == l)) Hp[pk(r2, k2)] += h[q];
+                                if (j == l && k1 > r1) Hp[pk(r2, k2)] += h[q];
+                            }
+                        }
+                }
+            }
+        }
+    }
+    if (FULL) {
         __syncwarp();
         // Gauss-Newton diagonal for the damping, then the exact second-order dynamics term
         double* dd = sm + L::oDD;
@@ -341,17 +466,18 @@ __device__ __forceinline__ bool ws_ldl(const DevProb& P, double* Hp, double* xs,
     return true;
 }
 
-template <int K, int N, int M, int E, int NM, int DYN>
-__global__ void __launch_bounds__(WS_WARPS * 32, 4)
+template <class C>
+__global__ void __launch_bounds__(C::WARPS * 32, 512 / (C::WARPS * 32))
 wsolve_kernel(const __grid_constant__ DevProb P, int B, double* __restrict__ z_io, const double* __restrict__ U,
               const double* __restrict__ data, nlpf_opts opt, double* __restrict__ cost_out, int* __restrict__ iters_out,
               int* __restrict__ status_out, double* __restrict__ hlin_all, int* __restrict__ counter) {
-    typedef WsLayout<K, N, M, E, NM> L;
+    typedef WsLayout<C> L;
+    constexpr int K = C::K, N = C::N, M = C::M, E = C::E, NM = C::NM;
     constexpr int NZ = L::NZ;
     extern __shared__ double smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     double* Dt = smem + L::oDt;
-    for (int i = threadIdx.x; i < K * K; i += WS_WARPS * 32) Dt[i] = P.Dt[i];
+    for (int i = threadIdx.x; i < K * K; i += C::WARPS * 32) Dt[i] = P.Dt[i];
     __syncthreads();
     double* sm = smem + warp * L::PER_WARP;
     double* Hp = sm + L::oH;
@@ -369,8 +495,11 @@ wsolve_kernel(const __grid_constant__ DevProb P, int B, double* __restrict__ z_i
         if (b >= B) break;
         const double* Ug = U + (size_t)b * K * (M > 0 ? M : 1);
         const double* dg = data + (size_t)b * P.Ldata;
-        double* hlin = hlin_all + (size_t)b * L::NP;
+        const double* hlin = P.Hc;
         for (int i = lane; i < NZ; i += 32) zs[i] = z_io[(size_t)b * NZ + i];
+        if (C::MEAS == 0) {
+        double* hl = hlin_all + (size_t)b * L::NP;
+        hlin = hl;
         // constant H of this window: Hc + sum_e (phi_e phi_e^T) (x) diag(w_e)
         for (int p = lane; p < L::NP; p += 32) Hp[p] = P.Hc[p];
         double* wts = sm + L::oQ;                          // measurement weights of this window
@@ -395,12 +524,13 @@ wsolve_kernel(const __grid_constant__ DevProb P, int B, double* __restrict__ z_i
             }
         }
         __syncwarp();
-        for (int p = lane; p < L::NP; p += 32) hlin[p] = Hp[p];
+        for (int p = lane; p < L::NP; p += 32) hl[p] = Hp[p];
+        }
         __syncwarp();
 
         int iters = 0, status = NLPF_ST_MAXITER, floor_steps = 0;
         double lam = opt.lam0, J, nse0;
-        ws_eval<K, N, M, E, NM, DYN, true>(P, sm, Dt, zs, Ug, dg, hlin, J, nse0);
+        ws_eval<C, true>(P, sm, Dt, zs, Ug, dg, hlin, J, nse0);
         double merit = 0.5 * J;
         if (!isfinite(merit)) {
             status = NLPF_ST_NUMERIC;
@@ -417,7 +547,7 @@ wsolve_kernel(const __grid_constant__ DevProb P, int B, double* __restrict__ z_i
                 while (lam <= 1e18) {
                     if (!h_valid) {
                         double Jd, nd;
-                        ws_eval<K, N, M, E, NM, DYN, true>(P, sm, Dt, zs, Ug, dg, hlin, Jd, nd);
+                        ws_eval<C, true>(P, sm, Dt, zs, Ug, dg, hlin, Jd, nd);
                         h_valid = true;
                     }
                     for (int i = lane; i < NZ; i += 32) {
@@ -439,7 +569,7 @@ wsolve_kernel(const __grid_constant__ DevProb P, int B, double* __restrict__ z_i
                         pred = wsum(pred);
                         __syncwarp();
                         if (fin == 0.0) {
-                            ws_eval<K, N, M, E, NM, DYN, false>(P, sm, Dt, zt, Ug, dg, hlin, Jt, nset);
+                            ws_eval<C, false>(P, sm, Dt, zt, Ug, dg, hlin, Jt, nset);
                             const double mt = 0.5 * Jt;
                             if (isfinite(mt) && mt < merit) { accepted = true; dzmax = dmx; break; }
                             const double nb = nse0 + nset;
@@ -463,7 +593,7 @@ wsolve_kernel(const __grid_constant__ DevProb P, int B, double* __restrict__ z_i
                 lam = fmax(lam / 10.0, 1e-12);
                 ++iters;
                 __syncwarp();
-                ws_eval<K, N, M, E, NM, DYN, true>(P, sm, Dt, zs, Ug, dg, hlin, J, nse0);
+                ws_eval<C, true>(P, sm, Dt, zs, Ug, dg, hlin, J, nse0);
                 merit = 0.5 * J;
                 if (dzmax < opt.tol_step * (1.0 + zm)) { status = NLPF_ST_CONVERGED; break; }
                 if (at_floor && ++floor_steps >= 5) { status = NLPF_ST_CONVERGED; break; }
@@ -479,11 +609,11 @@ wsolve_kernel(const __grid_constant__ DevProb P, int B, double* __restrict__ z_i
     }
 }
 
-template <int K, int N, int M, int E, int NM, int DYN>
+template <class C>
 int ws_launch(nlpf_problem* p, int B, double* z, const double* U, const double* data, const nlpf_opts* o,
               double* cost_out, int* iters_out, int* status_out, double* hlin, int* counter, cudaStream_t st) {
-    typedef WsLayout<K, N, M, E, NM> L;
-    auto kern = wsolve_kernel<K, N, M, E, NM, DYN>;
+    typedef WsLayout<C> L;
+    auto kern = wsolve_kernel<C>;
     const size_t smem = sizeof(double) * L::TOTAL;
     static bool attr = false;
     if (!attr) {
@@ -494,20 +624,26 @@ int ws_launch(nlpf_problem* p, int B, double* z, const double* U, const double* 
     if (nlpf_check_cuda(cudaMemsetAsync(counter, 0, sizeof(int), st), "wsolve counter reset")) return NLPF_E_CUDA;
     int per_sm = (int)((227 * 1024) / (smem + 1024));
     if (per_sm < 1) per_sm = 1;
-    if (per_sm > 4) per_sm = 4;
+    if (per_sm > 512 / (C::WARPS * 32)) per_sm = 512 / (C::WARPS * 32);
     int grid = 148 * per_sm;
-    const int need = (B + WS_WARPS - 1) / WS_WARPS;
+    const int need = (B + C::WARPS - 1) / C::WARPS;
     if (grid > need) grid = need;
-    kern<<<grid, WS_WARPS * 32, smem, st>>>(p->d, B, z, U, data, *o, cost_out, iters_out, status_out, hlin, counter);
+    kern<<<grid, C::WARPS * 32, smem, st>>>(p->d, B, z, U, data, *o, cost_out, iters_out, status_out, hlin, counter);
     return nlpf_check_cuda(cudaGetLastError(), "wsolve_kernel launch");
 }
 
+typedef WsCfg<21, 2, 1, 50, 2, NLPF_DYN_VDP, 0, 4> CfgVdp;          // van der Pol MHE (BASELINE configs[1])
+typedef WsCfg<21, 2, 2, 50, 2, NLPF_DYN_AFFINE, 0, 4> CfgExample;   // estimation_example.py
+typedef WsCfg<11, 5, 3, 51, 12, NLPF_DYN_AFFINE, 1, 2> CfgGnss;     // gnss_stationary.py MHE (BASELINE configs[2])
+
 }  // namespace
 
-// instantiated shapes: (K, N, M, E, NM, DYN).  Returns the variant index or -1.
-extern "C" int nlpf_ws_variant(int K, int N, int M, int E, int NM, int dyn) {
-    if (K == 21 && N == 2 && M == 1 && E == 50 && NM == 2 && dyn == NLPF_DYN_VDP) return 0;      // van der Pol MHE (BASELINE configs[1])
-    if (K == 21 && N == 2 && M == 2 && E == 50 && NM == 2 && dyn == NLPF_DYN_AFFINE) return 1;   // estimation_example.py
+// instantiated shapes.  meas: 0 linear state measurements (NM components per epoch), 1 pseudoranges
+// (NM satellite slots per epoch).  Returns the variant index or -1.
+extern "C" int nlpf_ws_variant(int K, int N, int M, int E, int NM, int dyn, int meas) {
+    if (meas == 0 && K == 21 && N == 2 && M == 1 && E == 50 && NM == 2 && dyn == NLPF_DYN_VDP) return 0;
+    if (meas == 0 && K == 21 && N == 2 && M == 2 && E == 50 && NM == 2 && dyn == NLPF_DYN_AFFINE) return 1;
+    if (meas == 1 && K == 11 && N == 5 && M == 3 && E == 51 && NM == 12 && dyn == NLPF_DYN_AFFINE) return 2;
     return -1;
 }
 
@@ -515,8 +651,9 @@ extern "C" int nlpf_ws_launch(int variant, nlpf_problem* p, int B, double* z, co
                               const nlpf_opts* o, double* cost_out, int* iters_out, int* status_out, double* hlin,
                               int* counter, cudaStream_t st) {
     switch (variant) {
-        case 0: return ws_launch<21, 2, 1, 50, 2, NLPF_DYN_VDP>(p, B, z, U, data, o, cost_out, iters_out, status_out, hlin, counter, st);
-        case 1: return ws_launch<21, 2, 2, 50, 2, NLPF_DYN_AFFINE>(p, B, z, U, data, o, cost_out, iters_out, status_out, hlin, counter, st);
+        case 0: return ws_launch<CfgVdp>(p, B, z, U, data, o, cost_out, iters_out, status_out, hlin, counter, st);
+        case 1: return ws_launch<CfgExample>(p, B, z, U, data, o, cost_out, iters_out, status_out, hlin, counter, st);
+        case 2: return ws_launch<CfgGnss>(p, B, z, U, data, o, cost_out, iters_out, status_out, hlin, counter, st);
     }
     nlpf_set_error("unknown warp-solve variant %d", variant);
     return NLPF_E_ARG;
