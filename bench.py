@@ -29,15 +29,18 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 # algorithmic flop per Gauss-Newton iteration and compulsory bytes per window
-FLOP_PER_ITER = {"vdp": 146480.0, "gnss": 297342.0, "ekf": 9178.0, "ls": 806.0}
-BYTES_PER_WINDOW = {"vdp": 2104.0 + 360.0, "gnss": 25184.0 + 464.0, "ekf": 448.0, "ls": 416.0}
+FLOP_PER_ITER = {"vdp": 146480.0, "gnss": 297342.0, "car": 172272.0, "ekf": 9178.0, "ls": 806.0}
+BYTES_PER_WINDOW = {"vdp": 2104.0 + 360.0, "gnss": 25184.0 + 464.0, "car": 9840.0 + 456.0, "ekf": 448.0, "ls": 416.0}
 WORKLOAD_DESC = {
     "vdp": "van_der_pol MHE windows (K=21 nodes, n=2, m=1, 50 full-state epochs, Q=1e-2 I, nz=42)",
     "gnss": "stationary-receiver GNSS MHE windows (K=11, n=5, m=3, 51 epochs x 12 pseudoranges, nz=55)",
+    "car": "vehicle MHE chains (autonomous-car.py shape: K=6, n=9, m=2, 21 epochs x 11 pseudoranges, arrival cost, bounds, nz=54), "
+           "receding-horizon windows DT = 1 s, warm-started",
     "ekf": "5-state GNSS EKF (utils/ekf.py + utils/gnss.py), 256 filters x 64 predict/update steps, 12 satellites",
     "ls": "iterative GNSS least squares (utils/leastsquares.py:19-42), 16384 independent epochs x 12 satellites, ECEF",
 }
 METRIC = {"vdp": ("solved_windows_per_sec", "windows/s"), "gnss": ("solved_windows_per_sec", "windows/s"),
+          "car": ("solved_windows_per_sec", "windows/s"),
           "ekf": ("ekf_steps_per_sec", "filter-steps/s"), "ls": ("ls_epochs_per_sec", "epochs/s")}
 
 
@@ -305,17 +308,131 @@ def run_aux(args):
     print(json.dumps(line))
     return 0
 
+
+# ---------------------------------------------------------------------------------------------
+# vehicle chains (BASELINE configs[3]): B runs x W chained windows per step, all on the device
+# ---------------------------------------------------------------------------------------------
+def _cpu_car_chain(b):
+    from oracle import nls
+    d, ch = _CPU["d"], _CPU["ch"]
+    z = np.zeros(d.nz)
+    xp = ch["xhat0"][b].copy()
+    it = 0
+    for w in range(ch["data"].shape[0]):
+        z, info = nls.solve(d, nls.Window(d, U=ch["U"][w, b], data=ch["data"][w, b], xprior=xp), z)
+        xp = (ch["PhiDT"] @ z.reshape(d.K, d.nv))[0]
+        it += info["iters"]
+    return it
+
+
+def cpu_car_windows_per_sec(runs, windows, cores):
+    from nlp_filter_b200 import shapes, synth
+    d = shapes.car()
+    _CPU["d"], _CPU["ch"] = d, synth.car_chain_batch(d, runs, windows, seed=4000)
+    ctx = mp.get_context("fork")
+    with ctx.Pool(cores) as pool:
+        t0 = time.perf_counter()
+        its = pool.map(_cpu_car_chain, range(runs))
+        dt = time.perf_counter() - t0
+    return runs * windows / dt, float(np.sum(its)) / (runs * windows)
+
+
+def run_car(args):
+    cores = os.cpu_count() or 1
+    cpu_base = None
+    if not args.no_cpu_baseline:
+        runs, wins = (args.cpu_windows or 2 * cores), 3
+        v, it = cpu_car_windows_per_sec(runs, wins, cores)
+        cpu_base = {"value": v, "unit": "windows/s", "cores": cores, "kind": "port",
+                    "sample": "%d runs x %d chained windows of the same synthetic workload, NumPy restatement oracle/nls.py, "
+                              "%d-process pool, mean %.1f iterations/window" % (runs, wins, cores, it)}
+    import torch
+    from nlp_filter_b200 import engine, shapes, synth
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the hot path has no CPU fallback")
+    torch.cuda.set_device(0)
+    B, W = args.windows if args.windows != 4096 else 2048, args.chain
+    d = shapes.car()
+    ch = synth.car_chain_batch(d, B, W, seed=4000)
+    prob = engine.WindowProblem(d)
+    dev = lambda a: torch.as_tensor(np.ascontiguousarray(a)).cuda()
+    U_all, data_all, xh0 = dev(ch["U"]), dev(ch["data"]), dev(ch["xhat0"])
+    hU, hdata = torch.as_tensor(ch["U"]).pin_memory(), torch.as_tensor(ch["data"]).pin_memory()
+    z = torch.zeros((B, d.nz), dtype=torch.float64, device="cuda")
+    xp = torch.empty_like(xh0)
+    h_out = torch.empty((B, d.nz), dtype=torch.float64).pin_memory()
+    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device="cuda")
+    peak_fp64 = engine.fp64_peak_tflops()
+    stats = {}
+
+    def step_device():
+        z.zero_()
+        xp.copy_(xh0)
+        stats["it"], stats["bad"] = engine.solve_chain(prob, z, U_all, data_all, xp, ch["PhiDT"])
+
+    def step_e2e():
+        U_all.copy_(hU, non_blocking=True)
+        data_all.copy_(hdata, non_blocking=True)
+        step_device()
+        h_out.copy_(z, non_blocking=True)
+
+    def timed(fn):
+        for _ in range(args.warmup):
+            flush.zero_(); fn()
+        torch.cuda.synchronize()
+        evs = []
+        for _ in range(args.steps):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); fn(); e1.record()
+            evs.append((e0, e1))
+        torch.cuda.synchronize()
+        return sum(a.elapsed_time(b) for a, b in evs)
+
+    sampler = ClockSampler(0)
+    sampler.start()
+    ms_dev = timed(step_device)
+    it_mean = float(stats["it"].to(torch.float64).mean().item()) / W
+    nbad = int(stats["bad"].sum().item())
+    ms_e2e = timed(step_e2e)
+    clocks = sampler.stop()
+    units = B * W
+    ms_step = ms_dev / args.steps
+    achieved = FLOP_PER_ITER["car"] * it_mean * units / (ms_step * 1e-3) / 1e12
+    line = {"metric": "solved_windows_per_sec", "value": units * args.steps / (ms_dev * 1e-3), "unit": "windows/s", "n_gpus": 1,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": WORKLOAD_DESC["car"], "runs": B, "chained_windows_per_run": W, "windows_per_step": units,
+                       "l2": "256 MB buffer written between timed iterations; chain inputs (%d MB) exceed L2" % (data_all.numel() * 8 // 2 ** 20),
+                       "mean_iterations_per_window": it_mean, "windows_not_converged": nbad},
+            "e2e": {"value": units * args.steps / (ms_e2e * 1e-3), "unit": "windows/s",
+                    "h2d_bytes_per_step": int(hU.numel() * 8 + hdata.numel() * 8), "d2h_bytes_per_step": int(h_out.numel() * 8),
+                    "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": args.steps * W * 2,
+            "roofline": {"bound": "fp64", "kernel": "solve_kernel_pr", "achieved": achieved, "peak": peak_fp64, "unit": "TFLOP/s",
+                         "frac": achieved / peak_fp64, "traffic": None, "kernel_ms": ms_step / W,
+                         "peak_source": "FP64 FMA probe measured in this run",
+                         "note": "kernel_ms = step time / chained windows (solve + sample kernels per window)"},
+            "clocks": clocks}
+    if cpu_base is not None:
+        line["cpu_baseline"] = cpu_base
+    print(json.dumps(line))
+    return 0
+
 # ---------------------------------------------------------------------------------------------
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
     cores = os.cpu_count() or 1
-    n = args.cpu_windows or {"vdp": 256, "gnss": 64, "ekf": 64, "ls": 2048}[args.workload]
+    n = args.cpu_windows or {"vdp": 256, "gnss": 64, "ekf": 64, "ls": 2048, "car": 0}[args.workload]
     vals = []
     for s in range(args.warmup + args.steps):
         t0 = time.perf_counter()
-        if args.workload in ("ekf", "ls"):
+        if args.workload == "car":
+            v, it = cpu_car_windows_per_sec(2 * cores, 3, cores)
+            n = 2 * cores * 3
+        elif args.workload in ("ekf", "ls"):
             v, it = cpu_aux_per_sec(args.workload, n, cores), 0.0
         else:
             v, it = cpu_path_windows_per_sec(args.workload, n, cores, seed=2000 + s)
@@ -497,7 +614,8 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="vdp", choices=["vdp", "gnss", "ekf", "ls"])
+    ap.add_argument("--workload", default="vdp", choices=["vdp", "gnss", "car", "ekf", "ls"])
+    ap.add_argument("--chain", type=int, default=25, help="chained windows per run (car workload; BASELINE names 200)")
     ap.add_argument("--windows", type=int, default=4096, help="windows per GPU per step")
     ap.add_argument("--cpu-windows", type=int, default=0, help="size of the CPU-path sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -507,6 +625,8 @@ def main():
         return run_reference(args)
     if args.workload in ("ekf", "ls"):
         return run_aux(args)
+    if args.workload == "car":
+        return run_car(args)
     return run_ours(args)
 
 

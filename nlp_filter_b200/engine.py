@@ -203,6 +203,31 @@ class HostBatch(object):
             cur.wait_event(done)
 
 
+def solve_chain(prob, z, U_all, data_all, xprior, PhiDT, opts=None, keep=False):
+    """Receding-horizon chains of B independent runs, all on the device (autonomous-car.py:232-288):
+    for every window w: solve from the previous window's solution (warm start), then the next arrival
+    cost is centred on this solution sampled at t = DT.  z (B, nz) and xprior (B, n) are updated in
+    place; U_all (W, B, K, m), data_all (W, B, Ldata) device tensors.  Nothing is synchronised.
+    Returns (iters_sum (B,), bad (B,) windows that did not converge[, Z (W, B, nz)])."""
+    d = prob.desc
+    W, B = data_all.shape[0], z.shape[0]
+    cost = torch.empty((B,), dtype=torch.float64, device=z.device)
+    iters = torch.empty((B,), dtype=torch.int32, device=z.device)
+    status = torch.empty((B,), dtype=torch.int32, device=z.device)
+    it_sum = torch.zeros((B,), dtype=torch.int64, device=z.device)
+    bad = torch.zeros((B,), dtype=torch.int64, device=z.device)
+    Z = torch.empty((W, B, d.nz), dtype=torch.float64, device=z.device) if keep else None
+    PhiDT = _f8(PhiDT, (-1, d.K))
+    for w in range(W):
+        prob.solve(z, None if U_all is None else U_all[w], data_all[w], xprior, None, opts, out=(cost, iters, status))
+        xprior.copy_(prob.sample(z, PhiDT)[:, 0, :])
+        it_sum += iters
+        bad += (status > 1)
+        if keep:
+            Z[w].copy_(z)
+    return (it_sum, bad, Z) if keep else (it_sum, bad)
+
+
 def solve_windows_host(prob, z0, U=None, data=None, xprior=None, opts=None):
     """Solve B windows held in NumPy arrays; returns (z, J, iters, status) as NumPy arrays."""
     z0 = np.asarray(z0, dtype=np.float64).reshape(-1, prob.desc.nz)

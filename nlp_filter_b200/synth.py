@@ -98,3 +98,89 @@ def gnss_batch(desc, B, seed=3000, n_sat=12, r_pr=100.0):
     z0[:, :, 4] = a_g[:, None]
     U = np.zeros((B, K, 3))
     return dict(z0=z0.reshape(B, -1), U=U, data=data, xprior=None, pos=pos, b0=b0, alpha=alpha)
+
+
+# ---------------------------------------------------------------------------------------------
+# vehicle chains (autonomous-car.py:184-288 shape): B runs, each a chain of receding-horizon windows
+# ---------------------------------------------------------------------------------------------
+def _vehicle_rhs(x, u, par):
+    """Single-track model with linear tyres (nlp/dynamics.py:148-164) + clock (166-174), vectorised
+    over runs: x (B,9), u (B,2)."""
+    C_AF, C_AR, M, D_F, D_R, I_Z = par[:6]
+    psi, vx, vy, r = x[:, 2], x[:, 3], x[:, 4], x[:, 5]
+    den = vx + 0.001
+    Fyr = -C_AR * (vy - D_R * r) / den
+    Fyf = -C_AF * ((vy + D_F * r) / den - u[:, 1])
+    d = np.zeros_like(x)
+    d[:, 0] = vx * np.cos(psi) - vy * np.sin(psi)
+    d[:, 1] = vx * np.sin(psi) + vy * np.cos(psi)
+    d[:, 2] = r
+    d[:, 3] = (-Fyf * np.sin(u[:, 1]) + u[:, 0]) / M + r * vy
+    d[:, 4] = (Fyf * np.cos(u[:, 1]) + Fyr) / M - r * vx
+    d[:, 5] = (D_F * Fyf * np.cos(u[:, 1]) - D_R * Fyr) / I_Z
+    d[:, 6] = x[:, 7]
+    return d
+
+
+def car_chain_batch(desc, B, n_windows, seed=4000, DT=1.0, alpha=200.0, r_pr=10.0, dt_gnss=0.1):
+    """Synthetic vehicle runs: truth by RK4 (dt 0.01) of the model the estimator uses, smooth random
+    throttle/steering, 11 satellites, pseudoranges at 10 Hz with clock drift `alpha` and variance
+    `r_pr` (utils/vehicle_sim.py:119-121).  Returns per-window inputs for the whole chain:
+    U (n_windows, B, K, 2), data (n_windows, B, Ldata), xhat0 (B, 9), truth at window starts."""
+    rng = np.random.default_rng(seed)
+    par = desc.dyn_par
+    T = desc.T
+    dt = 0.01
+    t_end = (n_windows - 1) * DT + T
+    nstep = int(round(t_end / dt))
+    ph = rng.uniform(0, 2 * np.pi, (B, 2))
+    amp = rng.uniform(0.5, 1.5, (B, 2))
+
+    def ctrl(t):
+        return np.stack([400.0 + 300.0 * amp[:, 0] * np.sin(0.3 * t + ph[:, 0]),
+                         0.03 * amp[:, 1] * np.sin(0.5 * t + ph[:, 1])], 1)
+
+    x = np.zeros((B, 9))
+    x[:, 2] = rng.uniform(-1.0, 1.0, B)
+    x[:, 3] = 10.0
+    x[:, 7] = alpha
+    xs = np.zeros((nstep + 1, B, 9))
+    xs[0] = x
+    for i in range(nstep):
+        t = i * dt
+        k1 = _vehicle_rhs(x, ctrl(t), par)
+        k2 = _vehicle_rhs(x + 0.5 * dt * k1, ctrl(t + 0.5 * dt), par)
+        k3 = _vehicle_rhs(x + 0.5 * dt * k2, ctrl(t + 0.5 * dt), par)
+        k4 = _vehicle_rhs(x + dt * k3, ctrl(t + dt), par)
+        x = x + dt / 6 * (k1 + 2 * k2 + 2 * k3 + k4)
+        xs[i + 1] = x
+    n_sat = 11
+    el = np.arcsin(rng.uniform(np.sin(np.deg2rad(15)), 1.0, n_sat))
+    az = rng.uniform(0, 2 * np.pi, n_sat)
+    rad = rng.uniform(2.0e7, 2.6e7, n_sat)
+    sat = np.stack([rad * np.cos(el) * np.sin(az), rad * np.cos(el) * np.cos(az), rad * np.sin(el)], 1)
+    tn = desc.cpm.tau2t(desc.cpm.tau)
+    n_ep = desc.E
+    K = desc.K
+    U = np.zeros((n_windows, B, K, 2))
+    data = np.zeros((n_windows, B, desc.Ldata))
+    off = desc.roff.reshape(n_ep, n_sat)
+    every = int(round(dt_gnss / dt))
+    w_meas = dt_gnss * (1.0 / r_pr)
+    for w in range(n_windows):
+        t0 = w * DT
+        for k in range(K):
+            U[w, :, k, :] = ctrl(t0 + tn[k])
+        i0 = int(round(t0 / dt))
+        for e in range(n_ep):
+            xe = xs[i0 + e * every]
+            p = np.stack([xe[:, 0], xe[:, 1], xe[:, 8]], 1)
+            rho = np.sqrt(np.sum((p[:, None, :] - sat[None, :, :]) ** 2, 2))
+            pr = rho + xe[:, 6:7] + rng.normal(0.0, np.sqrt(r_pr), rho.shape)
+            for j in range(n_sat):
+                o = off[e, j]
+                data[w, :, o] = pr[:, j]
+                data[w, :, o + 1] = w_meas
+                data[w, :, o + 2:o + 5] = sat[j]
+    starts = xs[(np.arange(n_windows) * int(round(DT / dt)))]
+    return dict(U=U, data=data, xhat0=xs[0].copy(), truth=starts, PhiDT=desc.cpm.basisMatrix([DT]))

@@ -98,3 +98,34 @@ def test_256_filters_64_steps_against_oracle_subset():
         ref, Sref = ekf_ls.ekf_run(0, x0[b], np.eye(5), u[b], z[b], sat[b], nsat[b], Q, 100.0, 1.0)
         assert np.max(np.abs(traj[b] - ref) / (1 + np.abs(ref))) < 1e-9
         assert np.max(np.abs(S_.cpu().numpy()[b] - Sref)) < 1e-9
+
+
+def test_vehicle_chains_against_oracle_and_truth():
+    """Synthetic receding-horizon vehicle chains (autonomous-car.py:232-288 pattern): device-side chain
+    driver vs the oracle run through the same chain, and estimates close to the simulated truth."""
+    import torch
+    from nlp_filter_b200 import engine
+    from oracle import nls
+    d = shapes.car()
+    B, W = 64, 5
+    ch = synth.car_chain_batch(d, B, W, seed=11)
+    prob = engine.WindowProblem(d)
+    dev = lambda a: torch.as_tensor(np.ascontiguousarray(a)).cuda()
+    z = torch.zeros((B, d.nz), dtype=torch.float64, device="cuda")
+    xp = dev(ch["xhat0"])
+    it_sum, bad, Z = engine.solve_chain(prob, z, dev(ch["U"]), dev(ch["data"]), xp, ch["PhiDT"], keep=True)
+    torch.cuda.synchronize()
+    assert int(bad.sum()) == 0
+    Z = Z.cpu().numpy()
+    V = Z[-1].reshape(B, d.K, d.nv)
+    assert np.median(np.linalg.norm(V[:, 0, :2] - ch["truth"][-1][:, :2], axis=1)) < 1.5      # metres, GNSS noise level
+    for b in (0, 17, 63):
+        zo = np.zeros(d.nz)
+        xpo = ch["xhat0"][b].copy()
+        for w in range(W):
+            zo, info = nls.solve(d, nls.Window(d, U=ch["U"][w, b], data=ch["data"][w, b], xprior=xpo), zo)
+            xpo = (ch["PhiDT"] @ zo.reshape(d.K, d.nv))[0]
+            Vg, Vo = Z[w, b].reshape(d.K, d.nv), zo.reshape(d.K, d.nv)
+            assert np.max(np.abs(Vg[:, [0, 1, 8]] - Vo[:, [0, 1, 8]])) < 1e-3                  # positions within 1 mm
+            assert np.max(np.abs(Vg - Vo) / (1 + np.abs(Vo))) < 1e-5
+    prob.close()
