@@ -29,29 +29,31 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 # algorithmic flop per Gauss-Newton iteration and compulsory bytes per window
-FLOP_PER_ITER = {"vdp": 146480.0, "gnss": 297342.0, "car": 172272.0, "ekf": 9178.0, "ls": 806.0}
-BYTES_PER_WINDOW = {"vdp": 2104.0 + 360.0, "gnss": 25184.0 + 464.0, "car": 9840.0 + 456.0, "ekf": 448.0, "ls": 416.0}
+FLOP_PER_ITER = {"vdp": 146480.0, "gnss": 297342.0, "2rx": 1338750.0, "car": 172272.0, "ekf": 9178.0, "ls": 806.0}
+BYTES_PER_WINDOW = {"vdp": 2104.0 + 360.0, "gnss": 25184.0 + 464.0, "2rx": 7920.0 + 904.0, "car": 9840.0 + 456.0, "ekf": 448.0, "ls": 416.0}
 WORKLOAD_DESC = {
     "vdp": "van_der_pol MHE windows (K=21 nodes, n=2, m=1, 50 full-state epochs, Q=1e-2 I, nz=42)",
     "gnss": "stationary-receiver GNSS MHE windows (K=11, n=5, m=3, 51 epochs x 12 pseudoranges, nz=55)",
+    "2rx": "two-receiver GNSS MHE scenarios (gnss-multi-receiver.py shape: K=11, n=10, m=6, 120 pseudorange slots + 51 range + "
+           "51 heading residuals, arrival cost, zA == zB folded, nz=99), 1024 scenarios in total sharded over the GPUs",
     "car": "vehicle MHE chains (autonomous-car.py shape: K=6, n=9, m=2, 21 epochs x 11 pseudoranges, arrival cost, bounds, nz=54), "
            "receding-horizon windows DT = 1 s, warm-started",
     "ekf": "5-state GNSS EKF (utils/ekf.py + utils/gnss.py), 256 filters x 64 predict/update steps, 12 satellites",
     "ls": "iterative GNSS least squares (utils/leastsquares.py:19-42), 16384 independent epochs x 12 satellites, ECEF",
 }
 METRIC = {"vdp": ("solved_windows_per_sec", "windows/s"), "gnss": ("solved_windows_per_sec", "windows/s"),
-          "car": ("solved_windows_per_sec", "windows/s"),
+          "car": ("solved_windows_per_sec", "windows/s"), "2rx": ("solved_windows_per_sec", "windows/s"),
           "ekf": ("ekf_steps_per_sec", "filter-steps/s"), "ls": ("ls_epochs_per_sec", "epochs/s")}
 
 
 def make_problem(workload):
     from nlp_filter_b200 import shapes
-    return shapes.vdp_mhe() if workload == "vdp" else shapes.gnss()
+    return {"vdp": shapes.vdp_mhe, "gnss": shapes.gnss, "2rx": shapes.two_receiver}[workload]()
 
 
 def make_batch(desc, workload, B, seed):
     from nlp_filter_b200 import synth
-    return synth.vdp_mhe_batch(desc, B, seed=seed) if workload == "vdp" else synth.gnss_batch(desc, B, seed=seed)
+    return {"vdp": synth.vdp_mhe_batch, "gnss": synth.gnss_batch, "2rx": synth.two_receiver_batch}[workload](desc, B, seed=seed)
 
 
 # ---------------------------------------------------------------------------------------------
@@ -70,7 +72,7 @@ def _cpu_init(workload, B, seed):
 def _cpu_solve(i):
     from oracle import nls
     d, bt = _CPU["d"], _CPU["bt"]
-    win = nls.Window(d, U=bt["U"][i], data=bt["data"][i])
+    win = nls.Window(d, U=bt["U"][i], data=bt["data"][i], xprior=None if bt.get("xprior") is None else bt["xprior"][i])
     z, info = nls.solve(d, win, bt["z0"][i])
     return info["iters"]
 
@@ -425,7 +427,7 @@ def run_reference(args):
     if rank != 0:
         return 0
     cores = os.cpu_count() or 1
-    n = args.cpu_windows or {"vdp": 256, "gnss": 64, "ekf": 64, "ls": 2048, "car": 0}[args.workload]
+    n = args.cpu_windows or {"vdp": 256, "gnss": 64, "2rx": 48, "ekf": 64, "ls": 2048, "car": 0}[args.workload]
     vals = []
     for s in range(args.warmup + args.steps):
         t0 = time.perf_counter()
@@ -461,7 +463,7 @@ def run_ours(args):
     cpu_base = None
     if world == 1 and rank == 0 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
-        n = args.cpu_windows or (512 if args.workload == "vdp" else 128)
+        n = args.cpu_windows or {"vdp": 512, "gnss": 128, "2rx": 64}[args.workload]
         v, it = cpu_path_windows_per_sec(args.workload, n, cores)        # before CUDA is initialised (fork)
         cpu_base = {"value": v, "unit": "windows/s", "cores": cores, "kind": "port",
                     "sample": "%d windows of the same synthetic workload (seed 2000), NumPy restatement "
@@ -476,12 +478,14 @@ def run_ours(args):
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    B = args.windows
+    strong = args.workload == "2rx"          # BASELINE configs[4]: 1024 scenarios in total, sharded over the GPUs
+    B = (1024 // world if args.windows == 4096 else args.windows) if strong else args.windows
     desc = make_problem(args.workload)
     prob = engine.WindowProblem(desc)
     bt = make_batch(desc, args.workload, B, seed=2000 + rank)
     dev = lambda a: torch.as_tensor(np.ascontiguousarray(a)).cuda()
     z0, U, data = dev(bt["z0"]), dev(bt["U"]), dev(bt["data"])
+    xprior = dev(bt["xprior"]) if bt.get("xprior") is not None else None
     z = torch.empty_like(z0)
     cost = torch.empty((B,), dtype=torch.float64, device="cuda")
     iters = torch.empty((B,), dtype=torch.int32, device="cuda")
@@ -492,12 +496,12 @@ def run_ours(args):
 
     def step_device():
         z.copy_(z0)
-        prob.solve(z, U, data, None, None, None, out=(cost, iters, status))
+        prob.solve(z, U, data, xprior, None, None, out=(cost, iters, status))
         if world > 1:
             dist.all_gather_into_tensor(gathered, z)
 
     hb = engine.HostBatch(prob, B)
-    hb.load(bt["z0"], bt["U"], bt["data"], None)
+    hb.load(bt["z0"], bt["U"], bt["data"], bt.get("xprior"))
     h_gather = torch.empty((world * B, desc.nz), dtype=torch.float64).pin_memory() if world > 1 else None
 
     def step_e2e():
@@ -545,7 +549,7 @@ def run_ours(args):
         z.copy_(z0)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        prob.solve(z, U, data, None, None, None, out=(cost, iters, status))
+        prob.solve(z, U, data, xprior, None, None, out=(cost, iters, status))
         e1.record()
         kev.append((e0, e1))
     torch.cuda.synchronize()
@@ -581,7 +585,7 @@ def run_ours(args):
         line = {
             "metric": "solved_windows_per_sec", "value": value, "unit": "windows/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": WORKLOAD_DESC[args.workload], "windows_per_gpu": B, "global_windows": world * B,
                        "parallelism": "windows sharded over %d GPU(s), all-gather of estimates at the end" % world,
                        "l2": "256 MB buffer written between timed iterations (inputs are smaller than L2)",
@@ -590,7 +594,7 @@ def run_ours(args):
             "e2e": {"value": e2e, "unit": "windows/s", "h2d_bytes_per_step": hb.h2d_bytes, "d2h_bytes_per_step": hb.d2h_bytes,
                     "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": args.steps,
-            "roofline": {"bound": "fp64", "kernel": "solve_kernel", "achieved": achieved, "peak": peak_fp64,
+            "roofline": {"bound": "fp64", "kernel": {"vdp": "wsolve_kernel<CfgVdp>", "gnss": "wsolve_kernel<CfgGnss>", "2rx": "solve_kernel_pr"}[args.workload], "achieved": achieved, "peak": peak_fp64,
                          "unit": "TFLOP/s", "frac": achieved / peak_fp64 if peak_fp64 > 0 else None,
                          "traffic": traffic, "kernel_ms": ms_kernel,
                          "peak_source": "FP64 FMA probe (nlpf_fp64_probe) measured in this run; MEASURED_PEAKS.json "
@@ -614,7 +618,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="vdp", choices=["vdp", "gnss", "car", "ekf", "ls"])
+    ap.add_argument("--workload", default="vdp", choices=["vdp", "gnss", "2rx", "car", "ekf", "ls"])
     ap.add_argument("--chain", type=int, default=25, help="chained windows per run (car workload; BASELINE names 200)")
     ap.add_argument("--windows", type=int, default=4096, help="windows per GPU per step")
     ap.add_argument("--cpu-windows", type=int, default=0, help="size of the CPU-path sample")

@@ -36,10 +36,10 @@ extern "C" int nlpf_launch_solve_gen(nlpf_problem*, int, double*, const double*,
 extern "C" int nlpf_launch_solve_pr(nlpf_problem*, int, double*, const double*, const double*, const double*,
                                     const double*, const nlpf_opts*, double*, int*, int*, double*, cudaStream_t);
 extern "C" int nlpf_launch_sample(nlpf_problem*, int, const double*, int, const double*, double*, cudaStream_t);
-extern "C" int nlpf_ws_variant(int K, int N, int M, int E, int NM, int dyn, int meas);
+extern "C" int nlpf_ws_variant(int K, int N, int M, int E, int NM, int dyn, int meas, int nb, int prior, int loss);
 extern "C" int nlpf_ws_launch(int variant, nlpf_problem* p, int B, double* z, const double* U, const double* data,
-                              const nlpf_opts* o, double* cost_out, int* iters_out, int* status_out, double* hlin,
-                              int* counter, cudaStream_t st);
+                              const double* xprior, const nlpf_opts* o, double* cost_out, int* iters_out, int* status_out,
+                              double* hlin, int* counter, cudaStream_t st);
 extern "C" int nlpf_set_smem_attrs_gen(size_t bytes);
 extern "C" int nlpf_set_smem_attrs_pr(size_t bytes);
 
@@ -308,8 +308,7 @@ extern "C" int nlpf_problem_create(const nlpf_desc* D, nlpf_problem** out) {
         for (int i = 0; i < n; ++i) if (D->cmap[i] != i) ident = false;
         bool upar = true;
         for (int i = 0; i < m; ++i) if (D->ucol[i] >= 0) upar = false;
-        const bool plain = ident && upar && D->loss == NLPF_LOSS_L2 && D->nb == 0 && !P.has_prior && !P.has_nodecost &&
-                           P.has_dyncost && !getenv("NLPF_NO_WARP_KERNEL");
+        const bool plain = ident && upar && !P.has_nodecost && P.has_dyncost && !getenv("NLPF_NO_WARP_KERNEL");
         if (E > 0 && M > 0 && M % E == 0) {
             const int NM = M / E;
             bool uniform = true;                    // every epoch carries the same record set, in the same order
@@ -324,14 +323,14 @@ extern "C" int nlpf_problem_create(const nlpf_desc* D, nlpf_problem** out) {
             }
             if (uniform && P.lin_meas) {
                 for (int s2 = 0; s2 < NM; ++s2) mslot[act[rloc_s[(size_t)s2 * NLPF_NIDX]]] = s2;
-                if (plain) p->ws_variant = nlpf_ws_variant(K, n, m, E, NM, D->dyn_id, 0);
+                if (plain) p->ws_variant = nlpf_ws_variant(K, n, m, E, NM, D->dyn_id, 0, D->nb, P.has_prior, D->loss);
             } else if (uniform && plain) {
                 bool allpr = true;                  // one pseudorange run per epoch with a single index quadruple
                 for (int r = 0; r < M; ++r) if (rtype_s[r] != NLPF_RT_PR) allpr = false;
                 for (int s2 = 1; s2 < NM && allpr; ++s2)
                     for (int q = 0; q < 4; ++q)
                         if (rloc_s[(size_t)s2 * NLPF_NIDX + q] != rloc_s[q]) allpr = false;
-                if (allpr) p->ws_variant = nlpf_ws_variant(K, n, m, E, NM, D->dyn_id, 1);
+                if (allpr) p->ws_variant = nlpf_ws_variant(K, n, m, E, NM, D->dyn_id, 1, D->nb, P.has_prior, D->loss);
             }
         }
     }
@@ -453,7 +452,7 @@ extern "C" int nlpf_solve(nlpf_problem* p, int B, double* z, const double* U, co
     int rc = check_batch(p, B, z, data);
     if (rc) return rc;
     if (!opts || !cost_out || !iters_out || !status_out) { nlpf_set_error("null opts/output buffer"); return NLPF_E_ARG; }
-    if (p->ws_variant >= 0 && !xprior && !wshift && (p->d.m == 0 || U)) {
+    if (p->ws_variant >= 0 && !wshift && (p->d.m == 0 || U) && (!p->d.has_prior || xprior)) {
         // small linear-measurement class: warp-per-window kernel (its own constant-H cache and work counter)
         const size_t need = (size_t)B * p->d.np;
         if (need > p->scratch_doubles) {
@@ -462,8 +461,8 @@ extern "C" int nlpf_solve(nlpf_problem* p, int B, double* z, const double* U, co
             p->scratch_doubles = need;
         }
         if (!p->counter && nlpf_check_cuda(cudaMalloc((void**)&p->counter, sizeof(int)), "cudaMalloc(work counter)")) return NLPF_E_CUDA;
-        return nlpf_ws_launch(p->ws_variant, p, B, z, U, data, opts, cost_out, iters_out, status_out, p->scratch, p->counter,
-                              (cudaStream_t)stream);
+        return nlpf_ws_launch(p->ws_variant, p, B, z, U, data, xprior, opts, cost_out, iters_out, status_out, p->scratch,
+                              p->counter, (cudaStream_t)stream);
     }
     double* hlin = nullptr;
     if (p->d.lin_meas) {        // per-window constant-H cache (not shared between concurrent calls on one handle)

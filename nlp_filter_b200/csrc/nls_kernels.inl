@@ -903,6 +903,14 @@ __device__ void eval_window(const DevProb& P, double* sm, const double* zc, cons
     __syncthreads();
 }
 
+// Out-of-line copy of the full evaluation for the rarely taken call sites of the solve loop (first
+// evaluation of a window, re-assembly after a rejected step, new barrier stage).  Inlining all five
+// sites gave a 1.7 KB stack frame and five copies of the assembly code in the instruction stream.
+__device__ __noinline__ void eval_window_cold(const DevProb& P, double* sm, const double* zc, const WinPtr& wp, double mu,
+                                              double& J_out, double& merit_out, double& noise_out, int hmode) {
+    eval_window<true>(P, sm, zc, wp, mu, J_out, merit_out, noise_out, hmode);
+}
+
 // ------------------------------------------------------------------------------------------
 // Kernel (3): LDL^T of the packed matrix with the right-hand side appended as row nz.
 // On entry Hp holds the lower triangle of H (+ damping) and row nz holds g.  The elimination
@@ -1136,7 +1144,7 @@ __device__ void build_hlin(const DevProb& P, double* sm, const WinPtr& wp) {
 // Same decisions, in the same order, as oracle/nls.py:solve (the CPU checker).
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(NLPF_NT, NLPF_MIN_CTAS)
-VN(solve_kernel)(DevProb P, int B, double* __restrict__ z_io, const double* __restrict__ U,
+VN(solve_kernel)(const __grid_constant__ DevProb P, int B, double* __restrict__ z_io, const double* __restrict__ U,
              const double* __restrict__ data, const double* __restrict__ xprior,
              const double* __restrict__ wshift, nlpf_opts opt, double* __restrict__ cost_out,
              int* __restrict__ iters_out, int* __restrict__ status_out, double* __restrict__ hlin) {
@@ -1180,7 +1188,7 @@ VN(solve_kernel)(DevProb P, int B, double* __restrict__ z_io, const double* __re
         int status = NLPF_ST_MAXITER;
         double lam = opt.lam0;
         double J, merit, nse0;
-        eval_window<true>(P, sm, zs, wp, mu, J, merit, nse0, hmode);
+        eval_window_cold(P, sm, zs, wp, mu, J, merit, nse0, hmode);
         if (!isfinite(merit)) {
             status = NLPF_ST_NUMERIC;
         } else {
@@ -1212,7 +1220,7 @@ VN(solve_kernel)(DevProb P, int B, double* __restrict__ z_io, const double* __re
                     while (lam <= 1e18) {
                         if (!h_valid) {       // the factorisation overwrote H: rebuild it at z
                             double Jd, md, nd;
-                            eval_window<true>(P, sm, zs, wp, mu, Jd, md, nd, hmode);
+                            eval_window_cold(P, sm, zs, wp, mu, Jd, md, nd, hmode);
                             h_valid = true;
                         }
                         for (int i = tid; i < nz; i += NLPF_NT) {
@@ -1276,7 +1284,7 @@ VN(solve_kernel)(DevProb P, int B, double* __restrict__ z_io, const double* __re
                         status = NLPF_ST_STALLED;
                         if (!h_valid) {   // leave H, g consistent with z for a following stage
                             double Jd, md, nd;
-                            eval_window<true>(P, sm, zs, wp, mu, Jd, md, nd, hmode);
+                            eval_window_cold(P, sm, zs, wp, mu, Jd, md, nd, hmode);
                         }
                         break;
                     }
@@ -1302,7 +1310,7 @@ VN(solve_kernel)(DevProb P, int B, double* __restrict__ z_io, const double* __re
                 }
                 if (!bounded || mu <= opt.mu_min || iters >= opt.max_iter) break;
                 mu = fmax(opt.mu_min, fmin(0.2 * mu, mu * sqrt(mu)));
-                eval_window<true>(P, sm, zs, wp, mu, J, merit, nse0, hmode);
+                eval_window_cold(P, sm, zs, wp, mu, J, merit, nse0, hmode);
             }
         }
         for (int i = tid; i < nz; i += NLPF_NT) z_io[(size_t)b * nz + i] = zs[i];

@@ -1,22 +1,24 @@
-// wsolve_kernels.cu -- warp-per-window whole-solve kernel for SMALL estimation windows whose
-// measurements are linear (RT_STATE of a fixed set of components at every epoch): the van der
-// Pol MHE shape of BASELINE.json configs[1] and the estimation_example.py pattern.
+// wsolve_kernels.cu -- warp-per-window whole-solve kernel for SMALL estimation windows with a
+// uniform measurement layout: the van der Pol MHE shape of BASELINE.json configs[1], the
+// estimation_example.py pattern, the stationary-receiver GNSS shape (configs[2]) and the vehicle
+// shape of autonomous-car.py (configs[3]: arrival cost, bounds through the log barrier, L2 or
+// pseudo-Huber loss).
 //
-// Why a second kernel (profiles/r1_vdp_kernel_full.json, CTA-per-window kernel): ~27 k useful
-// FMAs per iteration were buried under 40 k warp instructions -- runtime sizes and index tables,
-// 128 threads of which <= 42 had work in most phases, ~70 block barriers per iteration, a
+// Why a second kernel (profiles/r1_vdp_general_kernel_full.json, CTA-per-window kernel): ~27 k
+// useful FMAs per iteration were buried under 40 k warp instructions -- runtime sizes and index
+// tables, 128 threads of which <= 42 had work in most phases, ~70 block barriers per iteration, a
 // 64-register cap.  Here every size is a template parameter (loops unroll, indices fold), one
 // warp owns one window (only __syncwarp), windows are handed out through an atomic counter (no
-// tail behind slow windows), and 16 warps/SM leave 128 registers per thread.
+// tail behind slow windows), and <= 16 warps/SM leave 128 registers per thread.
 //
-// Same algorithm and decisions as solve_kernel (nls_kernels.inl) and oracle/nls.py:
-// damped Gauss-Newton with the exact second-order dynamics term, LDL^T with the right-hand side
-// appended, rounding-bound step acceptance.  Restrictions (checked on the host, anything else
-// goes to the general kernel): L2 loss, no bounds, no arrival cost, no global unknowns, identity
-// cmap, parameter controls, every epoch measures the same NM components.
+// Same algorithm and decisions as solve_kernel (nls_kernels.inl) and oracle/nls.py: damped
+// Gauss-Newton with the exact second-order dynamics term where the model has one, monotone log
+// barrier for the bounds, LDL^T with the right-hand side appended, rounding-bound step
+// acceptance.  Restrictions (checked on the host, anything else goes to the general kernel): no
+// global unknowns, identity cmap, parameter controls, every epoch carries the same record set
+// (NM state components, or NM pseudorange slots with one index quadruple).
 #include "common.cuh"
 #include <math.h>
-
 
 namespace {
 
@@ -37,12 +39,52 @@ template <int DYN, int N, int M>
 __device__ __forceinline__ void ws_dyn(const DevProb& P, const double* x, const double* u, double* f, double* F) {
 #pragma unroll
     for (int i = 0; i < N * N; ++i) F[i] = 0.0;
-    if (DYN == NLPF_DYN_VDP) {                         // dynamics.py:61-66
+    if constexpr (DYN == NLPF_DYN_VDP) {               // dynamics.py:61-66
         f[0] = (1.0 - x[1] * x[1]) * x[0] - x[1] + u[0];
         f[1] = x[0];
         F[0] = 1.0 - x[1] * x[1];
         F[1] = -2.0 * x[0] * x[1] - 1.0;
         F[N] = 1.0;
+    } else if constexpr (DYN == NLPF_DYN_VEHICLE_GNSS) {   // dynamics.py:148-174; par = C_AF C_AR M D_F D_R I_Z
+        const double C_AF = P.dyn_par[0], C_AR = P.dyn_par[1], Mv = P.dyn_par[2], D_F = P.dyn_par[3], D_R = P.dyn_par[4],
+                     I_Z = P.dyn_par[5];
+        const double psi = x[2], vx = x[3], vy = x[4], r = x[5];
+        const double Fx = u[0], dl = u[1];
+        const double den = vx + 0.001;
+        const double Fyr = -C_AR * (vy - D_R * r) / den;
+        const double Fyf = -C_AF * ((vy + D_F * r) / den - dl);
+        double sp, cp, sd, cd;
+        sincos(psi, &sp, &cp);
+        sincos(dl, &sd, &cd);
+        f[0] = vx * cp - vy * sp;
+        f[1] = vx * sp + vy * cp;
+        f[2] = r;
+        f[3] = (-Fyf * sd + Fx) / Mv + r * vy;
+        f[4] = (Fyf * cd + Fyr) / Mv - r * vx;
+        f[5] = (D_F * Fyf * cd - D_R * Fyr) / I_Z;
+        f[6] = x[7];
+        f[7] = 0.0;
+        f[8] = 0.0;
+        const double den2 = den * den;
+        const double a_r = C_AR * (vy - D_R * r) / den2, b_r = -C_AR / den, c_r = C_AR * D_R / den;
+        const double a_f = C_AF * (vy + D_F * r) / den2, b_f = -C_AF / den, c_f = -C_AF * D_F / den;
+        F[0 * N + 2] = -vx * sp - vy * cp;
+        F[0 * N + 3] = cp;
+        F[0 * N + 4] = -sp;
+        F[1 * N + 2] = vx * cp - vy * sp;
+        F[1 * N + 3] = sp;
+        F[1 * N + 4] = cp;
+        F[2 * N + 5] = 1.0;
+        F[3 * N + 3] = -sd * a_f / Mv;
+        F[3 * N + 4] = -sd * b_f / Mv + r;
+        F[3 * N + 5] = -sd * c_f / Mv + vy;
+        F[4 * N + 3] = (cd * a_f + a_r) / Mv - r;
+        F[4 * N + 4] = (cd * b_f + b_r) / Mv;
+        F[4 * N + 5] = (cd * c_f + c_r) / Mv - vx;
+        F[5 * N + 3] = (D_F * cd * a_f - D_R * a_r) / I_Z;
+        F[5 * N + 4] = (D_F * cd * b_f - D_R * b_r) / I_Z;
+        F[5 * N + 5] = (D_F * cd * c_f - D_R * c_r) / I_Z;
+        F[6 * N + 7] = 1.0;
     } else {                                           // affine: f = A x + B u + c0
 #pragma unroll
         for (int i = 0; i < N; ++i) {
@@ -60,14 +102,19 @@ __device__ __forceinline__ void ws_dyn(const DevProb& P, const double* x, const 
 }
 
 // compile-time description of one problem class
-template <int K_, int N_, int M_, int E_, int NM_, int DYN_, int MEAS_, int WARPS_>
+template <int K_, int N_, int M_, int E_, int NM_, int DYN_, int MEAS_, int WARPS_, int NB_ = 0, bool PRIOR_ = false,
+          int LOSS_ = NLPF_LOSS_L2>
 struct WsCfg {
     static constexpr int K = K_, N = N_, M = M_, E = E_;
     static constexpr int NM = NM_;          // records per epoch: measured components (MEAS 0) or satellite slots (MEAS 1)
     static constexpr int DYN = DYN_;
     static constexpr int MEAS = MEAS_;      // 0: RT_STATE of a fixed component set, 1: RT_PR with one index quadruple
     static constexpr int WARPS = WARPS_;    // windows (warps) per CTA
+    static constexpr int NB = NB_;          // bounded node components (log barrier)
+    static constexpr bool PRIOR = PRIOR_;   // arrival cost on X_0
+    static constexpr int LOSS = LOSS_;
     static constexpr bool HCONST = (DYN_ == NLPF_DYN_AFFINE);   // dynamics part of H constant (in Hc)
+    static_assert(!(HCONST && LOSS_ == NLPF_LOSS_HUBER), "affine + pseudo-Huber goes to the general kernel");
 };
 
 template <class C>
@@ -86,35 +133,37 @@ struct WsLayout {
     static constexpr int oDD = oDS + ev(NZ);
     static constexpr int oLW = oDD + ev(NZ);
     static constexpr int oFB = oLW + ev(NZ);
-    static constexpr int oF = oFB + ev(NZ);
-    static constexpr int NBLK = C::HCONST ? 0 : K * N * N;       // per-node Jacobian blocks only for nonlinear models
-    static constexpr int oGF = oF + ev(NBLK);
-    static constexpr int oFF = oGF + ev(NBLK);
-    static constexpr int oQ = oFF + ev(NBLK);
+    static constexpr int oWH = oFB + ev(NZ);
+    static constexpr int oF = oWH + ev(C::LOSS == NLPF_LOSS_HUBER ? NZ : 0);
+    static constexpr int NBLK = C::HCONST ? 0 : K * N * N;       // per-node Jacobians only for nonlinear models
+    static constexpr int oQ = oF + ev(NBLK);
     static constexpr int NQ = (C::MEAS == 0) ? NR : E * 14;      // w*r per residual, or [G_e (10) | q_e (4)] per epoch
     static constexpr int PER_WARP = oQ + ev(NQ);
     static constexpr int oDt = C::WARPS * PER_WARP;    // shared by the CTA
     static constexpr int TOTAL = oDt + ev(K * K);
 };
 
-// objective J, its first-order rounding bound and (FULL) H (packed, shared memory), g
+// objective J, merit = J/2 + barrier, first-order rounding bound of the merit and (FULL) H (packed,
+// shared memory), g.  merit = +inf flags an iterate outside the bounds or a non-finite objective.
 template <class C, bool FULL>
 __device__ __forceinline__ void ws_eval(const DevProb& P, double* sm, const double* Dt, const double* zc,
-                                        const double* Ug, const double* dg, const double* h0,
-                                        double& J_out, double& noise_out) {
+                                        const double* Ug, const double* dg, const double* xp, const double* h0, double mu,
+                                        double& J_out, double& merit_out, double& noise_out) {
     typedef WsLayout<C> L;
     constexpr int K = C::K, N = C::N, M = C::M, E = C::E, NM = C::NM, DYN = C::DYN;
     constexpr int NZ = L::NZ;
+    constexpr bool HUB = (C::LOSS == NLPF_LOSS_HUBER);
     const int lane = threadIdx.x & 31;
     double* Hp = sm + L::oH;
     double* g = sm + L::oG;
     double* lw = sm + L::oLW;
     double* fb = sm + L::oFB;
+    double* wh = sm + L::oWH;
     double* Fm = sm + L::oF;
-    double* GF = sm + L::oGF;
-    double* FF = sm + L::oFF;
     double* qv = sm + L::oQ;
-    double cost = 0.0, nse = 0.0;
+    double cost = 0.0, nse = 0.0, bar = 0.0;
+    bool bad = false;
+    auto whv = [&](int k, int i) -> double { return HUB ? wh[k * N + i] : P.cw[k] * P.qinv[i]; };
 
     if (FULL) {
         for (int p = lane; p < L::NP; p += 32) Hp[p] = h0[p];        // constant part (+ linear measurements)
@@ -147,24 +196,20 @@ __device__ __forceinline__ void ws_eval(const DevProb& P, double* sm, const doub
             mag += fabs(dx);
         }
         const double cq = P.cw[k] * P.qinv[i];
-        cost = fma(cq * W, W, cost);
-        lw[t] = cq * W;
-        nse += 2.0 * fabs(cq * W) * mag;
+        if (HUB) {                                          // pseudo_huber_loss, cost_functions.py:25-31
+            const double wd = W / P.delta;
+            const double s = sqrt(1.0 + wd * wd);
+            cost += cq * 2.0 * P.delta * P.delta * (s - 1.0);
+            lw[t] = cq * W / s;
+            wh[t] = cq * (s + 1.0) / (2.0 * s * s);
+        } else {
+            cost = fma(cq * W, W, cost);
+            lw[t] = cq * W;
+        }
+        nse += 2.0 * fabs(lw[t]) * mag;
     }
     __syncwarp();
     if (FULL) {
-        if (!C::HCONST) {
-            // per-node blocks GF = Lambda F, FF = F^T Lambda F
-            for (int t = lane; t < K * N * N; t += 32) {
-                const int k = t / (N * N), rem = t - k * N * N, a = rem / N, b = rem - a * N;
-                const double* Fk = Fm + k * N * N;
-                GF[t] = P.cw[k] * P.qinv[a] * Fk[a * N + b];
-                double s = 0.0;
-#pragma unroll
-                for (int i = 0; i < N; ++i) s = fma(Fk[i * N + a] * (P.cw[k] * P.qinv[i]), Fk[i * N + b], s);
-                FF[t] = s;
-            }
-        }
         // gradient of the dynamics cost: g_(j,a) = sum_k Dt_kj lw_ka - sum_i F_j[i][a] lw_ji
         for (int t = lane; t < NZ; t += 32) {
             const int j = t / N, a = t - j * N;
@@ -180,24 +225,50 @@ __device__ __forceinline__ void ws_eval(const DevProb& P, double* sm, const doub
             }
             g[t] = s;
         }
-        __syncwarp();
         if (!C::HCONST) {
-            // H += -Dt_jl GF_j[b][a] - Dt_lj GF_l[a][b] (+ FF_j on the diagonal blocks), per node pair
+            // H_(j,a),(l,b) += -Dt_jl w_jb F_j[b][a] - Dt_lj w_la F_l[a][b]  (+ Huber: sum_k Dt_kj Dt_kl w_ka on a == b)
             for (int pr = lane; pr < K * (K + 1) / 2; pr += 32) {
                 const int pe = P.ptab[pr];
                 const int j = pe & 255, l = pe >> 8;
                 const double djl = Dt[j * K + l], dlj = Dt[l * K + j];
+#pragma unroll 3
+                for (int a = 0; a < N; ++a) {
+                    double s1 = 0.0;
+                    if (HUB) {
 #pragma unroll
-                for (int a = 0; a < N; ++a)
+                        for (int k = 0; k < K; ++k) s1 = fma(Dt[k * K + j] * Dt[k * K + l], wh[k * N + a], s1);
+                    }
+                    const double wla = whv(l, a);
 #pragma unroll
                     for (int b = 0; b < N; ++b) {
                         if (j == l && b > a) continue;
-                        double s = -djl * GF[j * N * N + b * N + a] - dlj * GF[l * N * N + a * N + b];
-                        if (j == l) s += FF[j * N * N + a * N + b];
+                        double s = -djl * whv(j, b) * Fm[j * N * N + b * N + a] - dlj * wla * Fm[l * N * N + a * N + b];
+                        if (HUB && a == b) s += s1;
                         Hp[pk(j * N + a, l * N + b)] += s;
                     }
+                }
             }
             __syncwarp();
+            // diagonal blocks: + F_k^T Lambda_k F_k
+            for (int t = lane; t < K * N * N; t += 32) {
+                const int k = t / (N * N), rem = t - k * N * N, a = rem / N, b = rem - a * N;
+                if (b > a) continue;
+                const double* Fk = Fm + k * N * N;
+                double s = 0.0;
+#pragma unroll
+                for (int i = 0; i < N; ++i) s = fma(Fk[i * N + a] * whv(k, i), Fk[i * N + b], s);
+                Hp[pk(k * N + a, k * N + b)] += s;
+            }
+        }
+        __syncwarp();
+    }
+    // arrival cost (nlp.py:279-286); its constant Hessian block is part of Hc
+    if (C::PRIOR) {
+        for (int i = lane; i < N; i += 32) {
+            const double d0 = zc[i] - xp[i];
+            cost += P.pinv[i] * d0 * d0;
+            nse += 2.0 * P.pinv[i] * fabs(d0) * (fabs(zc[i]) + fabs(xp[i]));
+            if (FULL) g[i] += P.pinv[i] * d0;
         }
     }
     if (C::MEAS == 0) {
@@ -229,7 +300,7 @@ __device__ __forceinline__ void ws_eval(const DevProb& P, double* sm, const doub
             }
         }
     } else {
-        // pseudoranges (measurements.py:56-70): one lane per epoch, NM satellite slots, components
+        // pseudoranges (measurements.py:56-70, 81-87): one lane per epoch, NM satellite slots, components
         // (c0,c1,c2 | cb); G_e = sum w grad grad^T (10 unique) and q_e = sum w r grad in registers
         const int c0 = P.act[P.run_loc[0]], c1 = P.act[P.run_loc[1]], c2 = P.act[P.run_loc[2]], cb = P.act[P.run_loc[3]];
         for (int e = lane; e < E; e += 32) {
@@ -342,12 +413,38 @@ __device__ __forceinline__ void ws_eval(const DevProb& P, double* sm, const doub
             }
         }
     }
+    // log barrier on the bounded components (nlp.py:314-317)
+    if (C::NB > 0 && mu > 0.0) {
+        if (FULL) __syncwarp();
+        for (int t = lane; t < K * C::NB; t += 32) {
+            const int k = t / (C::NB > 0 ? C::NB : 1), b = t - k * C::NB;
+            const int idx = k * N + P.bidx[b];
+            const double v = zc[idx];
+            const double lo = P.blo[b], hi = P.bhi[b];
+            if (lo > -1e300) {
+                const double s = v - lo;
+                if (!(s > 0.0)) bad = true;
+                else {
+                    bar -= mu * log(s);
+                    if (FULL) { g[idx] -= mu / s; Hp[pk(idx, idx)] += mu / (s * s); }
+                }
+            }
+            if (hi < 1e300) {
+                const double s = hi - v;
+                if (!(s > 0.0)) bad = true;
+                else {
+                    bar -= mu * log(s);
+                    if (FULL) { g[idx] += mu / s; Hp[pk(idx, idx)] += mu / (s * s); }
+                }
+            }
+        }
+    }
     if (FULL) {
         __syncwarp();
         // Gauss-Newton diagonal for the damping, then the exact second-order dynamics term
         double* dd = sm + L::oDD;
         for (int i = lane; i < NZ; i += 32) dd[i] = Hp[pk(i, i)];
-        if (DYN == NLPF_DYN_VDP) {
+        if constexpr (DYN == NLPF_DYN_VDP) {
             __syncwarp();
             for (int k = lane; k < K; k += 32) {           // hess f0 = [[0, -2 x1], [-2 x1, -2 x0]]
                 const double x0 = zc[k * N], x1 = zc[k * N + 1], l0 = lw[k * N];
@@ -356,14 +453,19 @@ __device__ __forceinline__ void ws_eval(const DevProb& P, double* sm, const doub
             }
         }
     }
-    J_out = wsum(cost);
-    noise_out = 2.220446049250313e-16 * (0.5 * wsum(nse) + 0.5 * fabs(J_out));
+    const double J = wsum(cost);
+    double merit = 0.5 * J + ((C::NB > 0) ? wsum(bar) : 0.0);
+    const double anybad = (C::NB > 0) ? wmax(bad ? 1.0 : 0.0) : 0.0;
+    if (anybad > 0.0 || !isfinite(merit)) merit = INFINITY;
+    J_out = J;
+    merit_out = merit;
+    noise_out = 2.220446049250313e-16 * (0.5 * wsum(nse) + fabs(merit));
     __syncwarp();
 }
 
 // LDL^T of the packed matrix with the right-hand side appended as row NZ (see nls_kernels.inl:
 // ldl_solve); warp version: panels of 4 columns, redundant 4x4 factorisation per lane, (row,
-// 8-column segment) items from the host-built table.
+// 8-column segment) items from the host-built table; reciprocal pivots kept for the backward sweep.
 template <int NZ>
 __device__ __forceinline__ bool ws_ldl(const DevProb& P, double* Hp, double* xs, double* rdv) {
     const int lane = threadIdx.x & 31;
@@ -484,11 +586,14 @@ __device__ __forceinline__ bool ws_ldl(const DevProb& P, double* Hp, double* xs,
 template <class C>
 __global__ void __launch_bounds__(C::WARPS * 32, 512 / (C::WARPS * 32))
 wsolve_kernel(const __grid_constant__ DevProb P, int B, double* __restrict__ z_io, const double* __restrict__ U,
-              const double* __restrict__ data, nlpf_opts opt, double* __restrict__ cost_out, int* __restrict__ iters_out,
-              int* __restrict__ status_out, double* __restrict__ hlin_all, int* __restrict__ counter) {
+              const double* __restrict__ data, const double* __restrict__ xprior, nlpf_opts opt,
+              double* __restrict__ cost_out, int* __restrict__ iters_out, int* __restrict__ status_out,
+              double* __restrict__ hlin_all, int* __restrict__ counter) {
     typedef WsLayout<C> L;
     constexpr int K = C::K, N = C::N, M = C::M, E = C::E, NM = C::NM;
     constexpr int NZ = L::NZ;
+    constexpr bool BND = C::NB > 0;
+    constexpr int NBD = BND ? C::NB : 1;
     extern __shared__ double smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     double* Dt = smem + L::oDt;
@@ -510,108 +615,146 @@ wsolve_kernel(const __grid_constant__ DevProb P, int B, double* __restrict__ z_i
         if (b >= B) break;
         const double* Ug = U + (size_t)b * K * (M > 0 ? M : 1);
         const double* dg = data + (size_t)b * P.Ldata;
+        const double* xp = C::PRIOR ? xprior + (size_t)b * N : nullptr;
         const double* hlin = P.Hc;
         for (int i = lane; i < NZ; i += 32) zs[i] = z_io[(size_t)b * NZ + i];
         if (C::MEAS == 0) {
-        double* hl = hlin_all + (size_t)b * L::NP;
-        hlin = hl;
-        // constant H of this window: Hc + sum_e (phi_e phi_e^T) (x) diag(w_e)
-        for (int p = lane; p < L::NP; p += 32) Hp[p] = P.Hc[p];
-        double* wts = sm + L::oQ;                          // measurement weights of this window
-        for (int t = lane; t < L::NR; t += 32) wts[t] = dg[P.roff[t] + 1];
-        __syncwarp();
-        for (int pr = lane; pr < K * (K + 1) / 2; pr += 32) {
-            const int pe = P.ptab[pr];
-            const int j = pe & 255, l = pe >> 8;
-            double acc[NM];
+            // constant H of this window: Hc + sum_e (phi_e phi_e^T) (x) diag(w_e), kept in an L2-resident cache
+            double* hl = hlin_all + (size_t)b * L::NP;
+            hlin = hl;
+            for (int p = lane; p < L::NP; p += 32) Hp[p] = P.Hc[p];
+            double* wts = sm + L::oQ;
+            for (int t = lane; t < L::NR; t += 32) wts[t] = dg[P.roff[t] + 1];
+            __syncwarp();
+            for (int pr = lane; pr < K * (K + 1) / 2; pr += 32) {
+                const int pe = P.ptab[pr];
+                const int j = pe & 255, l = pe >> 8;
+                double acc[NM];
 #pragma unroll
-            for (int s = 0; s < NM; ++s) acc[s] = 0.0;
+                for (int s = 0; s < NM; ++s) acc[s] = 0.0;
 #pragma unroll 5
-            for (int e = 0; e < E; ++e) {
-                const double pp = P.Phi[e * K + j] * P.Phi[e * K + l];
+                for (int e = 0; e < E; ++e) {
+                    const double pp = P.Phi[e * K + j] * P.Phi[e * K + l];
 #pragma unroll
-                for (int s = 0; s < NM; ++s) acc[s] = fma(pp, wts[e * NM + s], acc[s]);
-            }
+                    for (int s = 0; s < NM; ++s) acc[s] = fma(pp, wts[e * NM + s], acc[s]);
+                }
 #pragma unroll
-            for (int s = 0; s < NM; ++s) {
-                const int c = P.act[P.rloc[s * NLPF_NIDX]];
-                Hp[pk(j * N + c, l * N + c)] += acc[s];
+                for (int s = 0; s < NM; ++s) {
+                    const int c = P.act[P.rloc[s * NLPF_NIDX]];
+                    Hp[pk(j * N + c, l * N + c)] += acc[s];
+                }
             }
+            __syncwarp();
+            for (int p = lane; p < L::NP; p += 32) hl[p] = Hp[p];
         }
         __syncwarp();
-        for (int p = lane; p < L::NP; p += 32) hl[p] = Hp[p];
+        if (BND) {   // start strictly inside the bounds (IPOPT bound_push)
+            for (int t = lane; t < K * C::NB; t += 32) {
+                const int k = t / NBD, bb = t - k * NBD;
+                const int idx = k * N + P.bidx[bb];
+                double v = zs[idx];
+                if (P.blo[bb] > -1e300) v = fmax(v, P.blo[bb] + opt.bound_push);
+                if (P.bhi[bb] < 1e300) v = fmin(v, P.bhi[bb] - opt.bound_push);
+                zs[idx] = v;
+            }
+            __syncwarp();
         }
-        __syncwarp();
-
-        int iters = 0, status = NLPF_ST_MAXITER, floor_steps = 0;
-        double lam = opt.lam0, J, nse0;
-        ws_eval<C, true>(P, sm, Dt, zs, Ug, dg, hlin, J, nse0);
-        double merit = 0.5 * J;
+        double mu = BND ? opt.mu0 : 0.0;
+        int iters = 0, status = NLPF_ST_MAXITER;
+        double lam = opt.lam0, J, merit, nse0;
+        ws_eval<C, true>(P, sm, Dt, zs, Ug, dg, xp, hlin, mu, J, merit, nse0);
         if (!isfinite(merit)) {
             status = NLPF_ST_NUMERIC;
         } else {
-            while (iters < opt.max_iter) {
-                double dm = 0.0;
-                for (int i = lane; i < NZ; i += 32) {
-                    ds[i] = Hp[pk(i, i)];
-                    dm = fmax(dm, dd[i]);
-                }
-                dm = wmax(dm);
-                bool accepted = false, at_floor = false, h_valid = true;
-                double Jt = J, nset = 0.0, dzmax = 0.0;
-                while (lam <= 1e18) {
-                    if (!h_valid) {
-                        double Jd, nd;
-                        ws_eval<C, true>(P, sm, Dt, zs, Ug, dg, hlin, Jd, nd);
-                        h_valid = true;
-                    }
+            while (true) {   // barrier stages (a single pass without bounds)
+                lam = opt.lam0;
+                int stage_steps = 0, floor_steps = 0;
+                status = NLPF_ST_MAXITER;
+                while (iters < opt.max_iter && stage_steps < opt.max_stage_iter) {
+                    double gm = 0.0, dm = 0.0;
                     for (int i = lane; i < NZ; i += 32) {
-                        Hp[pk(i, i)] = ds[i] + lam * (dd[i] + 1e-14 * dm);
-                        Hp[pk(NZ, i)] = g[i];
+                        gm = fmax(gm, fabs(g[i]));
+                        ds[i] = Hp[pk(i, i)];
+                        dm = fmax(dm, dd[i]);
                     }
-                    h_valid = false;
-                    const bool ok = ws_ldl<NZ>(P, Hp, dz, sm + L::oFB);
-                    if (ok) {
-                        double dmx = 0.0, fin = 0.0, pred = 0.0;
-                        for (int i = lane; i < NZ; i += 32) {
-                            dmx = fmax(dmx, fabs(dz[i]));
-                            if (!isfinite(dz[i])) fin = 1.0;
-                            pred = fma(g[i], dz[i], pred);
-                            zt[i] = zs[i] - dz[i];
+                    dm = wmax(dm);
+                    if (BND) {
+                        gm = wmax(gm);
+                        if (mu > opt.mu_min && stage_steps >= 1 && gm < 10.0 * mu) { status = NLPF_ST_CONVERGED; break; }
+                    }
+                    bool accepted = false, at_floor = false, h_valid = true;
+                    double Jt = J, mt = merit, nset = 0.0, dzmax = 0.0, alpha = 1.0;
+                    while (lam <= 1e18) {
+                        if (!h_valid) {
+                            double Jd, md, nd;
+                            ws_eval<C, true>(P, sm, Dt, zs, Ug, dg, xp, hlin, mu, Jd, md, nd);
+                            h_valid = true;
                         }
-                        dmx = wmax(dmx);
-                        fin = wmax(fin);
-                        pred = wsum(pred);
-                        __syncwarp();
-                        if (fin == 0.0) {
-                            ws_eval<C, false>(P, sm, Dt, zt, Ug, dg, hlin, Jt, nset);
-                            const double mt = 0.5 * Jt;
-                            if (isfinite(mt) && mt < merit) { accepted = true; dzmax = dmx; break; }
-                            const double nb = nse0 + nset;
-                            if (isfinite(mt) && (mt - merit) <= nb && pred <= 4.0 * nb) {
-                                accepted = true; at_floor = true; dzmax = dmx; break;
+                        for (int i = lane; i < NZ; i += 32) {
+                            Hp[pk(i, i)] = ds[i] + lam * (dd[i] + 1e-14 * dm);
+                            Hp[pk(NZ, i)] = g[i];
+                        }
+                        h_valid = false;
+                        const bool ok = ws_ldl<NZ>(P, Hp, dz, sm + L::oFB);
+                        if (ok) {
+                            double a = 1.0, dmx = 0.0, fin = 0.0, pred = 0.0;
+                            for (int i = lane; i < NZ; i += 32) {
+                                dmx = fmax(dmx, fabs(dz[i]));
+                                if (!isfinite(dz[i])) fin = 1.0;
+                                pred = fma(g[i], dz[i], pred);
+                            }
+                            if (BND) {   // fraction to the boundary
+                                for (int t = lane; t < K * C::NB; t += 32) {
+                                    const int k = t / NBD, bb = t - k * NBD;
+                                    const int idx = k * N + P.bidx[bb];
+                                    const double st = -dz[idx];
+                                    if (st < 0.0 && P.blo[bb] > -1e300) a = fmin(a, opt.tau_ftb * (zs[idx] - P.blo[bb]) / (-st));
+                                    if (st > 0.0 && P.bhi[bb] < 1e300) a = fmin(a, opt.tau_ftb * (P.bhi[bb] - zs[idx]) / st);
+                                }
+                                a = -wmax(-a);
+                            }
+                            dmx = wmax(dmx);
+                            fin = wmax(fin);
+                            pred = a * wsum(pred);
+                            if (fin == 0.0) {
+                                for (int i = lane; i < NZ; i += 32) zt[i] = fma(-a, dz[i], zs[i]);
+                                __syncwarp();
+                                ws_eval<C, false>(P, sm, Dt, zt, Ug, dg, xp, hlin, mu, Jt, mt, nset);
+                                if (isfinite(mt) && mt < merit) { accepted = true; alpha = a; dzmax = dmx; break; }
+                                const double nb = nse0 + nset;
+                                if (isfinite(mt) && (mt - merit) <= nb && pred <= 4.0 * nb) {
+                                    accepted = true; at_floor = true; alpha = a; dzmax = dmx; break;
+                                }
                             }
                         }
+                        lam *= 10.0;
                     }
-                    lam *= 10.0;
+                    if (!accepted) {
+                        status = NLPF_ST_STALLED;
+                        if (BND && !h_valid) {   // leave H, g consistent with z for a following stage
+                            double Jd, md, nd;
+                            ws_eval<C, true>(P, sm, Dt, zs, Ug, dg, xp, hlin, mu, Jd, md, nd);
+                        }
+                        break;
+                    }
+                    const double step = alpha * dzmax;
+                    double zm = 0.0;
+                    for (int i = lane; i < NZ; i += 32) {
+                        zs[i] = zt[i];
+                        zm = fmax(zm, fabs(zt[i]));
+                    }
+                    zm = wmax(zm);
+                    lam = fmax(lam / 10.0, 1e-12);
+                    ++iters;
+                    ++stage_steps;
+                    __syncwarp();
+                    ws_eval<C, true>(P, sm, Dt, zs, Ug, dg, xp, hlin, mu, J, merit, nse0);
+                    if (step < opt.tol_step * (1.0 + zm)) { status = NLPF_ST_CONVERGED; break; }
+                    if (at_floor && ++floor_steps >= 5) { status = NLPF_ST_CONVERGED; break; }
                 }
-                if (!accepted) {
-                    status = NLPF_ST_STALLED;
-                    break;
-                }
-                double zm = 0.0;
-                for (int i = lane; i < NZ; i += 32) {
-                    zs[i] = zt[i];
-                    zm = fmax(zm, fabs(zt[i]));
-                }
-                zm = wmax(zm);
-                lam = fmax(lam / 10.0, 1e-12);
-                ++iters;
-                __syncwarp();
-                ws_eval<C, true>(P, sm, Dt, zs, Ug, dg, hlin, J, nse0);
-                merit = 0.5 * J;
-                if (dzmax < opt.tol_step * (1.0 + zm)) { status = NLPF_ST_CONVERGED; break; }
-                if (at_floor && ++floor_steps >= 5) { status = NLPF_ST_CONVERGED; break; }
+                if (!BND || mu <= opt.mu_min || iters >= opt.max_iter) break;
+                mu = fmax(opt.mu_min, fmin(0.2 * mu, mu * sqrt(mu)));
+                ws_eval<C, true>(P, sm, Dt, zs, Ug, dg, xp, hlin, mu, J, merit, nse0);
             }
         }
         for (int i = lane; i < NZ; i += 32) z_io[(size_t)b * NZ + i] = zs[i];
@@ -625,8 +768,9 @@ wsolve_kernel(const __grid_constant__ DevProb P, int B, double* __restrict__ z_i
 }
 
 template <class C>
-int ws_launch(nlpf_problem* p, int B, double* z, const double* U, const double* data, const nlpf_opts* o,
-              double* cost_out, int* iters_out, int* status_out, double* hlin, int* counter, cudaStream_t st) {
+int ws_launch(nlpf_problem* p, int B, double* z, const double* U, const double* data, const double* xprior,
+              const nlpf_opts* o, double* cost_out, int* iters_out, int* status_out, double* hlin, int* counter,
+              cudaStream_t st) {
     typedef WsLayout<C> L;
     auto kern = wsolve_kernel<C>;
     const size_t smem = sizeof(double) * L::TOTAL;
@@ -643,32 +787,39 @@ int ws_launch(nlpf_problem* p, int B, double* z, const double* U, const double* 
     int grid = 148 * per_sm;
     const int need = (B + C::WARPS - 1) / C::WARPS;
     if (grid > need) grid = need;
-    kern<<<grid, C::WARPS * 32, smem, st>>>(p->d, B, z, U, data, *o, cost_out, iters_out, status_out, hlin, counter);
+    kern<<<grid, C::WARPS * 32, smem, st>>>(p->d, B, z, U, data, xprior, *o, cost_out, iters_out, status_out, hlin, counter);
     return nlpf_check_cuda(cudaGetLastError(), "wsolve_kernel launch");
 }
 
 typedef WsCfg<21, 2, 1, 50, 2, NLPF_DYN_VDP, 0, 4> CfgVdp;          // van der Pol MHE (BASELINE configs[1])
 typedef WsCfg<21, 2, 2, 50, 2, NLPF_DYN_AFFINE, 0, 4> CfgExample;   // estimation_example.py
 typedef WsCfg<11, 5, 3, 51, 12, NLPF_DYN_AFFINE, 1, 2> CfgGnss;     // gnss_stationary.py MHE (BASELINE configs[2])
+typedef WsCfg<6, 9, 2, 21, 11, NLPF_DYN_VEHICLE_GNSS, 1, 2, 2, true, NLPF_LOSS_L2> CfgCar;         // autonomous-car.py:184-220
+typedef WsCfg<6, 9, 2, 21, 11, NLPF_DYN_VEHICLE_GNSS, 1, 2, 2, true, NLPF_LOSS_HUBER> CfgCarHuber;  // autonomous-car.py:293-318
 
 }  // namespace
 
 // instantiated shapes.  meas: 0 linear state measurements (NM components per epoch), 1 pseudoranges
 // (NM satellite slots per epoch).  Returns the variant index or -1.
-extern "C" int nlpf_ws_variant(int K, int N, int M, int E, int NM, int dyn, int meas) {
-    if (meas == 0 && K == 21 && N == 2 && M == 1 && E == 50 && NM == 2 && dyn == NLPF_DYN_VDP) return 0;
-    if (meas == 0 && K == 21 && N == 2 && M == 2 && E == 50 && NM == 2 && dyn == NLPF_DYN_AFFINE) return 1;
-    if (meas == 1 && K == 11 && N == 5 && M == 3 && E == 51 && NM == 12 && dyn == NLPF_DYN_AFFINE) return 2;
+extern "C" int nlpf_ws_variant(int K, int N, int M, int E, int NM, int dyn, int meas, int nb, int prior, int loss) {
+    const bool plain = nb == 0 && !prior && loss == NLPF_LOSS_L2;
+    if (plain && meas == 0 && K == 21 && N == 2 && M == 1 && E == 50 && NM == 2 && dyn == NLPF_DYN_VDP) return 0;
+    if (plain && meas == 0 && K == 21 && N == 2 && M == 2 && E == 50 && NM == 2 && dyn == NLPF_DYN_AFFINE) return 1;
+    if (plain && meas == 1 && K == 11 && N == 5 && M == 3 && E == 51 && NM == 12 && dyn == NLPF_DYN_AFFINE) return 2;
+    if (meas == 1 && K == 6 && N == 9 && M == 2 && E == 21 && NM == 11 && dyn == NLPF_DYN_VEHICLE_GNSS && nb == 2 && prior)
+        return loss == NLPF_LOSS_L2 ? 3 : 4;
     return -1;
 }
 
 extern "C" int nlpf_ws_launch(int variant, nlpf_problem* p, int B, double* z, const double* U, const double* data,
-                              const nlpf_opts* o, double* cost_out, int* iters_out, int* status_out, double* hlin,
-                              int* counter, cudaStream_t st) {
+                              const double* xprior, const nlpf_opts* o, double* cost_out, int* iters_out, int* status_out,
+                              double* hlin, int* counter, cudaStream_t st) {
     switch (variant) {
-        case 0: return ws_launch<CfgVdp>(p, B, z, U, data, o, cost_out, iters_out, status_out, hlin, counter, st);
-        case 1: return ws_launch<CfgExample>(p, B, z, U, data, o, cost_out, iters_out, status_out, hlin, counter, st);
-        case 2: return ws_launch<CfgGnss>(p, B, z, U, data, o, cost_out, iters_out, status_out, hlin, counter, st);
+        case 0: return ws_launch<CfgVdp>(p, B, z, U, data, xprior, o, cost_out, iters_out, status_out, hlin, counter, st);
+        case 1: return ws_launch<CfgExample>(p, B, z, U, data, xprior, o, cost_out, iters_out, status_out, hlin, counter, st);
+        case 2: return ws_launch<CfgGnss>(p, B, z, U, data, xprior, o, cost_out, iters_out, status_out, hlin, counter, st);
+        case 3: return ws_launch<CfgCar>(p, B, z, U, data, xprior, o, cost_out, iters_out, status_out, hlin, counter, st);
+        case 4: return ws_launch<CfgCarHuber>(p, B, z, U, data, xprior, o, cost_out, iters_out, status_out, hlin, counter, st);
     }
     nlpf_set_error("unknown warp-solve variant %d", variant);
     return NLPF_E_ARG;
