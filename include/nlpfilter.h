@@ -177,6 +177,13 @@ int nlpf_ls_vel(int B, int smax, const double* sat, const double* satvel, const 
 int nlpf_blocktri_solve(int B, int nblk, int bs, const double* Dg, const double* Lo, const double* rhs,
                         double* x_out, int* info_out, int variant, void* stream);
 
+/* "Next" row: batched ECEF -> ENU of n points about one reference point.
+ * replaces: utils.ecef2enu per satellite per epoch, utils/utils.py:58-84 (callers gnss_stationary.py:92-94,
+ * autonomous-car.py:152-154).  p_ecef[n*3], out[n*3] device; R9_host = rows of the ECEF->ENU rotation,
+ * ref3_host = reference point (HOST pointers); rotation_only != 0 rotates without subtracting (velocities). */
+int nlpf_ecef2enu(long long n, const double* p_ecef, const double* R9_host, const double* ref3_host, int rotation_only,
+                  double* out, void* stream);
+
 /* shared memory (bytes) one window of this problem class needs in the whole-solve kernel */
 int nlpf_problem_smem_bytes(const nlpf_problem* p);
 

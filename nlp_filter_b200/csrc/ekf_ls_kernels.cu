@@ -414,3 +414,35 @@ extern "C" int nlpf_fp64_probe(int iters, double* sink_dev, double* flops_out, v
     if (flops_out) *flops_out = 2.0 * 8.0 * (double)iters * blocks * threads;
     return nlpf_check_cuda(cudaGetLastError(), "fp64_probe launch");
 }
+
+// ------------------------------------------------------------------------------------------
+// Batched ECEF -> ENU of satellite positions: the reference calls
+// utils.ecef2enu once per satellite per epoch and re-derives the reference latitude by Bowring
+// iteration every call (utils/utils.py:58-84; callers gnss_stationary.py:92-94,123).  Here the 3x3
+// rotation of the reference point is formed once on the host and n points are rotated per launch:
+//   out_i = R (p_i - p_ref)      (rotation_only: out_i = R p_i, for velocities)
+// 48 B per point in + out: HBM-bound, one thread per point, grid-stride.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) ecef2enu_kernel(size_t n, const double* __restrict__ p, double r00, double r01,
+                                                        double r02, double r10, double r11, double r12, double r20,
+                                                        double r21, double r22, double x0, double y0, double z0,
+                                                        double* __restrict__ out) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const double dx = p[3 * i] - x0, dy = p[3 * i + 1] - y0, dz = p[3 * i + 2] - z0;
+        out[3 * i] = r00 * dx + r01 * dy + r02 * dz;
+        out[3 * i + 1] = r10 * dx + r11 * dy + r12 * dz;
+        out[3 * i + 2] = r20 * dx + r21 * dy + r22 * dz;
+    }
+}
+
+extern "C" int nlpf_ecef2enu(long long n, const double* p_ecef, const double* R9_host, const double* ref3_host,
+                             int rotation_only, double* out, void* stream) {
+    if (n < 1 || !p_ecef || !R9_host || !ref3_host || !out) { nlpf_set_error("bad ecef2enu argument"); return NLPF_E_ARG; }
+    const double* R = R9_host;
+    const double x0 = rotation_only ? 0.0 : ref3_host[0], y0 = rotation_only ? 0.0 : ref3_host[1], z0 = rotation_only ? 0.0 : ref3_host[2];
+    long long blocks = (n + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    ecef2enu_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>((size_t)n, p_ecef, R[0], R[1], R[2], R[3], R[4], R[5], R[6], R[7],
+                                                                  R[8], x0, y0, z0, out);
+    return nlpf_check_cuda(cudaGetLastError(), "ecef2enu_kernel launch");
+}

@@ -293,6 +293,23 @@ def ls_vel(sat, satvel, prr, nsat, xpos):
     return out
 
 
+def ecef2enu_batch(p_ecef, p_ref_ECEF, rotation_only=False):
+    """ENU coordinates of many ECEF points about one reference point in a single launch
+    (utils/utils.py:58-84 applied per point by the reference).  p_ecef (..., 3) array or CUDA tensor."""
+    _require_cuda()
+    from .utils.utils import _enu_rows
+    L = _capi.lib()
+    p = _f8(p_ecef)
+    shape = p.shape
+    p = p.reshape(-1, 3).contiguous()
+    R = np.ascontiguousarray(_enu_rows(np.asarray(p_ref_ECEF, dtype=float)).reshape(-1))
+    ref = np.ascontiguousarray(np.asarray(p_ref_ECEF, dtype=float).reshape(3))
+    out = torch.empty_like(p)
+    _capi.check(L.nlpf_ecef2enu(p.shape[0], _ptr(p), R.ctypes.data_as(_capi.c_double_p), ref.ctypes.data_as(_capi.c_double_p),
+                                1 if rotation_only else 0, _ptr(out), _stream()))
+    return out.reshape(shape)
+
+
 BLOCKTRI_RICCATI = 0
 BLOCKTRI_CYCLIC = 1
 

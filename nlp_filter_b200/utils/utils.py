@@ -78,3 +78,10 @@ def enu2ecef(p_ENU, p_ref_ECEF):
 def get_time_indices(t, t0, tf):
     """Indices with t0 <= t[i] <= tf   (utils/utils.py:107-110)."""
     return np.where((t >= t0) & (t <= tf))[0]
+
+
+def ecef2enu_batch(p_ECEF, p_ref_ECEF, rotation_only=False):
+    """Many points at once on the device (addition to the reference API): `ecef2enu` applied to every
+    row of p_ECEF (N, 3) about one reference point.  Returns a NumPy array."""
+    from .. import engine
+    return engine.ecef2enu_batch(np.asarray(p_ECEF, dtype=float), p_ref_ECEF, rotation_only).cpu().numpy()

@@ -15,6 +15,12 @@ def G():
     return np.load(os.path.join(GOLDEN, "ekf_ls.npz"))
 
 
+@pytest.fixture(scope="module", autouse=True)
+def _names():
+    import nlp_filter_b200
+    nlp_filter_b200.install_reference_names()
+
+
 def _eng():
     from nlp_filter_b200 import engine
     return engine
@@ -102,3 +108,22 @@ def test_ls_velocity_two_receiver_logs(G):
         out = eng.ls_vel(G["rx%s_sat" % tag], G["rx%s_vel" % tag], G["rx%s_prr" % tag], G["rx%s_nsat" % tag],
                          np.ascontiguousarray(sol[:, :3])).cpu().numpy()
         assert np.max(np.abs(out - sol[:, 4:8])) < 1e-9
+
+
+def test_ecef2enu_batch_matches_reference_per_point(G):
+    """one launch for all satellites of all epochs == the per-satellite call."""
+    import utils.utils as utils
+    eng = _eng()
+    p_ref = G["p_ref_ECEF"]
+    sats = G["gs_sat_ecef"].reshape(-1, 3)
+    out = eng.ecef2enu_batch(sats, p_ref).cpu().numpy()
+    rot = eng.ecef2enu_batch(sats, p_ref, rotation_only=True).cpu().numpy()
+    for i in range(0, sats.shape[0], 37):
+        ref = utils.ecef2enu(sats[i], p_ref)
+        assert np.max(np.abs(out[i] - ref)) <= 1e-8 * (1 + np.max(np.abs(ref)))          # 2e7 m magnitudes: < 1 um
+        assert np.max(np.abs(rot[i] - utils.ecef2enu(sats[i], p_ref, rotation_only=True))) <= 1e-8 * 3e7
+    # stored ENU satellites of the golden file were produced by the reference's own ecef2enu
+    k = 7
+    n = int(G["gs_nsat"][k])
+    assert np.max(np.abs(out.reshape(51, 12, 3)[k, :n] - G["gs_sat_enu"][k, :n])) < 1e-7
+    assert np.array_equal(utils.ecef2enu_batch(sats[:5], p_ref), out[:5])
