@@ -345,6 +345,21 @@ extern "C" int nlpf_problem_create(const nlpf_desc* D, nlpf_problem** out) {
     }
     seg_cnt[nz + 1] = (int)seg_tab.size();
 
+    // warp-per-window kernel: padded packed layout of the constant part, 2x4 tiles of the generic triangle
+    auto ppo = [](int r) { return 2 * ((r + 1) >> 1) * ((r + 2) >> 1); };
+    std::vector<double> Hcp((size_t)ppo(nz), 0.0);
+    for (int r = 0; r < nz; ++r)
+        for (int c = 0; c <= r; ++c) Hcp[(size_t)ppo(r) + c] = Hc[(size_t)r * (r + 1) / 2 + c];
+    std::vector<uint16_t> tile_tab;
+    std::vector<int> tile_cnt(nz + 2, 0);
+    for (int s = 0; s <= nz + 1; ++s) {            // rows di < s; row pair rp covers di = 2rp, 2rp+1
+        if (s >= 1 && (s - 1) % 2 == 0) {          // a new row pair starts at di = s-1
+            const int rp = (s - 1) / 2;
+            for (int ct = 0; 4 * ct <= 2 * rp + 1; ++ct) tile_tab.push_back((uint16_t)(rp | (ct << 8)));
+        }
+        tile_cnt[s] = (int)tile_tab.size();
+    }
+
     // ---- blob ----
     Blob B;
     std::vector<double> zero1(1, 0.0);
@@ -358,7 +373,7 @@ extern "C" int nlpf_problem_create(const nlpf_desc* D, nlpf_problem** out) {
                  oPh = B.add(D->Phi, sizeof(double) * E * K), ort = B.addv(rtype_s), orl = B.addv(rloc_s),
                  oro = B.addv(roff_s), oes = B.addv(estart), oac = B.addv(act), oHc = B.addv(Hc), oFc = B.addv(Fc),
                  otb = B.addv(tab), opt = B.addv(ptab), osg = B.addv(seg_tab), osc = B.addv(seg_cnt),
-                 oPT = B.addv(PhiT), oms = B.addv(mslot), ogs = B.addv(gstart), oer = B.addv(erun), ors = B.addv(run_start), orn = B.addv(run_len), orc = B.addv(run_loc);
+                 oPT = B.addv(PhiT), oHp = B.addv(Hcp), ott = B.addv(tile_tab), otc = B.addv(tile_cnt), oms = B.addv(mslot), ogs = B.addv(gstart), oer = B.addv(erun), ors = B.addv(run_start), orn = B.addv(run_len), orc = B.addv(run_loc);
     B.add(zero1.data(), 16);
     p->blob_bytes = B.host.size();
     cudaGetDevice(&p->device);
@@ -376,6 +391,7 @@ extern "C" int nlpf_problem_create(const nlpf_desc* D, nlpf_problem** out) {
     P.estart = (const int*)(base + oes); P.act = (const int*)(base + oac); P.Hc = (const double*)(base + oHc);
     P.Fc = (const double*)(base + oFc); P.tab = (const uint32_t*)(base + otb); P.ptab = (const uint16_t*)(base + opt);
     P.seg_tab = (const uint16_t*)(base + osg); P.seg_cnt = (const int*)(base + osc);
+    P.Hcp = (const double*)(base + oHp); P.tile_tab = (const uint16_t*)(base + ott); P.tile_cnt = (const int*)(base + otc);
     P.PhiT = (const double*)(base + oPT); P.mslot = (const int*)(base + oms);
     P.gstart = (const int*)(base + ogs); P.erun = (const int*)(base + oer); P.run_start = (const int*)(base + ors);
     P.run_len = (const int*)(base + orn); P.run_loc = (const int*)(base + orc);
@@ -454,7 +470,8 @@ extern "C" int nlpf_solve(nlpf_problem* p, int B, double* z, const double* U, co
     if (!opts || !cost_out || !iters_out || !status_out) { nlpf_set_error("null opts/output buffer"); return NLPF_E_ARG; }
     if (p->ws_variant >= 0 && !wshift && (p->d.m == 0 || U) && (!p->d.has_prior || xprior)) {
         // small linear-measurement class: warp-per-window kernel (its own constant-H cache and work counter)
-        const size_t need = (size_t)B * p->d.np;
+        const int nzp = p->d.nz;
+        const size_t need = p->d.lin_meas ? (size_t)B * (2 * ((nzp + 1) >> 1) * ((nzp + 2) >> 1)) : 0;   // padded packed rows
         if (need > p->scratch_doubles) {
             if (p->scratch) { cudaStreamSynchronize((cudaStream_t)stream); cudaFree(p->scratch); p->scratch = nullptr; p->scratch_doubles = 0; }
             if (nlpf_check_cuda(cudaMalloc((void**)&p->scratch, need * sizeof(double)), "cudaMalloc(constant-H cache)")) return NLPF_E_CUDA;

@@ -64,6 +64,11 @@ struct DevProb {
     const uint16_t* ptab;             // npair  pair index -> j | l<<8
     const uint16_t* seg_tab;          // LDL trailing-update items of the generic triangle: di | (dk0/8)<<8
     const int* seg_cnt;               // nz+2  number of items of a trailing triangle with s rows
+    // warp-per-window kernel: H in the row-padded packed layout (row r starts at 2*((r+1)/2)*((r+2)/2), so every
+    // row is 16-byte aligned), 2-row x 4-column trailing-update tiles rp | ct<<8 sorted by row pair
+    const double* Hcp;                // Hc in the padded layout
+    const uint16_t* tile_tab;
+    const int* tile_cnt;              // nz+2  tiles of a trailing triangle with s rows
     // shared-memory layout, offsets in doubles
     int o_H, o_z, o_zt, o_g, o_ds, o_dd, o_dz, o_f, o_lw, o_wh, o_slw, o_F, o_GF, o_FF, o_whs;
     int o_Ve, o_G, o_q, o_Phi, o_Dt, o_red, smem_doubles;

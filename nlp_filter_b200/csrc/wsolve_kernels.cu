@@ -32,7 +32,19 @@ __device__ __forceinline__ double wmax(double v) {
     for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
     return v;
 }
-__device__ __forceinline__ constexpr int pk(int r, int c) { return ((r * (r + 1)) >> 1) + c; }
+// row-padded packed lower triangle: rows have even length, so every row starts 16-byte aligned and pairs of
+// entries at even columns load as double2
+__device__ __forceinline__ constexpr int po(int r) { return 2 * ((r + 1) >> 1) * ((r + 2) >> 1); }
+__device__ __forceinline__ constexpr int pk(int r, int c) { return po(r) + c; }
+// reciprocal without the slow path of the IEEE division: MUFU seed (2^-20) + two Newton steps (pivots are
+// checked for d > 0 and finiteness by the caller)
+__device__ __forceinline__ double frcp(double d) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(d));
+    r = fma(fma(-d, r, 1.0), r, r);
+    r = fma(fma(-d, r, 1.0), r, r);
+    return r;
+}
 
 // ---- models (nlp/dynamics.py), compile-time sized; F is the N x N Jacobian, row-major ----
 template <int DYN, int N, int M>
@@ -121,11 +133,12 @@ template <class C>
 struct WsLayout {
     static constexpr int K = C::K, N = C::N, E = C::E, NM = C::NM;
     static constexpr int NZ = K * N;
-    static constexpr int NP = NZ * (NZ + 1) / 2;
+    static constexpr int NP = po(NZ);                  // H rows 0..NZ-1 in the padded layout
     static constexpr int NR = E * NM;                  // residuals
     static constexpr int ev(int x) { return (x + 1) & ~1; }
+    static constexpr int LDW = (NZ + 2 + 3) & ~3;      // LDL panel copy W^T[4][LDW]
     static constexpr int oH = 0;
-    static constexpr int oZ = oH + ev(NP + NZ);
+    static constexpr int oZ = oH + po(NZ + 1);         // + the appended right-hand-side row
     static constexpr int oZT = oZ + ev(NZ);
     static constexpr int oG = oZT + ev(NZ);
     static constexpr int oDZ = oG + ev(NZ);
@@ -138,9 +151,17 @@ struct WsLayout {
     static constexpr int NBLK = C::HCONST ? 0 : K * N * N;       // per-node Jacobians only for nonlinear models
     static constexpr int oQ = oF + ev(NBLK);
     static constexpr int NQ = (C::MEAS == 0) ? NR : E * 14;      // w*r per residual, or [G_e (10) | q_e (4)] per epoch
-    static constexpr int PER_WARP = oQ + ev(NQ);
+    static constexpr int NFQ = (ev(NBLK) + ev(NQ) > 4 * LDW) ? ev(NBLK) + ev(NQ) : 4 * LDW;   // F | Q, reused by the LDL
+    static constexpr int PER_WARP = oF + NFQ;
     static constexpr int oDt = C::WARPS * PER_WARP;    // shared by the CTA
-    static constexpr int TOTAL = oDt + ev(K * K);
+    static constexpr int NTILE = ((NZ + 2) / 2) * ((NZ + 2) / 4 + 1);   // bound on the tile table
+    static constexpr int oTT = oDt + ev(K * K);        // tile table (uint16) and counts (int), as doubles
+    static constexpr int oTC = oTT + ev((NTILE + 3) / 4);
+    static constexpr int TOTAL = oTC + ev((NZ + 3) / 2);
+    // resident CTAs per SM: shared memory (227 KB, 1 KB reserved per CTA) or 16 warps, whichever is smaller;
+    // the register cap follows from it (GNSS / vehicle shapes: 8 warps per SM, so up to 255 registers)
+    static constexpr int CTAS_SMEM = (227 * 1024) / (TOTAL * 8 + 1024);
+    static constexpr int CTAS = (CTAS_SMEM < 512 / (C::WARPS * 32)) ? (CTAS_SMEM < 1 ? 1 : CTAS_SMEM) : 512 / (C::WARPS * 32);
 };
 
 // objective J, merit = J/2 + barrier, first-order rounding bound of the merit and (FULL) H (packed,
@@ -188,13 +209,16 @@ __device__ __forceinline__ void ws_eval(const DevProb& P, double* sm, const doub
     for (int t = lane; t < NZ; t += 32) {
         const int k = t / N, i = t - k * N;
         const double fki = fb[t];
-        double W = -fki, mag = fabs(fki);
+        // (sums over nodes / epochs below are split over 2-4 accumulators: with 4 warps per scheduler the
+        // kernel is bound by dependent-FMA latency, not by issue slots)
+        double Wa = -fki, Wb = 0.0, mga = fabs(fki), mgb = 0.0;
 #pragma unroll
         for (int j = 0; j < K; ++j) {
             const double dx = Dt[k * K + j] * zc[j * N + i];
-            W += dx;
-            mag += fabs(dx);
+            if (j & 1) { Wb += dx; mgb += fabs(dx); }
+            else { Wa += dx; mga += fabs(dx); }
         }
+        const double W = Wa + Wb, mag = mga + mgb;
         const double cq = P.cw[k] * P.qinv[i];
         if (HUB) {                                          // pseudo_huber_loss, cost_functions.py:25-31
             const double wd = W / P.delta;
@@ -213,9 +237,13 @@ __device__ __forceinline__ void ws_eval(const DevProb& P, double* sm, const doub
         // gradient of the dynamics cost: g_(j,a) = sum_k Dt_kj lw_ka - sum_i F_j[i][a] lw_ji
         for (int t = lane; t < NZ; t += 32) {
             const int j = t / N, a = t - j * N;
-            double s = 0.0;
+            double s = 0.0, s2 = 0.0;
 #pragma unroll
-            for (int k = 0; k < K; ++k) s = fma(Dt[k * K + j], lw[k * N + a], s);
+            for (int k = 0; k < K; ++k) {
+                if (k & 1) s2 = fma(Dt[k * K + j], lw[k * N + a], s2);
+                else s = fma(Dt[k * K + j], lw[k * N + a], s);
+            }
+            s += s2;
             if (C::HCONST) {
 #pragma unroll
                 for (int i = 0; i < N; ++i) s = fma(-P.A[i * N + a], lw[j * N + i], s);
@@ -278,9 +306,15 @@ __device__ __forceinline__ void ws_eval(const DevProb& P, double* sm, const doub
             const int c = P.act[P.rloc[t * NLPF_NIDX]];
             const double* rec = dg + P.roff[t];
             const double w = rec[1];
-            double v = 0.0;
+            double va = 0.0, vb = 0.0, vc = 0.0;
 #pragma unroll
-            for (int j = 0; j < K; ++j) v = fma(P.PhiT[j * E + e], zc[j * N + c], v);
+            for (int j = 0; j < K; ++j) {
+                const double ph = P.PhiT[j * E + e], zv = zc[j * N + c];
+                if (j % 3 == 0) va = fma(ph, zv, va);
+                else if (j % 3 == 1) vb = fma(ph, zv, vb);
+                else vc = fma(ph, zv, vc);
+            }
+            const double v = (va + vb) + vc;
             const double r = (w != 0.0) ? rec[0] - v : 0.0;
             cost = fma(w * r, r, cost);
             nse += 2.0 * w * fabs(r) * (2.0 * fabs(rec[0]) + fabs(r));
@@ -292,10 +326,15 @@ __device__ __forceinline__ void ws_eval(const DevProb& P, double* sm, const doub
                 const int j = t / N, a = t - j * N;
                 const int s = P.mslot[a];                  // slot of component a in an epoch's record set, or -1
                 if (s >= 0) {
-                    double acc = 0.0;
-#pragma unroll 10
-                    for (int e = 0; e < E; ++e) acc = fma(P.Phi[e * K + j], qv[e * NM + s], acc);
-                    g[t] -= acc;
+                    double ac[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll 3
+                    for (int e = 0; e + 3 < E; e += 4) {
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) ac[q] = fma(P.Phi[(e + q) * K + j], qv[(e + q) * NM + s], ac[q]);
+                    }
+#pragma unroll
+                    for (int e = E & ~3; e < E; ++e) ac[e & 3] = fma(P.Phi[e * K + j], qv[e * NM + s], ac[e & 3]);
+                    g[t] -= (ac[0] + ac[1]) + (ac[2] + ac[3]);
                 }
             }
         }
@@ -363,11 +402,16 @@ __device__ __forceinline__ void ws_eval(const DevProb& P, double* sm, const doub
             // gradient: g_(j,c_a) -= sum_e phi_ej q_e[a]
             for (int t = lane; t < K * 4; t += 32) {
                 const int j = t >> 2, a = t & 3;
-                double acc = 0.0;
+                double ac[4] = {0.0, 0.0, 0.0, 0.0};
 #pragma unroll 3
-                for (int e = 0; e < E; ++e) acc = fma(P.Phi[e * K + j], qv[e * 14 + 10 + a], acc);
+                for (int e = 0; e + 3 < E; e += 4) {
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) ac[q] = fma(P.Phi[(e + q) * K + j], qv[(e + q) * 14 + 10 + a], ac[q]);
+                }
+#pragma unroll
+                for (int e = E & ~3; e < E; ++e) ac[e & 3] = fma(P.Phi[e * K + j], qv[e * 14 + 10 + a], ac[e & 3]);
                 const int c = (a == 0) ? c0 : (a == 1) ? c1 : (a == 2) ? c2 : cb;
-                g[j * N + c] -= acc;
+                g[j * N + c] -= (ac[0] + ac[1]) + (ac[2] + ac[3]);
             }
             // H_(j,a),(l,b) += sum_e phi_ej phi_el G_e[a][b]: two lanes share a node pair (epoch halves),
             // 10 unique values per pair (G_e symmetric), combined with one shuffle
@@ -463,11 +507,19 @@ __device__ __forceinline__ void ws_eval(const DevProb& P, double* sm, const doub
     __syncwarp();
 }
 
-// LDL^T of the packed matrix with the right-hand side appended as row NZ (see nls_kernels.inl:
-// ldl_solve); warp version: panels of 4 columns, redundant 4x4 factorisation per lane, (row,
-// 8-column segment) items from the host-built table; reciprocal pivots kept for the backward sweep.
-template <int NZ>
-__device__ __forceinline__ bool ws_ldl(const DevProb& P, double* Hp, double* xs, double* rdv) {
+// LDL^T of the packed matrix with the right-hand side appended as row NZ, then the backward sweep.
+// Right-looking, panels of 4 columns:
+//   1. every lane factors the 4x4 diagonal block redundantly in registers (frcp pivots);
+//   2. one lane per row below: w = a L11^-T by substitution; W^T goes to a side buffer, the SCALED
+//      l = w / d is stored in place (so the backward sweep needs no pivots);
+//   3. the trailing triangle is updated in 2-row x 4-column register tiles from a table (32 independent
+//      FMAs per tile, all shared-memory traffic as 16-byte accesses; the per-entry loop this replaces
+//      took 30 % of the kernel: 16 instructions and a load->4 FMA->store chain per entry);
+//   4. the diagonal block is overwritten with the strict lower part of L11^-1, which turns the 4x4
+//      triangular solve of the backward sweep into independent dot products.
+template <int NZ, int LDW>
+__device__ __forceinline__ bool ws_ldl(const uint16_t* __restrict__ ttab, const int* __restrict__ tcnt, double* Hp,
+                                       double* xs, double* Wt) {
     const int lane = threadIdx.x & 31;
     bool ok = true;
 #pragma unroll 1
@@ -475,10 +527,27 @@ __device__ __forceinline__ bool ws_ldl(const DevProb& P, double* Hp, double* xs,
         const int pw = (NZ - j0 < 4) ? NZ - j0 : 4;
         __syncwarp();
         double a[4][4], l[4][4], d[4], rd[4];
+        {
+            const double* r0 = Hp + pk(j0, j0);
+            const double* r1 = Hp + pk(j0 + 1, j0);
+            const double* r2 = Hp + pk(j0 + 2, j0);
+            const double* r3 = Hp + pk(j0 + 3, j0);
+            const double2 v1 = *reinterpret_cast<const double2*>(r1);
+            const double2 v2 = *reinterpret_cast<const double2*>(r2);
+            const double2 v3a = *reinterpret_cast<const double2*>(r3);
+            const double2 v3b = *reinterpret_cast<const double2*>(r3 + 2);
+            a[0][0] = r0[0];
+            a[1][0] = v1.x; a[1][1] = v1.y;
+            a[2][0] = v2.x; a[2][1] = v2.y; a[2][2] = r2[2];
+            a[3][0] = v3a.x; a[3][1] = v3a.y; a[3][2] = v3b.x; a[3][3] = v3b.y;
+            if (pw < 4) {
 #pragma unroll
-        for (int r = 0; r < 4; ++r)
+                for (int r = 1; r < 4; ++r)
 #pragma unroll
-            for (int c = 0; c <= r; ++c) a[r][c] = (r < pw) ? Hp[pk(j0 + r, j0 + c)] : (r == c ? 1.0 : 0.0);
+                    for (int c = 0; c <= r; ++c)
+                        if (r >= pw) a[r][c] = (r == c) ? 1.0 : 0.0;
+            }
+        }
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
 #pragma unroll
@@ -489,102 +558,127 @@ __device__ __forceinline__ bool ws_ldl(const DevProb& P, double* Hp, double* xs,
                 a[r][c] = w;
             }
             d[c] = a[c][c];
-            rd[c] = 1.0 / d[c];
+            rd[c] = frcp(d[c]);
 #pragma unroll
             for (int r = c + 1; r < 4; ++r) l[r][c] = a[r][c] * rd[c];
         }
-        bool good = true;
-#pragma unroll
-        for (int c = 0; c < 4; ++c)
-            if (c < pw && (!(d[c] > 0.0) || !isfinite(d[c]))) good = false;
-        if (!good) { ok = false; break; }
+        const double dmin = fmin(fmin(d[0], d[1]), fmin(d[2], d[3])), dmax = fmax(fmax(d[0], d[1]), fmax(d[2], d[3]));
+        if (!(dmin > 0.0) || !(dmax < INFINITY)) { ok = false; break; }
         const int j1 = j0 + pw;
         for (int i = j1 + lane; i <= NZ; i += 32) {
             double* Hi = Hp + pk(i, j0);
-            double w[4];
-#pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                if (c < pw) {
-                    double v = Hi[c];
-#pragma unroll
-                    for (int q = 0; q < c; ++q) v = fma(-w[q], l[c][q], v);
-                    w[c] = v;
-                    Hi[c] = v;
-                } else w[c] = 0.0;
+            const double2 u01 = *reinterpret_cast<const double2*>(Hi);
+            const double2 u23 = *reinterpret_cast<const double2*>(Hi + 2);   // (pw < 4: past the row, unused)
+            const double w0 = u01.x;
+            const double w1 = fma(-w0, l[1][0], u01.y);
+            const double w2 = fma(-w1, l[2][1], fma(-w0, l[2][0], u23.x));
+            const double w3 = fma(-w2, l[3][2], fma(-w1, l[3][1], fma(-w0, l[3][0], u23.y)));
+            Wt[i] = w0;
+            Wt[LDW + i] = w1;
+            Wt[2 * LDW + i] = w2;
+            Wt[3 * LDW + i] = w3;
+            if (pw == 4) {
+                *reinterpret_cast<double2*>(Hi) = make_double2(w0 * rd[0], w1 * rd[1]);
+                *reinterpret_cast<double2*>(Hi + 2) = make_double2(w2 * rd[2], w3 * rd[3]);
+            } else {
+                Hi[0] = w0 * rd[0];
+                if (pw > 1) Hi[1] = w1 * rd[1];
+                if (pw > 2) Hi[2] = w2 * rd[2];
             }
         }
         __syncwarp();
-        if (lane == 31) {
-#pragma unroll
-            for (int r = 0; r < 4; ++r) {
-#pragma unroll
-                for (int c = 0; c <= r; ++c)
-                    if (r < pw) Hp[pk(j0 + r, j0 + c)] = a[r][c];
-                if (r < pw) rdv[j0 + r] = rd[r];           // reciprocal pivots for the backward sweep
-            }
+        if (lane == 31) {       // strict lower part of L11^-1 (rows/columns >= pw are identity)
+            const double m10 = -l[1][0], m21 = -l[2][1], m32 = -l[3][2];
+            const double m20 = fma(-l[2][1], m10, -l[2][0]);
+            const double m31 = fma(-l[3][2], m21, -l[3][1]);
+            const double m30 = fma(-l[3][2], m20, fma(-l[3][1], m10, -l[3][0]));
+            if (pw > 1) Hp[pk(j0 + 1, j0)] = m10;
+            if (pw > 2) { Hp[pk(j0 + 2, j0)] = m20; Hp[pk(j0 + 2, j0 + 1)] = m21; }
+            if (pw > 3) { Hp[pk(j0 + 3, j0)] = m30; Hp[pk(j0 + 3, j0 + 1)] = m31; Hp[pk(j0 + 3, j0 + 2)] = m32; }
         }
-        const int nitem = P.seg_cnt[NZ + 1 - j1];
+        if (j1 >= NZ) continue;
+        const int nitem = tcnt[NZ + 1 - j1];
         for (int it = lane; it < nitem; it += 32) {
-            const int e = P.seg_tab[it];
-            const int i = j1 + (e & 255);
-            const int k0 = j1 + ((e >> 8) << 3);
-            int kend = k0 + 7;
-            if (kend > i) kend = i;
-            if (kend > NZ - 1) kend = NZ - 1;
-            double* Hi = Hp + pk(i, 0);
-            double li[4];
+            const int e = ttab[it];
+            const int i = j1 + ((e & 255) << 1);          // even row; its partner i+1 follows at + i + 2
+            const int k0 = j1 + ((e >> 8) << 2);
+            double* R0 = Hp + po(i);
+            double* R1 = R0 + i + 2;
+            double2 la[2], lb[2], x0[2], x1[2];
+            la[0] = *reinterpret_cast<const double2*>(R0 + j0);
+            lb[0] = *reinterpret_cast<const double2*>(R0 + j0 + 2);
+            la[1] = *reinterpret_cast<const double2*>(R1 + j0);
+            lb[1] = *reinterpret_cast<const double2*>(R1 + j0 + 2);
+            x0[0] = *reinterpret_cast<const double2*>(R0 + k0);
+            x1[0] = *reinterpret_cast<const double2*>(R0 + k0 + 2);
+            x0[1] = *reinterpret_cast<const double2*>(R1 + k0);
+            x1[1] = *reinterpret_cast<const double2*>(R1 + k0 + 2);
+            const double* Wk = Wt + k0;
 #pragma unroll
-            for (int c = 0; c < 4; ++c) li[c] = (c < pw) ? Hi[j0 + c] * rd[c] : 0.0;
-            for (int k = k0; k <= kend; ++k) {
-                const double* Hk = Hp + pk(k, j0);
-                double v = Hi[k];
+            for (int c = 0; c < 4; ++c) {
+                const double2 wa = *reinterpret_cast<const double2*>(Wk + c * LDW);
+                const double2 wb = *reinterpret_cast<const double2*>(Wk + c * LDW + 2);
 #pragma unroll
-                for (int c = 0; c < 4; ++c)
-                    if (c < pw) v = fma(-li[c], Hk[c], v);
-                Hi[k] = v;
+                for (int r = 0; r < 2; ++r) {
+                    const double lv = (c == 0) ? la[r].x : (c == 1) ? la[r].y : (c == 2) ? lb[r].x : lb[r].y;
+                    x0[r].x = fma(-lv, wa.x, x0[r].x);
+                    x0[r].y = fma(-lv, wa.y, x0[r].y);
+                    x1[r].x = fma(-lv, wb.x, x1[r].x);
+                    x1[r].y = fma(-lv, wb.y, x1[r].y);
+                }
+            }
+            if (k0 <= i) *reinterpret_cast<double2*>(R0 + k0) = x0[0];
+            if (k0 + 2 <= i) *reinterpret_cast<double2*>(R0 + k0 + 2) = x1[0];
+            if (i + 1 <= NZ) {
+                if (k0 <= i + 1) *reinterpret_cast<double2*>(R1 + k0) = x0[1];
+                if (k0 + 2 <= i + 1) *reinterpret_cast<double2*>(R1 + k0 + 2) = x1[1];
             }
         }
     }
     __syncwarp();
     if (!ok) return false;
-    // backward sweep, four unknowns per step: every lane solves the 4x4 triangle redundantly in
-    // registers (x_j = (u_j - sum_{k>j in block} Hraw[k][j] x_k) / d_j), then the lanes share the update
-    // u_i -= sum_c Hraw[j_c][i] x_c of the rows above.  (The one-unknown-per-step version with a
-    // division was 14 % of the kernel's stall samples.)
-    double* u = Hp + pk(NZ, 0);
+    // backward sweep L^T x = y (y = the scaled appended row), one panel per step: x_B = L11^-T y_B as four
+    // independent dot products with the stored inverse, then y_i -= sum_c l_(j0+c),i x_c for the rows above
+    double* y = Hp + pk(NZ, 0);
 #pragma unroll 1
-    for (int jb = NZ; jb > 0; jb -= 4) {
-        const int j0 = (jb >= 4) ? jb - 4 : 0;
-        const int pw = jb - j0;
+    for (int j0 = ((NZ - 1) >> 2) << 2; j0 >= 0; j0 -= 4) {
+        const int pw = (NZ - j0 < 4) ? NZ - j0 : 4;
+        const double2 y01 = *reinterpret_cast<const double2*>(y + j0);
+        const double2 y23 = *reinterpret_cast<const double2*>(y + j0 + 2);
+        const double m10 = Hp[pk(j0 + 1, j0)];
+        const double2 m2 = *reinterpret_cast<const double2*>(Hp + pk(j0 + 2, j0));
+        const double2 m3 = *reinterpret_cast<const double2*>(Hp + pk(j0 + 3, j0));
+        const double m32 = Hp[pk(j0 + 3, j0 + 2)];
         double x[4];
-#pragma unroll
-        for (int r = 3; r >= 0; --r) {
-            if (r < pw) {
-                double v = u[j0 + r];
-#pragma unroll
-                for (int q = 3; q > r; --q)
-                    if (q < pw) v = fma(-Hp[pk(j0 + q, j0 + r)], x[q], v);
-                x[r] = v * rdv[j0 + r];
-            } else x[r] = 0.0;
+        if (pw == 4) {
+            x[3] = y23.y;
+            x[2] = fma(m32, y23.y, y23.x);
+            x[1] = fma(m3.y, y23.y, fma(m2.y, y23.x, y01.y));
+            x[0] = fma(m3.x, y23.y, fma(m2.x, y23.x, fma(m10, y01.y, y01.x)));
+        } else {
+            x[3] = 0.0;
+            x[2] = (pw > 2) ? y23.x : 0.0;
+            x[1] = (pw > 1) ? ((pw > 2) ? fma(m2.y, y23.x, y01.y) : y01.y) : 0.0;
+            x[0] = y01.x;
+            if (pw > 1) x[0] = fma(m10, y01.y, x[0]);
+            if (pw > 2) x[0] = fma(m2.x, y23.x, x[0]);
         }
-        __syncwarp();
         for (int i = lane; i < j0; i += 32) {
-            double v = u[i];
-#pragma unroll
-            for (int c = 0; c < 4; ++c)
-                if (c < pw) v = fma(-Hp[pk(j0 + c, i)], x[c], v);
-            u[i] = v;
+            double v = y[i];
+            v = fma(-Hp[pk(j0, i)], x[0], v);
+            if (pw > 1) v = fma(-Hp[pk(j0 + 1, i)], x[1], v);
+            if (pw > 2) v = fma(-Hp[pk(j0 + 2, i)], x[2], v);
+            if (pw > 3) v = fma(-Hp[pk(j0 + 3, i)], x[3], v);
+            y[i] = v;
         }
-#pragma unroll
-        for (int c = 0; c < 4; ++c)
-            if (lane == c && c < pw) xs[j0 + c] = x[c];
+        if (lane < pw) xs[j0 + lane] = (lane == 0) ? x[0] : (lane == 1) ? x[1] : (lane == 2) ? x[2] : x[3];
         __syncwarp();
     }
     return true;
 }
 
 template <class C>
-__global__ void __launch_bounds__(C::WARPS * 32, 512 / (C::WARPS * 32))
+__global__ void __launch_bounds__(C::WARPS * 32, WsLayout<C>::CTAS)
 wsolve_kernel(const __grid_constant__ DevProb P, int B, double* __restrict__ z_io, const double* __restrict__ U,
               const double* __restrict__ data, const double* __restrict__ xprior, nlpf_opts opt,
               double* __restrict__ cost_out, int* __restrict__ iters_out, int* __restrict__ status_out,
@@ -598,6 +692,10 @@ wsolve_kernel(const __grid_constant__ DevProb P, int B, double* __restrict__ z_i
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     double* Dt = smem + L::oDt;
     for (int i = threadIdx.x; i < K * K; i += C::WARPS * 32) Dt[i] = P.Dt[i];
+    uint16_t* ttab = reinterpret_cast<uint16_t*>(smem + L::oTT);
+    int* tcnt = reinterpret_cast<int*>(smem + L::oTC);
+    for (int i = threadIdx.x; i < P.tile_cnt[NZ + 1]; i += C::WARPS * 32) ttab[i] = P.tile_tab[i];
+    for (int i = threadIdx.x; i < NZ + 2; i += C::WARPS * 32) tcnt[i] = P.tile_cnt[i];
     __syncthreads();
     double* sm = smem + warp * L::PER_WARP;
     double* Hp = sm + L::oH;
@@ -616,32 +714,40 @@ wsolve_kernel(const __grid_constant__ DevProb P, int B, double* __restrict__ z_i
         const double* Ug = U + (size_t)b * K * (M > 0 ? M : 1);
         const double* dg = data + (size_t)b * P.Ldata;
         const double* xp = C::PRIOR ? xprior + (size_t)b * N : nullptr;
-        const double* hlin = P.Hc;
+        const double* hlin = P.Hcp;
         for (int i = lane; i < NZ; i += 32) zs[i] = z_io[(size_t)b * NZ + i];
         if (C::MEAS == 0) {
             // constant H of this window: Hc + sum_e (phi_e phi_e^T) (x) diag(w_e), kept in an L2-resident cache
             double* hl = hlin_all + (size_t)b * L::NP;
             hlin = hl;
-            for (int p = lane; p < L::NP; p += 32) Hp[p] = P.Hc[p];
+            for (int p = lane; p < L::NP; p += 32) Hp[p] = P.Hcp[p];
             double* wts = sm + L::oQ;
             for (int t = lane; t < L::NR; t += 32) wts[t] = dg[P.roff[t] + 1];
             __syncwarp();
             for (int pr = lane; pr < K * (K + 1) / 2; pr += 32) {
                 const int pe = P.ptab[pr];
                 const int j = pe & 255, l = pe >> 8;
-                double acc[NM];
+                double acc[2][NM];
 #pragma unroll
-                for (int s = 0; s < NM; ++s) acc[s] = 0.0;
-#pragma unroll 5
-                for (int e = 0; e < E; ++e) {
-                    const double pp = P.Phi[e * K + j] * P.Phi[e * K + l];
+                for (int s = 0; s < NM; ++s) acc[0][s] = acc[1][s] = 0.0;
+#pragma unroll 4
+                for (int e = 0; e + 1 < E; e += 2) {
 #pragma unroll
-                    for (int s = 0; s < NM; ++s) acc[s] = fma(pp, wts[e * NM + s], acc[s]);
+                    for (int h = 0; h < 2; ++h) {
+                        const double pp = P.Phi[(e + h) * K + j] * P.Phi[(e + h) * K + l];
+#pragma unroll
+                        for (int s = 0; s < NM; ++s) acc[h][s] = fma(pp, wts[(e + h) * NM + s], acc[h][s]);
+                    }
+                }
+                if (E & 1) {
+                    const double pp = P.Phi[(E - 1) * K + j] * P.Phi[(E - 1) * K + l];
+#pragma unroll
+                    for (int s = 0; s < NM; ++s) acc[0][s] = fma(pp, wts[(E - 1) * NM + s], acc[0][s]);
                 }
 #pragma unroll
                 for (int s = 0; s < NM; ++s) {
                     const int c = P.act[P.rloc[s * NLPF_NIDX]];
-                    Hp[pk(j * N + c, l * N + c)] += acc[s];
+                    Hp[pk(j * N + c, l * N + c)] += acc[0][s] + acc[1][s];
                 }
             }
             __syncwarp();
@@ -695,7 +801,7 @@ wsolve_kernel(const __grid_constant__ DevProb P, int B, double* __restrict__ z_i
                             Hp[pk(NZ, i)] = g[i];
                         }
                         h_valid = false;
-                        const bool ok = ws_ldl<NZ>(P, Hp, dz, sm + L::oFB);
+                        const bool ok = ws_ldl<NZ, L::LDW>(ttab, tcnt, Hp, dz, sm + L::oF);
                         if (ok) {
                             double a = 1.0, dmx = 0.0, fin = 0.0, pred = 0.0;
                             for (int i = lane; i < NZ; i += 32) {
@@ -781,10 +887,7 @@ int ws_launch(nlpf_problem* p, int B, double* z, const double* U, const double* 
         attr = true;
     }
     if (nlpf_check_cuda(cudaMemsetAsync(counter, 0, sizeof(int), st), "wsolve counter reset")) return NLPF_E_CUDA;
-    int per_sm = (int)((227 * 1024) / (smem + 1024));
-    if (per_sm < 1) per_sm = 1;
-    if (per_sm > 512 / (C::WARPS * 32)) per_sm = 512 / (C::WARPS * 32);
-    int grid = 148 * per_sm;
+    int grid = 148 * L::CTAS;
     const int need = (B + C::WARPS - 1) / C::WARPS;
     if (grid > need) grid = need;
     kern<<<grid, C::WARPS * 32, smem, st>>>(p->d, B, z, U, data, xprior, *o, cost_out, iters_out, status_out, hlin, counter);
