@@ -36,6 +36,15 @@ __device__ __forceinline__ double wmax(double v) {
 // entries at even columns load as double2
 __device__ __forceinline__ constexpr int po(int r) { return 2 * ((r + 1) >> 1) * ((r + 2) >> 1); }
 __device__ __forceinline__ constexpr int pk(int r, int c) { return po(r) + c; }
+// 16-byte asynchronous global -> shared copy (LDGSTS): the constant part of H streams in while the node
+// phases of the evaluation run.  CG: through L2 only (per-window cache, no reuse from L1).
+template <bool CG>
+__device__ __forceinline__ void cp_async16(double* dst_smem, const double* src) {
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(dst_smem);
+    if (CG) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(src) : "memory");
+    else asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 // reciprocal without the slow path of the IEEE division: MUFU seed (2^-20) + two Newton steps (pivots are
 // checked for d > 0 and finiteness by the caller)
 __device__ __forceinline__ double frcp(double d) {
@@ -157,7 +166,9 @@ struct WsLayout {
     static constexpr int NTILE = ((NZ + 2) / 2) * ((NZ + 2) / 4 + 1);   // bound on the tile table
     static constexpr int oTT = oDt + ev(K * K);        // tile table (uint16) and counts (int), as doubles
     static constexpr int oTC = oTT + ev((NTILE + 3) / 4);
-    static constexpr int TOTAL = oTC + ev((NZ + 3) / 2);
+    static constexpr bool PHIS = (C::MEAS == 1);       // interpolation matrix Phi (E x K) in shared memory, per CTA
+    static constexpr int oPhi = oTC + ev((NZ + 3) / 2);
+    static constexpr int TOTAL = oPhi + (PHIS ? ev(E * K) : 0);
     // resident CTAs per SM: shared memory (227 KB, 1 KB reserved per CTA) or 16 warps, whichever is smaller;
     // the register cap follows from it (GNSS / vehicle shapes: 8 warps per SM, so up to 255 registers)
     static constexpr int CTAS_SMEM = (227 * 1024) / (TOTAL * 8 + 1024);
@@ -167,7 +178,7 @@ struct WsLayout {
 // objective J, merit = J/2 + barrier, first-order rounding bound of the merit and (FULL) H (packed,
 // shared memory), g.  merit = +inf flags an iterate outside the bounds or a non-finite objective.
 template <class C, bool FULL>
-__device__ __forceinline__ void ws_eval(const DevProb& P, double* sm, const double* Dt, const double* zc,
+__device__ __forceinline__ void ws_eval(const DevProb& P, double* sm, const double* Dt, const double* PhiS, const double* zc,
                                         const double* Ug, const double* dg, const double* xp, const double* h0, double mu,
                                         double& J_out, double& merit_out, double& noise_out) {
     typedef WsLayout<C> L;
@@ -185,9 +196,11 @@ __device__ __forceinline__ void ws_eval(const DevProb& P, double* sm, const doub
     double cost = 0.0, nse = 0.0, bar = 0.0;
     bool bad = false;
     auto whv = [&](int k, int i) -> double { return HUB ? wh[k * N + i] : P.cw[k] * P.qinv[i]; };
+    auto phi = [&](int e, int j) -> double { return L::PHIS ? PhiS[e * K + j] : P.Phi[e * K + j]; };
+    auto phiT = [&](int j, int e) -> double { return L::PHIS ? PhiS[e * K + j] : P.PhiT[j * E + e]; };
 
-    if (FULL) {
-        for (int p = lane; p < L::NP; p += 32) Hp[p] = h0[p];        // constant part (+ linear measurements)
+    if (FULL) {       // constant part (+ linear measurements), asynchronously; waited for before the first use of Hp
+        for (int p = 2 * lane; p < L::NP; p += 64) cp_async16<C::MEAS == 0>(Hp + p, h0 + p);
     }
     // node dynamics
     for (int k = lane; k < K; k += 32) {
@@ -253,6 +266,8 @@ __device__ __forceinline__ void ws_eval(const DevProb& P, double* sm, const doub
             }
             g[t] = s;
         }
+        cp_async_wait_all();
+        __syncwarp();
         if (!C::HCONST) {
             // H_(j,a),(l,b) += -Dt_jl w_jb F_j[b][a] - Dt_lj w_la F_l[a][b]  (+ Huber: sum_k Dt_kj Dt_kl w_ka on a == b)
             for (int pr = lane; pr < K * (K + 1) / 2; pr += 32) {
@@ -346,7 +361,7 @@ __device__ __forceinline__ void ws_eval(const DevProb& P, double* sm, const doub
             double x0 = 0.0, x1 = 0.0, x2 = 0.0, xb = 0.0;
 #pragma unroll
             for (int j = 0; j < K; ++j) {
-                const double ph = P.PhiT[j * E + e];
+                const double ph = phiT(j, e);
                 x0 = fma(ph, zc[j * N + c0], x0);
                 x1 = fma(ph, zc[j * N + c1], x1);
                 x2 = fma(ph, zc[j * N + c2], x2);
@@ -356,7 +371,7 @@ __device__ __forceinline__ void ws_eval(const DevProb& P, double* sm, const doub
             double g00 = 0, g10 = 0, g11 = 0, g20 = 0, g21 = 0, g22 = 0, g30 = 0, g31 = 0, g32 = 0, g33 = 0;
             // records of the epoch's slots are fetched four at a time before any arithmetic (20 loads in
             // flight per lane: the slot-by-slot version spent a third of the kernel waiting on L2)
-#pragma unroll 1
+#pragma unroll
             for (int s0 = 0; s0 < NM; s0 += 4) {
                 double ry[4], rw[4], rx[4], rY[4], rz[4];
 #pragma unroll
@@ -391,10 +406,10 @@ __device__ __forceinline__ void ws_eval(const DevProb& P, double* sm, const doub
                 }
             }
             if (FULL) {
-                double* Ge = qv + e * 14;
-                Ge[0] = g00; Ge[1] = g10; Ge[2] = g11; Ge[3] = g20; Ge[4] = g21; Ge[5] = g22;
-                Ge[6] = g30; Ge[7] = g31; Ge[8] = g32; Ge[9] = g33;
-                Ge[10] = a0; Ge[11] = a1; Ge[12] = a2; Ge[13] = a3;
+                double2* Ge = reinterpret_cast<double2*>(qv + e * 14);     // 112-byte rows: 16-byte aligned
+                Ge[0] = make_double2(g00, g10); Ge[1] = make_double2(g11, g20); Ge[2] = make_double2(g21, g22);
+                Ge[3] = make_double2(g30, g31); Ge[4] = make_double2(g32, g33);
+                Ge[5] = make_double2(a0, a1); Ge[6] = make_double2(a2, a3);
             }
         }
         if (FULL) {
@@ -406,10 +421,10 @@ __device__ __forceinline__ void ws_eval(const DevProb& P, double* sm, const doub
 #pragma unroll 3
                 for (int e = 0; e + 3 < E; e += 4) {
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) ac[q] = fma(P.Phi[(e + q) * K + j], qv[(e + q) * 14 + 10 + a], ac[q]);
+                    for (int q = 0; q < 4; ++q) ac[q] = fma(phi(e + q, j), qv[(e + q) * 14 + 10 + a], ac[q]);
                 }
 #pragma unroll
-                for (int e = E & ~3; e < E; ++e) ac[e & 3] = fma(P.Phi[e * K + j], qv[e * 14 + 10 + a], ac[e & 3]);
+                for (int e = E & ~3; e < E; ++e) ac[e & 3] = fma(phi(e, j), qv[e * 14 + 10 + a], ac[e & 3]);
                 const int c = (a == 0) ? c0 : (a == 1) ? c1 : (a == 2) ? c2 : cb;
                 g[j * N + c] -= (ac[0] + ac[1]) + (ac[2] + ac[3]);
             }
@@ -428,10 +443,14 @@ __device__ __forceinline__ void ws_eval(const DevProb& P, double* sm, const doub
                 for (int q = 0; q < 10; ++q) h[q] = 0.0;
                 if (on) {
                     for (int e = eb; e < ee; ++e) {
-                        const double pp = P.Phi[e * K + j] * P.Phi[e * K + l];
-                        const double* Ge = qv + e * 14;
+                        const double pp = phi(e, j) * phi(e, l);
+                        const double2* Ge = reinterpret_cast<const double2*>(qv + e * 14);
 #pragma unroll
-                        for (int q = 0; q < 10; ++q) h[q] = fma(pp, Ge[q], h[q]);
+                        for (int q = 0; q < 5; ++q) {
+                            const double2 gv = Ge[q];
+                            h[2 * q] = fma(pp, gv.x, h[2 * q]);
+                            h[2 * q + 1] = fma(pp, gv.y, h[2 * q + 1]);
+                        }
                     }
                 }
 #pragma unroll
@@ -688,7 +707,7 @@ wsolve_kernel(const __grid_constant__ DevProb P, int B, double* __restrict__ z_i
     constexpr int NZ = L::NZ;
     constexpr bool BND = C::NB > 0;
     constexpr int NBD = BND ? C::NB : 1;
-    extern __shared__ double smem[];
+    extern __shared__ __align__(16) double smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     double* Dt = smem + L::oDt;
     for (int i = threadIdx.x; i < K * K; i += C::WARPS * 32) Dt[i] = P.Dt[i];
@@ -696,6 +715,10 @@ wsolve_kernel(const __grid_constant__ DevProb P, int B, double* __restrict__ z_i
     int* tcnt = reinterpret_cast<int*>(smem + L::oTC);
     for (int i = threadIdx.x; i < P.tile_cnt[NZ + 1]; i += C::WARPS * 32) ttab[i] = P.tile_tab[i];
     for (int i = threadIdx.x; i < NZ + 2; i += C::WARPS * 32) tcnt[i] = P.tile_cnt[i];
+    const double* PhiS = smem + L::oPhi;
+    if (L::PHIS) {
+        for (int i = threadIdx.x; i < E * K; i += C::WARPS * 32) smem[L::oPhi + i] = P.Phi[i];
+    }
     __syncthreads();
     double* sm = smem + warp * L::PER_WARP;
     double* Hp = sm + L::oH;
@@ -768,7 +791,7 @@ wsolve_kernel(const __grid_constant__ DevProb P, int B, double* __restrict__ z_i
         double mu = BND ? opt.mu0 : 0.0;
         int iters = 0, status = NLPF_ST_MAXITER;
         double lam = opt.lam0, J, merit, nse0;
-        ws_eval<C, true>(P, sm, Dt, zs, Ug, dg, xp, hlin, mu, J, merit, nse0);
+        ws_eval<C, true>(P, sm, Dt, PhiS, zs, Ug, dg, xp, hlin, mu, J, merit, nse0);
         if (!isfinite(merit)) {
             status = NLPF_ST_NUMERIC;
         } else {
@@ -793,7 +816,7 @@ wsolve_kernel(const __grid_constant__ DevProb P, int B, double* __restrict__ z_i
                     while (lam <= 1e18) {
                         if (!h_valid) {
                             double Jd, md, nd;
-                            ws_eval<C, true>(P, sm, Dt, zs, Ug, dg, xp, hlin, mu, Jd, md, nd);
+                            ws_eval<C, true>(P, sm, Dt, PhiS, zs, Ug, dg, xp, hlin, mu, Jd, md, nd);
                             h_valid = true;
                         }
                         for (int i = lane; i < NZ; i += 32) {
@@ -825,7 +848,7 @@ wsolve_kernel(const __grid_constant__ DevProb P, int B, double* __restrict__ z_i
                             if (fin == 0.0) {
                                 for (int i = lane; i < NZ; i += 32) zt[i] = fma(-a, dz[i], zs[i]);
                                 __syncwarp();
-                                ws_eval<C, false>(P, sm, Dt, zt, Ug, dg, xp, hlin, mu, Jt, mt, nset);
+                                ws_eval<C, false>(P, sm, Dt, PhiS, zt, Ug, dg, xp, hlin, mu, Jt, mt, nset);
                                 if (isfinite(mt) && mt < merit) { accepted = true; alpha = a; dzmax = dmx; break; }
                                 const double nb = nse0 + nset;
                                 if (isfinite(mt) && (mt - merit) <= nb && pred <= 4.0 * nb) {
@@ -839,7 +862,7 @@ wsolve_kernel(const __grid_constant__ DevProb P, int B, double* __restrict__ z_i
                         status = NLPF_ST_STALLED;
                         if (BND && !h_valid) {   // leave H, g consistent with z for a following stage
                             double Jd, md, nd;
-                            ws_eval<C, true>(P, sm, Dt, zs, Ug, dg, xp, hlin, mu, Jd, md, nd);
+                            ws_eval<C, true>(P, sm, Dt, PhiS, zs, Ug, dg, xp, hlin, mu, Jd, md, nd);
                         }
                         break;
                     }
@@ -854,13 +877,13 @@ wsolve_kernel(const __grid_constant__ DevProb P, int B, double* __restrict__ z_i
                     ++iters;
                     ++stage_steps;
                     __syncwarp();
-                    ws_eval<C, true>(P, sm, Dt, zs, Ug, dg, xp, hlin, mu, J, merit, nse0);
+                    ws_eval<C, true>(P, sm, Dt, PhiS, zs, Ug, dg, xp, hlin, mu, J, merit, nse0);
                     if (step < opt.tol_step * (1.0 + zm)) { status = NLPF_ST_CONVERGED; break; }
                     if (at_floor && ++floor_steps >= 5) { status = NLPF_ST_CONVERGED; break; }
                 }
                 if (!BND || mu <= opt.mu_min || iters >= opt.max_iter) break;
                 mu = fmax(opt.mu_min, fmin(0.2 * mu, mu * sqrt(mu)));
-                ws_eval<C, true>(P, sm, Dt, zs, Ug, dg, xp, hlin, mu, J, merit, nse0);
+                ws_eval<C, true>(P, sm, Dt, PhiS, zs, Ug, dg, xp, hlin, mu, J, merit, nse0);
             }
         }
         for (int i = lane; i < NZ; i += 32) z_io[(size_t)b * NZ + i] = zs[i];
@@ -894,11 +917,17 @@ int ws_launch(nlpf_problem* p, int B, double* z, const double* U, const double* 
     return nlpf_check_cuda(cudaGetLastError(), "wsolve_kernel launch");
 }
 
-typedef WsCfg<21, 2, 1, 50, 2, NLPF_DYN_VDP, 0, 4> CfgVdp;          // van der Pol MHE (BASELINE configs[1])
-typedef WsCfg<21, 2, 2, 50, 2, NLPF_DYN_AFFINE, 0, 4> CfgExample;   // estimation_example.py
-typedef WsCfg<11, 5, 3, 51, 12, NLPF_DYN_AFFINE, 1, 2> CfgGnss;     // gnss_stationary.py MHE (BASELINE configs[2])
-typedef WsCfg<6, 9, 2, 21, 11, NLPF_DYN_VEHICLE_GNSS, 1, 2, 2, true, NLPF_LOSS_L2> CfgCar;         // autonomous-car.py:184-220
-typedef WsCfg<6, 9, 2, 21, 11, NLPF_DYN_VEHICLE_GNSS, 1, 2, 2, true, NLPF_LOSS_HUBER> CfgCarHuber;  // autonomous-car.py:293-318
+#ifndef WS_PR_WARPS
+#define WS_PR_WARPS 2     // windows per CTA of the pseudorange shapes (shared memory allows 8-9 per SM)
+#endif
+#ifndef WS_LIN_WARPS
+#define WS_LIN_WARPS 8
+#endif
+typedef WsCfg<21, 2, 1, 50, 2, NLPF_DYN_VDP, 0, WS_LIN_WARPS> CfgVdp;          // van der Pol MHE (BASELINE configs[1])
+typedef WsCfg<21, 2, 2, 50, 2, NLPF_DYN_AFFINE, 0, WS_LIN_WARPS> CfgExample;   // estimation_example.py
+typedef WsCfg<11, 5, 3, 51, 12, NLPF_DYN_AFFINE, 1, WS_PR_WARPS> CfgGnss;     // gnss_stationary.py MHE (BASELINE configs[2])
+typedef WsCfg<6, 9, 2, 21, 11, NLPF_DYN_VEHICLE_GNSS, 1, WS_PR_WARPS, 2, true, NLPF_LOSS_L2> CfgCar;         // autonomous-car.py:184-220
+typedef WsCfg<6, 9, 2, 21, 11, NLPF_DYN_VEHICLE_GNSS, 1, WS_PR_WARPS, 2, true, NLPF_LOSS_HUBER> CfgCarHuber;  // autonomous-car.py:293-318
 
 }  // namespace
 
