@@ -848,7 +848,11 @@ wsolve_kernel(const __grid_constant__ DevProb P, int B, double* __restrict__ z_i
                             if (fin == 0.0) {
                                 for (int i = lane; i < NZ; i += 32) zt[i] = fma(-a, dz[i], zs[i]);
                                 __syncwarp();
-                                ws_eval<C, false>(P, sm, Dt, PhiS, zt, Ug, dg, xp, hlin, mu, Jt, mt, nset);
+                                // FULL evaluation at the trial point: an accepted step (the usual case) needs H and g
+                                // there anyway, so a cost-only pass would be paid on top (VDP +7 %, GNSS +20 %).  Choosing
+                                // between the two per step (cost-only after a rejection) was slower for every shape: the
+                                // second instantiation of the evaluation doubles the code (vehicle chains -15 %).
+                                ws_eval<C, true>(P, sm, Dt, PhiS, zt, Ug, dg, xp, hlin, mu, Jt, mt, nset);
                                 if (isfinite(mt) && mt < merit) { accepted = true; alpha = a; dzmax = dmx; break; }
                                 const double nb = nse0 + nset;
                                 if (isfinite(mt) && (mt - merit) <= nb && pred <= 4.0 * nb) {
@@ -876,8 +880,10 @@ wsolve_kernel(const __grid_constant__ DevProb P, int B, double* __restrict__ z_i
                     lam = fmax(lam / 10.0, 1e-12);
                     ++iters;
                     ++stage_steps;
+                    J = Jt;             // H, g, dd already belong to the accepted point
+                    merit = mt;
+                    nse0 = nset;
                     __syncwarp();
-                    ws_eval<C, true>(P, sm, Dt, PhiS, zs, Ug, dg, xp, hlin, mu, J, merit, nse0);
                     if (step < opt.tol_step * (1.0 + zm)) { status = NLPF_ST_CONVERGED; break; }
                     if (at_floor && ++floor_steps >= 5) { status = NLPF_ST_CONVERGED; break; }
                 }
@@ -918,7 +924,9 @@ int ws_launch(nlpf_problem* p, int B, double* z, const double* U, const double* 
 }
 
 #ifndef WS_PR_WARPS
-#define WS_PR_WARPS 2     // windows per CTA of the pseudorange shapes (shared memory allows 8-9 per SM)
+#define WS_PR_WARPS 2     // windows per CTA of the pseudorange shapes: 4 CTAs = 8 windows per SM (shared memory).
+                          // Measured alternatives: 3x3 / 1x9 warps 4 % slower (4096 windows = 27.7 per SM: 4 rounds
+                          // either way); 32-epoch chunks of G_e to fit 10 windows per SM: chunking cost 12 %, net -4 %
 #endif
 #ifndef WS_LIN_WARPS
 #define WS_LIN_WARPS 8
