@@ -788,19 +788,42 @@ wsolve_kernel(const __grid_constant__ DevProb P, int B, double* __restrict__ z_i
             }
             __syncwarp();
         }
+        // ---- solver driver (same decisions as solve_kernel in nls_kernels.inl and oracle/nls.py) ----
+        // Written as a state machine around ONE inlined evaluation and ONE factorisation site: with the
+        // evaluation inlined at its five logical call sites the vehicle kernel spent 23 % of its issue slots
+        // waiting for instructions (ncu stall "no_instructions").
+        //   EV_FIRST  evaluation at the start point            EV_STAGE  after a barrier-parameter update
+        //   EV_TRIAL  at the trial point z - alpha dz          EV_RESTORE / EV_STALL  H, g back at z after a
+        //                                                       rejected step (the factorisation overwrote H)
+        enum { EV_FIRST, EV_STAGE, EV_TRIAL, EV_RESTORE, EV_STALL };
+        enum { PC_STAGE_INIT, PC_ITER_TOP, PC_LAM_TOP, PC_SOLVE, PC_AFTER_TRIAL, PC_STAGE_END };
         double mu = BND ? opt.mu0 : 0.0;
-        int iters = 0, status = NLPF_ST_MAXITER;
-        double lam = opt.lam0, J, merit, nse0;
-        ws_eval<C, true>(P, sm, Dt, PhiS, zs, Ug, dg, xp, hlin, mu, J, merit, nse0);
-        if (!isfinite(merit)) {
-            status = NLPF_ST_NUMERIC;
-        } else {
-            while (true) {   // barrier stages (a single pass without bounds)
-                lam = opt.lam0;
-                int stage_steps = 0, floor_steps = 0;
-                status = NLPF_ST_MAXITER;
-                while (iters < opt.max_iter && stage_steps < opt.max_stage_iter) {
-                    double gm = 0.0, dm = 0.0;
+        int iters = 0, status = NLPF_ST_MAXITER, stage_steps = 0, floor_steps = 0;
+        double lam = opt.lam0, J = 0.0, merit = 0.0, nse0 = 0.0;
+        double Jt = 0.0, mt = 0.0, nset = 0.0, dzmax = 0.0, alpha = 1.0, pred = 0.0, dm = 0.0;
+        bool h_valid = true;
+        int ev = EV_FIRST;
+        while (true) {
+            {
+                double Je, me, ne;
+                ws_eval<C, true>(P, sm, Dt, PhiS, (ev == EV_TRIAL) ? zt : zs, Ug, dg, xp, hlin, mu, Je, me, ne);
+                if (ev == EV_TRIAL) { Jt = Je; mt = me; nset = ne; }
+                else if (ev == EV_FIRST || ev == EV_STAGE) { J = Je; merit = me; nse0 = ne; }
+            }
+            if (ev == EV_FIRST && !isfinite(merit)) { status = NLPF_ST_NUMERIC; break; }
+            int pc = (ev == EV_TRIAL) ? PC_AFTER_TRIAL : (ev == EV_RESTORE) ? PC_SOLVE : (ev == EV_STALL) ? PC_STAGE_END : PC_STAGE_INIT;
+            bool need_eval = false, finished = false;
+            while (!need_eval) {
+                if (pc == PC_STAGE_INIT) {
+                    lam = opt.lam0;
+                    stage_steps = 0;
+                    floor_steps = 0;
+                    status = NLPF_ST_MAXITER;
+                    pc = PC_ITER_TOP;
+                } else if (pc == PC_ITER_TOP) {
+                    if (!(iters < opt.max_iter && stage_steps < opt.max_stage_iter)) { pc = PC_STAGE_END; continue; }
+                    double gm = 0.0;
+                    dm = 0.0;
                     for (int i = lane; i < NZ; i += 32) {
                         gm = fmax(gm, fabs(g[i]));
                         ds[i] = Hp[pk(i, i)];
@@ -809,67 +832,69 @@ wsolve_kernel(const __grid_constant__ DevProb P, int B, double* __restrict__ z_i
                     dm = wmax(dm);
                     if (BND) {
                         gm = wmax(gm);
-                        if (mu > opt.mu_min && stage_steps >= 1 && gm < 10.0 * mu) { status = NLPF_ST_CONVERGED; break; }
+                        if (mu > opt.mu_min && stage_steps >= 1 && gm < 10.0 * mu) { status = NLPF_ST_CONVERGED; pc = PC_STAGE_END; continue; }
                     }
-                    bool accepted = false, at_floor = false, h_valid = true;
-                    double Jt = J, mt = merit, nset = 0.0, dzmax = 0.0, alpha = 1.0;
-                    while (lam <= 1e18) {
-                        if (!h_valid) {
-                            double Jd, md, nd;
-                            ws_eval<C, true>(P, sm, Dt, PhiS, zs, Ug, dg, xp, hlin, mu, Jd, md, nd);
-                            h_valid = true;
-                        }
-                        for (int i = lane; i < NZ; i += 32) {
-                            Hp[pk(i, i)] = ds[i] + lam * (dd[i] + 1e-14 * dm);
-                            Hp[pk(NZ, i)] = g[i];
-                        }
-                        h_valid = false;
-                        const bool ok = ws_ldl<NZ, L::LDW>(ttab, tcnt, Hp, dz, sm + L::oF);
-                        if (ok) {
-                            double a = 1.0, dmx = 0.0, fin = 0.0, pred = 0.0;
-                            for (int i = lane; i < NZ; i += 32) {
-                                dmx = fmax(dmx, fabs(dz[i]));
-                                if (!isfinite(dz[i])) fin = 1.0;
-                                pred = fma(g[i], dz[i], pred);
-                            }
-                            if (BND) {   // fraction to the boundary
-                                for (int t = lane; t < K * C::NB; t += 32) {
-                                    const int k = t / NBD, bb = t - k * NBD;
-                                    const int idx = k * N + P.bidx[bb];
-                                    const double st = -dz[idx];
-                                    if (st < 0.0 && P.blo[bb] > -1e300) a = fmin(a, opt.tau_ftb * (zs[idx] - P.blo[bb]) / (-st));
-                                    if (st > 0.0 && P.bhi[bb] < 1e300) a = fmin(a, opt.tau_ftb * (P.bhi[bb] - zs[idx]) / st);
-                                }
-                                a = -wmax(-a);
-                            }
-                            dmx = wmax(dmx);
-                            fin = wmax(fin);
-                            pred = a * wsum(pred);
-                            if (fin == 0.0) {
-                                for (int i = lane; i < NZ; i += 32) zt[i] = fma(-a, dz[i], zs[i]);
-                                __syncwarp();
-                                // FULL evaluation at the trial point: an accepted step (the usual case) needs H and g
-                                // there anyway, so a cost-only pass would be paid on top (VDP +7 %, GNSS +20 %).  Choosing
-                                // between the two per step (cost-only after a rejection) was slower for every shape: the
-                                // second instantiation of the evaluation doubles the code (vehicle chains -15 %).
-                                ws_eval<C, true>(P, sm, Dt, PhiS, zt, Ug, dg, xp, hlin, mu, Jt, mt, nset);
-                                if (isfinite(mt) && mt < merit) { accepted = true; alpha = a; dzmax = dmx; break; }
-                                const double nb = nse0 + nset;
-                                if (isfinite(mt) && (mt - merit) <= nb && pred <= 4.0 * nb) {
-                                    accepted = true; at_floor = true; alpha = a; dzmax = dmx; break;
-                                }
-                            }
-                        }
-                        lam *= 10.0;
-                    }
-                    if (!accepted) {
+                    h_valid = true;
+                    pc = PC_LAM_TOP;
+                } else if (pc == PC_LAM_TOP) {
+                    if (!(lam <= 1e18)) {   // no acceptable step
                         status = NLPF_ST_STALLED;
-                        if (BND && !h_valid) {   // leave H, g consistent with z for a following stage
-                            double Jd, md, nd;
-                            ws_eval<C, true>(P, sm, Dt, PhiS, zs, Ug, dg, xp, hlin, mu, Jd, md, nd);
-                        }
-                        break;
+                        if (BND && !h_valid) { ev = EV_STALL; need_eval = true; continue; }   // H, g consistent for a following stage
+                        pc = PC_STAGE_END;
+                        continue;
                     }
+                    if (!h_valid) { h_valid = true; ev = EV_RESTORE; need_eval = true; continue; }
+                    pc = PC_SOLVE;
+                } else if (pc == PC_SOLVE) {
+                    for (int i = lane; i < NZ; i += 32) {
+                        Hp[pk(i, i)] = ds[i] + lam * (dd[i] + 1e-14 * dm);
+                        Hp[pk(NZ, i)] = g[i];
+                    }
+                    h_valid = false;
+                    const bool ok = ws_ldl<NZ, L::LDW>(ttab, tcnt, Hp, dz, sm + L::oF);
+                    if (ok) {
+                        double a = 1.0, dmx = 0.0, fin = 0.0, pr = 0.0;
+                        for (int i = lane; i < NZ; i += 32) {
+                            dmx = fmax(dmx, fabs(dz[i]));
+                            if (!isfinite(dz[i])) fin = 1.0;
+                            pr = fma(g[i], dz[i], pr);
+                        }
+                        if (BND) {   // fraction to the boundary
+                            for (int t = lane; t < K * C::NB; t += 32) {
+                                const int k = t / NBD, bb = t - k * NBD;
+                                const int idx = k * N + P.bidx[bb];
+                                const double sd = -dz[idx];
+                                if (sd < 0.0 && P.blo[bb] > -1e300) a = fmin(a, opt.tau_ftb * (zs[idx] - P.blo[bb]) / (-sd));
+                                if (sd > 0.0 && P.bhi[bb] < 1e300) a = fmin(a, opt.tau_ftb * (P.bhi[bb] - zs[idx]) / sd);
+                            }
+                            a = -wmax(-a);
+                        }
+                        dmx = wmax(dmx);
+                        fin = wmax(fin);
+                        pr = a * wsum(pr);
+                        if (fin == 0.0) {
+                            for (int i = lane; i < NZ; i += 32) zt[i] = fma(-a, dz[i], zs[i]);
+                            __syncwarp();
+                            // FULL evaluation at the trial point: an accepted step (the usual case) needs H and g
+                            // there anyway, so a cost-only pass would be paid on top (VDP +7 %, GNSS +20 %)
+                            alpha = a;
+                            dzmax = dmx;
+                            pred = pr;
+                            ev = EV_TRIAL;
+                            need_eval = true;
+                            continue;
+                        }
+                    }
+                    lam *= 10.0;
+                    pc = PC_LAM_TOP;
+                } else if (pc == PC_AFTER_TRIAL) {
+                    bool accepted = false, at_floor = false;
+                    if (isfinite(mt) && mt < merit) accepted = true;
+                    else {
+                        const double nb = nse0 + nset;
+                        if (isfinite(mt) && (mt - merit) <= nb && pred <= 4.0 * nb) { accepted = true; at_floor = true; }
+                    }
+                    if (!accepted) { lam *= 10.0; pc = PC_LAM_TOP; continue; }
                     const double step = alpha * dzmax;
                     double zm = 0.0;
                     for (int i = lane; i < NZ; i += 32) {
@@ -884,13 +909,17 @@ wsolve_kernel(const __grid_constant__ DevProb P, int B, double* __restrict__ z_i
                     merit = mt;
                     nse0 = nset;
                     __syncwarp();
-                    if (step < opt.tol_step * (1.0 + zm)) { status = NLPF_ST_CONVERGED; break; }
-                    if (at_floor && ++floor_steps >= 5) { status = NLPF_ST_CONVERGED; break; }
+                    pc = PC_ITER_TOP;
+                    if (step < opt.tol_step * (1.0 + zm)) { status = NLPF_ST_CONVERGED; pc = PC_STAGE_END; }
+                    else if (at_floor && ++floor_steps >= 5) { status = NLPF_ST_CONVERGED; pc = PC_STAGE_END; }
+                } else {   // PC_STAGE_END
+                    if (!BND || mu <= opt.mu_min || iters >= opt.max_iter) { finished = true; break; }
+                    mu = fmax(opt.mu_min, fmin(0.2 * mu, mu * sqrt(mu)));
+                    ev = EV_STAGE;
+                    need_eval = true;
                 }
-                if (!BND || mu <= opt.mu_min || iters >= opt.max_iter) break;
-                mu = fmax(opt.mu_min, fmin(0.2 * mu, mu * sqrt(mu)));
-                ws_eval<C, true>(P, sm, Dt, PhiS, zs, Ug, dg, xp, hlin, mu, J, merit, nse0);
             }
+            if (finished) break;
         }
         for (int i = lane; i < NZ; i += 32) z_io[(size_t)b * NZ + i] = zs[i];
         if (lane == 0) {
