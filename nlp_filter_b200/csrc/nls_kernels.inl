@@ -1259,7 +1259,9 @@ VN(solve_kernel)(const __grid_constant__ DevProb P, int B, double* __restrict__ 
                             if (finite == 0.0) {
                                 for (int i = tid; i < nz; i += NLPF_NT) zt[i] = fma(-a, dz[i], zs[i]);
                                 __syncthreads();
-                                eval_window<false>(P, sm, zt, wp, mu, Jt, mt, nset, hmode);
+                                // FULL evaluation at the trial point: an accepted step (the usual case) needs H and g
+                                // there anyway; a rejected one rebuilds H at z below, as it had to before
+                                eval_window<true>(P, sm, zt, wp, mu, Jt, mt, nset, hmode);
                                 if (isfinite(mt) && mt < merit) {
                                     accepted = true;
                                     alpha = a;
@@ -1298,7 +1300,9 @@ VN(solve_kernel)(const __grid_constant__ DevProb P, int B, double* __restrict__ 
                     lam = fmax(lam / 10.0, 1e-12);
                     ++iters;
                     ++stage_steps;
-                    eval_window<true>(P, sm, zs, wp, mu, J, merit, nse0, hmode);
+                    J = Jt;               // H, g, dd already belong to the accepted point
+                    merit = mt;
+                    nse0 = nset;
                     if (step < opt.tol_step * (1.0 + zm)) {
                         status = NLPF_ST_CONVERGED;
                         break;

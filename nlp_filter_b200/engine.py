@@ -11,6 +11,8 @@ problem class at once.
 """
 import ctypes
 
+import os
+
 import numpy as np
 import torch
 
@@ -134,7 +136,12 @@ class HostBatch(object):
         d = prob.desc
         self.prob, self.B = prob, B
         if nchunk is None:
-            nchunk = 4 if B >= 1024 else 1
+            # chunk only when the copies are comparable to the solve: GNSS windows carry 25 KB of records
+            # (103 MB per 4096 windows: 4 chunks); a van der Pol window 2 KB (one launch fills the GPU better
+            # than four quarter-size ones).  NLPF_E2E_CHUNKS overrides.
+            env = os.environ.get("NLPF_E2E_CHUNKS")
+            in_bytes = 8 * B * (d.nz + d.K * d.m + max(d.Ldata, 1) + d.n)
+            nchunk = int(env) if env else (4 if (B >= 1024 and in_bytes >= (32 << 20)) else 1)
         self.nchunk = max(1, min(int(nchunk), B))
         cuts = [(B * c) // self.nchunk for c in range(self.nchunk + 1)]
         self.chunks = [(cuts[c], cuts[c + 1]) for c in range(self.nchunk)]
