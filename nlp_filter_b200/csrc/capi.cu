@@ -321,6 +321,10 @@ extern "C" int nlpf_problem_create(const nlpf_desc* D, nlpf_problem** out) {
                             (q == 0 || rtype_s[s2] == NLPF_RT_PR)) uniform = false;
                 }
             }
+            // the warp kernel addresses records arithmetically: [y, w] / [y, w, sat xyz] back to back
+            const int rlen = P.lin_meas ? 2 : 5;
+            for (int r = 0; r < M && uniform; ++r) if (roff_s[r] != rlen * r) uniform = false;
+            if (uniform && P.lin_meas && NM > 4) uniform = false;
             if (uniform && P.lin_meas) {
                 for (int s2 = 0; s2 < NM; ++s2) mslot[act[rloc_s[(size_t)s2 * NLPF_NIDX]]] = s2;
                 if (plain) p->ws_variant = nlpf_ws_variant(K, n, m, E, NM, D->dyn_id, 0, D->nb, P.has_prior, D->loss);

@@ -166,19 +166,30 @@ struct WsLayout {
     static constexpr int NTILE = ((NZ + 2) / 2) * ((NZ + 2) / 4 + 1);   // bound on the tile table
     static constexpr int oTT = oDt + ev(K * K);        // tile table (uint16) and counts (int), as doubles
     static constexpr int oTC = oTT + ev((NTILE + 3) / 4);
-    static constexpr bool PHIS = (C::MEAS == 1);       // interpolation matrix Phi (E x K) in shared memory, per CTA
+    // class constants staged once per CTA: interpolation matrix Phi (E x K), cw_k * qinv_i, node-pair table
     static constexpr int oPhi = oTC + ev((NZ + 3) / 2);
-    static constexpr int TOTAL = oPhi + (PHIS ? ev(E * K) : 0);
+    static constexpr int oCW = oPhi + ev(E * K);
+    static constexpr int oPT = oCW + ev(NZ);
+    static constexpr int TOTAL = oPT + ev((K * (K + 1) / 2 + 3) / 4);
     // resident CTAs per SM: shared memory (227 KB, 1 KB reserved per CTA) or 16 warps, whichever is smaller;
     // the register cap follows from it (GNSS / vehicle shapes: 8 warps per SM, so up to 255 registers)
     static constexpr int CTAS_SMEM = (227 * 1024) / (TOTAL * 8 + 1024);
     static constexpr int CTAS = (CTAS_SMEM < 512 / (C::WARPS * 32)) ? (CTAS_SMEM < 1 ? 1 : CTAS_SMEM) : 512 / (C::WARPS * 32);
 };
 
+// CTA-shared class constants (shared memory) and the measured components (registers)
+struct WsConst {
+    const double* Dt;        // K x K
+    const double* Phi;       // E x K
+    const double* cwq;       // cw_k * qinv_i
+    const uint16_t* ptab;    // node pairs j | l << 8
+    int c[4];                // MEAS 0: component of slot s (s < NM <= 4);  MEAS 1: (c0, c1, c2 | cb)
+};
+
 // objective J, merit = J/2 + barrier, first-order rounding bound of the merit and (FULL) H (packed,
 // shared memory), g.  merit = +inf flags an iterate outside the bounds or a non-finite objective.
 template <class C, bool FULL>
-__device__ __forceinline__ void ws_eval(const DevProb& P, double* sm, const double* Dt, const double* PhiS, const double* zc,
+__device__ __forceinline__ void ws_eval(const DevProb& P, double* sm, const WsConst& cs, const double* zc,
                                         const double* Ug, const double* dg, const double* xp, const double* h0, double mu,
                                         double& J_out, double& merit_out, double& noise_out) {
     typedef WsLayout<C> L;
@@ -195,9 +206,10 @@ __device__ __forceinline__ void ws_eval(const DevProb& P, double* sm, const doub
     double* qv = sm + L::oQ;
     double cost = 0.0, nse = 0.0, bar = 0.0;
     bool bad = false;
-    auto whv = [&](int k, int i) -> double { return HUB ? wh[k * N + i] : P.cw[k] * P.qinv[i]; };
-    auto phi = [&](int e, int j) -> double { return L::PHIS ? PhiS[e * K + j] : P.Phi[e * K + j]; };
-    auto phiT = [&](int j, int e) -> double { return L::PHIS ? PhiS[e * K + j] : P.PhiT[j * E + e]; };
+    const double* Dt = cs.Dt;
+    auto whv = [&](int k, int i) -> double { return HUB ? wh[k * N + i] : cs.cwq[k * N + i]; };
+    auto phi = [&](int e, int j) -> double { return cs.Phi[e * K + j]; };
+    auto phiT = [&](int j, int e) -> double { return cs.Phi[e * K + j]; };
 
     if (FULL) {       // constant part (+ linear measurements), asynchronously; waited for before the first use of Hp
         for (int p = 2 * lane; p < L::NP; p += 64) cp_async16<C::MEAS == 0>(Hp + p, h0 + p);
@@ -232,7 +244,7 @@ __device__ __forceinline__ void ws_eval(const DevProb& P, double* sm, const doub
             else { Wa += dx; mga += fabs(dx); }
         }
         const double W = Wa + Wb, mag = mga + mgb;
-        const double cq = P.cw[k] * P.qinv[i];
+        const double cq = cs.cwq[t];
         if (HUB) {                                          // pseudo_huber_loss, cost_functions.py:25-31
             const double wd = W / P.delta;
             const double s = sqrt(1.0 + wd * wd);
@@ -271,7 +283,7 @@ __device__ __forceinline__ void ws_eval(const DevProb& P, double* sm, const doub
         if (!C::HCONST) {
             // H_(j,a),(l,b) += -Dt_jl w_jb F_j[b][a] - Dt_lj w_la F_l[a][b]  (+ Huber: sum_k Dt_kj Dt_kl w_ka on a == b)
             for (int pr = lane; pr < K * (K + 1) / 2; pr += 32) {
-                const int pe = P.ptab[pr];
+                const int pe = cs.ptab[pr];
                 const int j = pe & 255, l = pe >> 8;
                 const double djl = Dt[j * K + l], dlj = Dt[l * K + j];
 #pragma unroll 3
@@ -318,13 +330,14 @@ __device__ __forceinline__ void ws_eval(const DevProb& P, double* sm, const doub
         // linear measurements: residual t = e*NM + s measures one state component at epoch e (record [y, w])
         for (int t = lane; t < L::NR; t += 32) {
             const int e = t / NM;
-            const int c = P.act[P.rloc[t * NLPF_NIDX]];
-            const double* rec = dg + P.roff[t];
+            const int sl = t - e * NM;
+            const int c = (sl == 0) ? cs.c[0] : (sl == 1) ? cs.c[1] : (sl == 2) ? cs.c[2] : cs.c[3];
+            const double* rec = dg + 2 * t;                  // uniform layout: records [y, w] back to back (checked on the host)
             const double w = rec[1];
             double va = 0.0, vb = 0.0, vc = 0.0;
 #pragma unroll
             for (int j = 0; j < K; ++j) {
-                const double ph = P.PhiT[j * E + e], zv = zc[j * N + c];
+                const double ph = phiT(j, e), zv = zc[j * N + c];
                 if (j % 3 == 0) va = fma(ph, zv, va);
                 else if (j % 3 == 1) vb = fma(ph, zv, vb);
                 else vc = fma(ph, zv, vc);
@@ -339,16 +352,19 @@ __device__ __forceinline__ void ws_eval(const DevProb& P, double* sm, const doub
             __syncwarp();
             for (int t = lane; t < NZ; t += 32) {
                 const int j = t / N, a = t - j * N;
-                const int s = P.mslot[a];                  // slot of component a in an epoch's record set, or -1
+                int s = -1;                                // slot of component a in an epoch's record set, or -1
+#pragma unroll
+                for (int q = 0; q < (NM < 4 ? NM : 4); ++q)
+                    if (cs.c[q] == a) s = q;
                 if (s >= 0) {
                     double ac[4] = {0.0, 0.0, 0.0, 0.0};
 #pragma unroll 3
                     for (int e = 0; e + 3 < E; e += 4) {
 #pragma unroll
-                        for (int q = 0; q < 4; ++q) ac[q] = fma(P.Phi[(e + q) * K + j], qv[(e + q) * NM + s], ac[q]);
+                        for (int q = 0; q < 4; ++q) ac[q] = fma(phi(e + q, j), qv[(e + q) * NM + s], ac[q]);
                     }
 #pragma unroll
-                    for (int e = E & ~3; e < E; ++e) ac[e & 3] = fma(P.Phi[e * K + j], qv[e * NM + s], ac[e & 3]);
+                    for (int e = E & ~3; e < E; ++e) ac[e & 3] = fma(phi(e, j), qv[e * NM + s], ac[e & 3]);
                     g[t] -= (ac[0] + ac[1]) + (ac[2] + ac[3]);
                 }
             }
@@ -356,7 +372,7 @@ __device__ __forceinline__ void ws_eval(const DevProb& P, double* sm, const doub
     } else {
         // pseudoranges (measurements.py:56-70, 81-87): one lane per epoch, NM satellite slots, components
         // (c0,c1,c2 | cb); G_e = sum w grad grad^T (10 unique) and q_e = sum w r grad in registers
-        const int c0 = P.act[P.run_loc[0]], c1 = P.act[P.run_loc[1]], c2 = P.act[P.run_loc[2]], cb = P.act[P.run_loc[3]];
+        const int c0 = cs.c[0], c1 = cs.c[1], c2 = cs.c[2], cb = cs.c[3];
         for (int e = lane; e < E; e += 32) {
             double x0 = 0.0, x1 = 0.0, x2 = 0.0, xb = 0.0;
 #pragma unroll
@@ -377,7 +393,7 @@ __device__ __forceinline__ void ws_eval(const DevProb& P, double* sm, const doub
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
                     const bool in = s0 + q < NM;
-                    const double* rec = dg + (in ? P.roff[e * NM + s0 + q] : 0);
+                    const double* rec = dg + (in ? 5 * (e * NM + s0 + q) : 0);   // uniform layout: [y, w, sat xyz] (host-checked)
                     ry[q] = rec[0];
                     rw[q] = in ? rec[1] : 0.0;
                     rx[q] = rec[2];
@@ -435,7 +451,7 @@ __device__ __forceinline__ void ws_eval(const DevProb& P, double* sm, const doub
             for (int it0 = 0; it0 < 2 * NPAIR; it0 += 32) {
                 const int it = it0 + lane;
                 const bool on = it < 2 * NPAIR;
-                const int pe = P.ptab[on ? (it >> 1) : 0];
+                const int pe = cs.ptab[on ? (it >> 1) : 0];
                 const int j = pe & 255, l = pe >> 8;
                 const int eb = (it & 1) * EH, ee = (it & 1) ? E : EH;
                 double h[10];
@@ -715,9 +731,19 @@ wsolve_kernel(const __grid_constant__ DevProb P, int B, double* __restrict__ z_i
     int* tcnt = reinterpret_cast<int*>(smem + L::oTC);
     for (int i = threadIdx.x; i < P.tile_cnt[NZ + 1]; i += C::WARPS * 32) ttab[i] = P.tile_tab[i];
     for (int i = threadIdx.x; i < NZ + 2; i += C::WARPS * 32) tcnt[i] = P.tile_cnt[i];
-    const double* PhiS = smem + L::oPhi;
-    if (L::PHIS) {
-        for (int i = threadIdx.x; i < E * K; i += C::WARPS * 32) smem[L::oPhi + i] = P.Phi[i];
+    uint16_t* ptab_s = reinterpret_cast<uint16_t*>(smem + L::oPT);
+    for (int i = threadIdx.x; i < E * K; i += C::WARPS * 32) smem[L::oPhi + i] = P.Phi[i];
+    for (int i = threadIdx.x; i < NZ; i += C::WARPS * 32) smem[L::oCW + i] = P.cw[i / N] * P.qinv[i % N];
+    for (int i = threadIdx.x; i < K * (K + 1) / 2; i += C::WARPS * 32) ptab_s[i] = P.ptab[i];
+    WsConst cs;
+    cs.Dt = Dt;
+    cs.Phi = smem + L::oPhi;
+    cs.cwq = smem + L::oCW;
+    cs.ptab = ptab_s;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        if (C::MEAS == 0) cs.c[q] = (q < NM) ? P.act[P.rloc[q * NLPF_NIDX]] : -1;
+        else cs.c[q] = P.act[P.run_loc[q]];
     }
     __syncthreads();
     double* sm = smem + warp * L::PER_WARP;
@@ -745,10 +771,10 @@ wsolve_kernel(const __grid_constant__ DevProb P, int B, double* __restrict__ z_i
             hlin = hl;
             for (int p = lane; p < L::NP; p += 32) Hp[p] = P.Hcp[p];
             double* wts = sm + L::oQ;
-            for (int t = lane; t < L::NR; t += 32) wts[t] = dg[P.roff[t] + 1];
+            for (int t = lane; t < L::NR; t += 32) wts[t] = dg[2 * t + 1];
             __syncwarp();
             for (int pr = lane; pr < K * (K + 1) / 2; pr += 32) {
-                const int pe = P.ptab[pr];
+                const int pe = cs.ptab[pr];
                 const int j = pe & 255, l = pe >> 8;
                 double acc[2][NM];
 #pragma unroll
@@ -757,19 +783,19 @@ wsolve_kernel(const __grid_constant__ DevProb P, int B, double* __restrict__ z_i
                 for (int e = 0; e + 1 < E; e += 2) {
 #pragma unroll
                     for (int h = 0; h < 2; ++h) {
-                        const double pp = P.Phi[(e + h) * K + j] * P.Phi[(e + h) * K + l];
+                        const double pp = cs.Phi[(e + h) * K + j] * cs.Phi[(e + h) * K + l];
 #pragma unroll
                         for (int s = 0; s < NM; ++s) acc[h][s] = fma(pp, wts[(e + h) * NM + s], acc[h][s]);
                     }
                 }
                 if (E & 1) {
-                    const double pp = P.Phi[(E - 1) * K + j] * P.Phi[(E - 1) * K + l];
+                    const double pp = cs.Phi[(E - 1) * K + j] * cs.Phi[(E - 1) * K + l];
 #pragma unroll
                     for (int s = 0; s < NM; ++s) acc[0][s] = fma(pp, wts[(E - 1) * NM + s], acc[0][s]);
                 }
 #pragma unroll
                 for (int s = 0; s < NM; ++s) {
-                    const int c = P.act[P.rloc[s * NLPF_NIDX]];
+                    const int c = cs.c[s < 4 ? s : 3];
                     Hp[pk(j * N + c, l * N + c)] += acc[0][s] + acc[1][s];
                 }
             }
@@ -806,7 +832,7 @@ wsolve_kernel(const __grid_constant__ DevProb P, int B, double* __restrict__ z_i
         while (true) {
             {
                 double Je, me, ne;
-                ws_eval<C, true>(P, sm, Dt, PhiS, (ev == EV_TRIAL) ? zt : zs, Ug, dg, xp, hlin, mu, Je, me, ne);
+                ws_eval<C, true>(P, sm, cs, (ev == EV_TRIAL) ? zt : zs, Ug, dg, xp, hlin, mu, Je, me, ne);
                 if (ev == EV_TRIAL) { Jt = Je; mt = me; nset = ne; }
                 else if (ev == EV_FIRST || ev == EV_STAGE) { J = Je; merit = me; nse0 = ne; }
             }
