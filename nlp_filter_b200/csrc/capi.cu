@@ -364,6 +364,12 @@ extern "C" int nlpf_problem_create(const nlpf_desc* D, nlpf_problem** out) {
         tile_cnt[s] = (int)tile_tab.size();
     }
 
+    // general measurement-Hessian accumulation: G_e is symmetric, so only b <= a is summed, in blocks of 4
+    std::vector<uint16_t> sym_tab;
+    for (int a = 0; a < na; ++a)
+        for (int b0 = 0; b0 <= a; b0 += 4) sym_tab.push_back((uint16_t)(a | (b0 << 8)));
+    P.nsym = (int)sym_tab.size();
+
     // ---- blob ----
     Blob B;
     std::vector<double> zero1(1, 0.0);
@@ -377,7 +383,7 @@ extern "C" int nlpf_problem_create(const nlpf_desc* D, nlpf_problem** out) {
                  oPh = B.add(D->Phi, sizeof(double) * E * K), ort = B.addv(rtype_s), orl = B.addv(rloc_s),
                  oro = B.addv(roff_s), oes = B.addv(estart), oac = B.addv(act), oHc = B.addv(Hc), oFc = B.addv(Fc),
                  otb = B.addv(tab), opt = B.addv(ptab), osg = B.addv(seg_tab), osc = B.addv(seg_cnt),
-                 oPT = B.addv(PhiT), oHp = B.addv(Hcp), ott = B.addv(tile_tab), otc = B.addv(tile_cnt), oms = B.addv(mslot), ogs = B.addv(gstart), oer = B.addv(erun), ors = B.addv(run_start), orn = B.addv(run_len), orc = B.addv(run_loc);
+                 oPT = B.addv(PhiT), oHp = B.addv(Hcp), osy = B.addv(sym_tab), ott = B.addv(tile_tab), otc = B.addv(tile_cnt), oms = B.addv(mslot), ogs = B.addv(gstart), oer = B.addv(erun), ors = B.addv(run_start), orn = B.addv(run_len), orc = B.addv(run_loc);
     B.add(zero1.data(), 16);
     p->blob_bytes = B.host.size();
     cudaGetDevice(&p->device);
@@ -395,6 +401,7 @@ extern "C" int nlpf_problem_create(const nlpf_desc* D, nlpf_problem** out) {
     P.estart = (const int*)(base + oes); P.act = (const int*)(base + oac); P.Hc = (const double*)(base + oHc);
     P.Fc = (const double*)(base + oFc); P.tab = (const uint32_t*)(base + otb); P.ptab = (const uint16_t*)(base + opt);
     P.seg_tab = (const uint16_t*)(base + osg); P.seg_cnt = (const int*)(base + osc);
+    P.sym_tab = (const uint16_t*)(base + osy);
     P.Hcp = (const double*)(base + oHp); P.tile_tab = (const uint16_t*)(base + ott); P.tile_cnt = (const int*)(base + otc);
     P.PhiT = (const double*)(base + oPT); P.mslot = (const int*)(base + oms);
     P.gstart = (const int*)(base + ogs); P.erun = (const int*)(base + oer); P.run_start = (const int*)(base + ors);

@@ -774,30 +774,49 @@ __device__ void eval_window(const DevProb& P, double* sm, const double* zc, cons
                     if (c3_ <= r) Hp[pk(r, c3_)] += a3;
                 }
             } else {
-                // work item = (node pair, component a, block of up to NLPF_NA_MAX components b)
-                const int nbb = (na + NLPF_NA_MAX - 1) / NLPF_NA_MAX;
-                for (int wk = tid; wk < nwork * nbb; wk += NLPF_NT) {
-                    const int w2 = wk / nbb, b0 = (wk - w2 * nbb) * NLPF_NA_MAX;
-                    const int pr = w2 / na, a = w2 - pr * na;
+                // work item = (node pair, row a, block of 4 columns b0..b0+3 <= a) of the LOWER triangle of G_e:
+                // G_e is symmetric, so block (j,l) of H is too and entry (a,b) also serves (b,a).  (The version
+                // that summed all na x na entries in predicated blocks of 8 was 37 % of the two-receiver kernel.)
+                const int nsym = accH ? P.nsym : 0;
+                for (int wk = tid; wk < P.npair * nsym; wk += NLPF_NT) {
+                    const int pr = wk / nsym;
+                    const int se = P.sym_tab[wk - pr * nsym];
+                    const int a = se & 255, b0 = se >> 8;
                     const int pe = P.ptab[pr];
                     const int j = pe & 255, l = pe >> 8;
-                    double acc[NLPF_NA_MAX];
-#pragma unroll
-                    for (int b = 0; b < NLPF_NA_MAX; ++b) acc[b] = 0.0;
-                    for (int el = 0; el < ne; ++el) {
-                        const double* ph = Phi + (c0 + el) * K;
-                        const double pp = ph[j] * ph[l];
-                        const double* Ga = G + (el * nat + a) * nat + b0;
-#pragma unroll
-                        for (int b = 0; b < NLPF_NA_MAX; ++b)
-                            if (b0 + b < na) acc[b] = fma(pp, Ga[b], acc[b]);
+                    double acc[4] = {0.0, 0.0, 0.0, 0.0};
+                    const double* ph = Phi + c0 * K;
+                    const double* Ga = G + a * nat + b0;
+                    const int nb4 = (a - b0 + 1 < 4) ? a - b0 + 1 : 4;
+                    if (nb4 == 4) {
+                        for (int el = 0; el < ne; ++el) {
+                            const double pp = ph[j] * ph[l];
+                            acc[0] = fma(pp, Ga[0], acc[0]);
+                            acc[1] = fma(pp, Ga[1], acc[1]);
+                            acc[2] = fma(pp, Ga[2], acc[2]);
+                            acc[3] = fma(pp, Ga[3], acc[3]);
+                            ph += K;
+                            Ga += nat * nat;
+                        }
+                    } else {
+                        for (int el = 0; el < ne; ++el) {
+                            const double pp = ph[j] * ph[l];
+                            acc[0] = fma(pp, Ga[0], acc[0]);
+                            if (nb4 > 1) acc[1] = fma(pp, Ga[1], acc[1]);
+                            if (nb4 > 2) acc[2] = fma(pp, Ga[2], acc[2]);
+                            ph += K;
+                            Ga += nat * nat;
+                        }
                     }
-                    const int r = j * nv + P.act[a];
+                    const int ca = P.act[a];
 #pragma unroll
-                    for (int b = 0; b < NLPF_NA_MAX; ++b) {
-                        if (b0 + b < na) {
-                            const int c = l * nv + P.act[b0 + b];
-                            if (c <= r) Hp[pk(r, c)] += acc[b];
+                    for (int q = 0; q < 4; ++q) {
+                        if (q < nb4) {
+                            const int cb = P.act[b0 + q];
+                            const int r1 = j * nv + ca, k1 = l * nv + cb;       // (a,b)
+                            const int r2 = j * nv + cb, k2 = l * nv + ca;       // its mirror (b,a)
+                            if (k1 <= r1) Hp[pk(r1, k1)] += acc[q];
+                            if (b0 + q != a && k2 <= r2 && !(j == l && k1 <= r1)) Hp[pk(r2, k2)] += acc[q];
                         }
                     }
                 }
@@ -994,6 +1013,8 @@ __device__ bool ldl_solve(const DevProb& P, int nz, double* Hp, double* xs) {
             double li[4];
 #pragma unroll
             for (int c = 0; c < 4; ++c) li[c] = (c < pw) ? Hi[j0 + c] * rd[c] : 0.0;
+            // (a two-columns-per-step version with the loads hoisted above the stores was 5-7 % SLOWER here: the
+            // 64-register cap turns the extra live values into spills; the warp kernel has the tiled version)
             for (int k = k0; k <= kend; ++k) {
                 const double* Hk = Hp + ((k * (k + 1)) >> 1) + j0;
                 double v = Hi[k];
