@@ -597,8 +597,13 @@ __device__ __forceinline__ bool ws_ldl(const uint16_t* __restrict__ ttab, const 
 #pragma unroll
             for (int r = c + 1; r < 4; ++r) l[r][c] = a[r][c] * rd[c];
         }
-        const double dmin = fmin(fmin(d[0], d[1]), fmin(d[2], d[3])), dmax = fmax(fmax(d[0], d[1]), fmax(d[2], d[3]));
-        if (!(dmin > 0.0) || !(dmax < INFINITY)) { ok = false; break; }
+        // pivots must be positive and finite: 1/d computed by frcp is positive and finite exactly then (d <= 0, NaN,
+        // +inf and subnormal d all give a non-positive or NaN reciprocal after the Newton steps); four compares instead of the
+        // fmin/fmax tree, which was 6 % of the kernel's instructions
+        if (!((rd[0] > 0.0) & (rd[1] > 0.0) & (rd[2] > 0.0) & (rd[3] > 0.0))) {
+            ok = false;
+            break;
+        }
         const int j1 = j0 + pw;
         for (int i = j1 + lane; i <= NZ; i += 32) {
             double* Hi = Hp + pk(i, j0);
