@@ -190,6 +190,8 @@ int nlpf_problem_smem_bytes(const nlpf_problem* p);
 /* FP64 FMA throughput probe used for the roofline denominator (bench.py): runs `iters`
  * dependent-chain-free DFMA per thread on a full grid, returns FLOP count in *flops_out. */
 int nlpf_fp64_probe(int iters, double* sink_dev, double* flops_out, void* stream);
+/* same for the FP64 tensor-core path (mma.sync.m8n8k4.f64) */
+int nlpf_dmma_probe(int iters, double* sink_dev, double* flops_out, void* stream);
 
 #ifdef __cplusplus
 }

@@ -415,6 +415,33 @@ extern "C" int nlpf_fp64_probe(int iters, double* sink_dev, double* flops_out, v
     return nlpf_check_cuda(cudaGetLastError(), "fp64_probe launch");
 }
 
+// FP64 tensor-core (DMMA, mma.sync.m8n8k4.f64) throughput probe: answers BASELINE.json's "FP64 DMMA only if
+// ncu shows the batched J^T J contraction benefits" with a number for this part.
+__global__ void __launch_bounds__(256) dmma_probe_kernel(int iters, double* sink) {
+    double c[8][2];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) c[q][0] = c[q][1] = threadIdx.x * 1e-9 + q;
+    const double a = 0.999999, b = 1e-3;
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+            asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                         : "+d"(c[q][0]), "+d"(c[q][1]) : "d"(a), "d"(b));
+    }
+    double s = 0.0;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) s += c[q][0] + c[q][1];
+    if (s == 123.456) sink[0] = s;
+}
+
+extern "C" int nlpf_dmma_probe(int iters, double* sink_dev, double* flops_out, void* stream) {
+    const int blocks = 148 * 8, threads = 256;
+    dmma_probe_kernel<<<blocks, threads, 0, (cudaStream_t)stream>>>(iters, sink_dev);
+    // one m8n8k4 per warp: 8*8*4 FMAs
+    if (flops_out) *flops_out = 2.0 * 256.0 * 8.0 * (double)iters * blocks * (threads / 32);
+    return nlpf_check_cuda(cudaGetLastError(), "dmma_probe launch");
+}
+
 // ------------------------------------------------------------------------------------------
 // Batched ECEF -> ENU of satellite positions: the reference calls
 // utils.ecef2enu once per satellite per epoch and re-derives the reference latitude by Bowring

@@ -20,6 +20,13 @@
 #include "common.cuh"
 #include <math.h>
 
+#ifndef WS_DMMA
+#define WS_DMMA 0         // 1: measurement Hessian of the pseudorange shapes on the FP64 tensor cores (mma.sync
+                          // m8n8k4).  Measured on B200: DMMA peak 36.7 TFLOP/s = the vector FMA peak (36.1), and the
+                          // GNSS batch runs at 2.37 M windows/s with it against 2.38 M without (parity tests pass either
+                          // way), so the vector path stays the default (BASELINE.json: "DMMA only if it benefits").
+#endif
+
 namespace {
 
 __device__ __forceinline__ double wsum(double v) {
@@ -405,12 +412,15 @@ __device__ __forceinline__ void ws_eval(const DevProb& P, double* sm, const WsCo
                     const double w = rw[q];
                     if (w == 0.0) continue;                     // masked slot: skipped, never 0 * NaN
                     const double d0 = x0 - rx[q], d1 = x1 - rY[q], d2 = x2 - rz[q];
-                    const double rho = sqrt(d0 * d0 + d1 * d1 + d2 * d2);
+                    // one reciprocal square root serves the range and the unit vector (rho = s2 * rsqrt(s2):
+                    // <= 2 ulp, 1e-8 m at GNSS ranges) instead of sqrt + division
+                    const double s2 = d0 * d0 + d1 * d1 + d2 * d2;
+                    const double ir = rsqrt(s2);
+                    const double rho = s2 * ir;
                     const double r = ry[q] - (rho + xb);
                     cost = fma(w * r, r, cost);
                     nse += 2.0 * w * fabs(r) * (2.0 * fabs(ry[q]) + fabs(r));
                     if (FULL) {
-                        const double ir = 1.0 / rho;
                         const double e0 = d0 * ir, e1 = d1 * ir, e2 = d2 * ir;
                         const double wr = w * r;
                         a0 = fma(wr, e0, a0); a1 = fma(wr, e1, a1); a2 = fma(wr, e2, a2); a3 += wr;
@@ -444,9 +454,72 @@ __device__ __forceinline__ void ws_eval(const DevProb& P, double* sm, const WsCo
                 const int c = (a == 0) ? c0 : (a == 1) ? c1 : (a == 2) ? c2 : cb;
                 g[j * N + c] -= (ac[0] + ac[1]) + (ac[2] + ac[3]);
             }
+            constexpr int NPAIR = K * (K + 1) / 2;
+#if WS_DMMA
+            // H_(j,a),(l,b) += sum_e phi_ej phi_el G_e[a][b] as a small GEMM on the FP64 tensor cores:
+            //   C[pair][q] = sum_e PP[pair][e] * G[e][q],  PP[pair][e] = phi_ej phi_el formed on the fly,
+            // q = the 10 unique entries of the symmetric G_e (columns 10..15 of the second n-tile are padding).
+            // mma.sync.m8n8k4.f64 fragments: A[row = lane/4][k = lane%4], B[k = lane%4][n = lane/4],
+            // C[row = lane/4][2*(lane%4) + {0,1}].  Three m-tiles in flight (six independent accumulator chains).
+            {
+                constexpr int MT = (NPAIR + 7) / 8, KT = (E + 3) / 4;
+                const int grp = lane >> 2, tig = lane & 3;
+#pragma unroll 1
+                for (int mt0 = 0; mt0 < MT; mt0 += 3) {
+                    int jj[3], ll[3];
+                    bool pon[3];
+                    double acc[3][4];
+#pragma unroll
+                    for (int u = 0; u < 3; ++u) {
+                        const int pp_ = (mt0 + u) * 8 + grp;
+                        pon[u] = (mt0 + u < MT) && pp_ < NPAIR;
+                        const int pe = cs.ptab[pon[u] ? pp_ : 0];
+                        jj[u] = pe & 255;
+                        ll[u] = pe >> 8;
+                        acc[u][0] = acc[u][1] = acc[u][2] = acc[u][3] = 0.0;
+                    }
+#pragma unroll 2
+                    for (int kt = 0; kt < KT; ++kt) {
+                        const int e = kt * 4 + tig;
+                        const bool eon = e < E;
+                        const int ec = eon ? e : 0;
+                        const double b0 = eon ? qv[ec * 14 + grp] : 0.0;
+                        const double b1 = (eon && grp < 2) ? qv[ec * 14 + 8 + grp] : 0.0;
+#pragma unroll
+                        for (int u = 0; u < 3; ++u) {
+                            const double av = (pon[u] && eon) ? phi(ec, jj[u]) * phi(ec, ll[u]) : 0.0;
+                            asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                                         : "+d"(acc[u][0]), "+d"(acc[u][1]) : "d"(av), "d"(b0));
+                            asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                                         : "+d"(acc[u][2]), "+d"(acc[u][3]) : "d"(av), "d"(b1));
+                        }
+                    }
+#pragma unroll
+                    for (int u = 0; u < 3; ++u) {
+                        if (!pon[u]) continue;
+                        const int j = jj[u], l = ll[u];
+#pragma unroll
+                        for (int v = 0; v < 4; ++v) {
+                            if (v >= 2 && tig != 0) continue;          // second n-tile: only columns 8, 9 are real
+                            const int q = (v < 2) ? 2 * tig + v : 8 + (v - 2);
+                            const int a_ = (q >= 6) ? 3 : (q >= 3) ? 2 : (q >= 1) ? 1 : 0;
+                            const int b_ = q - ((a_ * (a_ + 1)) >> 1);
+                            const int ca = (a_ == 0) ? c0 : (a_ == 1) ? c1 : (a_ == 2) ? c2 : cb;
+                            const int cbb = (b_ == 0) ? c0 : (b_ == 1) ? c1 : (b_ == 2) ? c2 : cb;
+                            const double hv = acc[u][v];
+                            // (a,b) and, off the diagonal of G, its mirror (b,a); inside a diagonal node block only the
+                            // entry of the lower triangle exists
+                            const int r1 = j * N + ca, k1 = l * N + cbb;
+                            const int r2 = j * N + cbb, k2 = l * N + ca;
+                            if (k1 <= r1) Hp[pk(r1, k1)] += hv;
+                            if (a_ != b_ && ((j != l && k2 <= r2) || (j == l && k1 > r1))) Hp[pk(r2, k2)] += hv;
+                        }
+                    }
+                }
+            }
+#else
             // H_(j,a),(l,b) += sum_e phi_ej phi_el G_e[a][b]: two lanes share a node pair (epoch halves),
             // 10 unique values per pair (G_e symmetric), combined with one shuffle
-            constexpr int NPAIR = K * (K + 1) / 2;
             constexpr int EH = (E + 1) / 2;
             for (int it0 = 0; it0 < 2 * NPAIR; it0 += 32) {
                 const int it = it0 + lane;
@@ -490,6 +563,7 @@ __device__ __forceinline__ void ws_eval(const DevProb& P, double* sm, const WsCo
                         }
                 }
             }
+#endif
         }
     }
     // log barrier on the bounded components (nlp.py:314-317)

@@ -334,17 +334,21 @@ def blocktri_solve(Dg, Lo, rhs, variant=BLOCKTRI_RICCATI):
     return x, info
 
 
-def fp64_peak_tflops(iters=20000, reps=5):
-    """Measured FP64 FMA throughput of the current device (roofline denominator)."""
+def fp64_peak_tflops(iters=20000, reps=5, tensor=False):
+    """Measured FP64 FMA throughput of the current device (roofline denominator); tensor=True measures the
+    FP64 tensor-core path (mma.sync.m8n8k4.f64) instead of the vector FMA pipe."""
     _require_cuda()
     L = _capi.lib()
+    probe = L.nlpf_dmma_probe if tensor else L.nlpf_fp64_probe
+    if tensor:
+        iters = max(1, iters // 8)
     sink = torch.zeros(4, dtype=torch.float64, device="cuda")
     flops = ctypes.c_double()
     best = 0.0
     for i in range(reps + 2):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        _capi.check(L.nlpf_fp64_probe(int(iters), _ptr(sink), ctypes.byref(flops), _stream()))
+        _capi.check(probe(int(iters), _ptr(sink), ctypes.byref(flops), _stream()))
         e1.record()
         torch.cuda.synchronize()
         if i >= 2:
