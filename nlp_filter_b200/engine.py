@@ -136,12 +136,12 @@ class HostBatch(object):
         d = prob.desc
         self.prob, self.B = prob, B
         if nchunk is None:
-            # chunk only when the copies are comparable to the solve: GNSS windows carry 25 KB of records
-            # (103 MB per 4096 windows: 4 chunks); a van der Pol window 2 KB (one launch fills the GPU better
-            # than four quarter-size ones).  NLPF_E2E_CHUNKS overrides.
+            # measured on B200 (4096 windows, e2e windows/s by chunk count): van der Pol (2 KB per window,
+            # solve-bound) 1: 3.07 M, 2: 3.61 M, 3: 3.74 M, 4: 3.57 M;  GNSS (25 KB of records per window,
+            # PCIe-bound: 103 MB per step) 2: 1.41 M, 4: 1.31-1.54 M, 8: 1.55 M.  NLPF_E2E_CHUNKS overrides.
             env = os.environ.get("NLPF_E2E_CHUNKS")
             in_bytes = 8 * B * (d.nz + d.K * d.m + max(d.Ldata, 1) + d.n)
-            nchunk = int(env) if env else (4 if (B >= 1024 and in_bytes >= (32 << 20)) else 1)
+            nchunk = int(env) if env else (1 if B < 1024 else (8 if in_bytes >= (32 << 20) else 3))
         self.nchunk = max(1, min(int(nchunk), B))
         cuts = [(B * c) // self.nchunk for c in range(self.nchunk + 1)]
         self.chunks = [(cuts[c], cuts[c + 1]) for c in range(self.nchunk)]
