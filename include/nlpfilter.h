@@ -184,6 +184,18 @@ int nlpf_blocktri_solve(int B, int nblk, int bs, const double* Dg, const double*
 int nlpf_ecef2enu(long long n, const double* p_ecef, const double* R9_host, const double* ref3_host, int rotation_only,
                   double* out, void* stream);
 
+/* Receding-horizon chains of B independent runs in ONE launch (batch form of the window loop of
+ * autonomous-car.py:232-288): for w = 0..W-1 solve window w of every run from the previous window's solution,
+ * then centre the next arrival cost on that solution sampled at t = DT (phiDT[K], device).  U_all[W][B][K][m],
+ * data_all[W][B][Ldata]; z[B][nz] and xprior[B][n] are updated in place; iters_sum_out[B] total iterations,
+ * bad_out[B] number of windows that did not converge; Z_out[W][B][nz] every window's estimate, or NULL.
+ * Only for problem classes with a warp-per-window kernel and an arrival cost (nlpf_problem_has_chain_kernel);
+ * NLPF_E_ARG otherwise (loop nlpf_solve + nlpf_sample on the host instead). */
+int nlpf_problem_has_chain_kernel(const nlpf_problem* p);
+int nlpf_solve_chain(nlpf_problem* p, int B, int W, double* z, const double* U_all, const double* data_all, double* xprior,
+                     const double* phiDT, const nlpf_opts* opts, double* cost_out, int* iters_sum_out, int* bad_out,
+                     double* Z_out, void* stream);
+
 /* shared memory (bytes) one window of this problem class needs in the whole-solve kernel */
 int nlpf_problem_smem_bytes(const nlpf_problem* p);
 

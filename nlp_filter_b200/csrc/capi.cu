@@ -38,8 +38,8 @@ extern "C" int nlpf_launch_solve_pr(nlpf_problem*, int, double*, const double*, 
 extern "C" int nlpf_launch_sample(nlpf_problem*, int, const double*, int, const double*, double*, cudaStream_t);
 extern "C" int nlpf_ws_variant(int K, int N, int M, int E, int NM, int dyn, int meas, int nb, int prior, int loss);
 extern "C" int nlpf_ws_launch(int variant, nlpf_problem* p, int B, double* z, const double* U, const double* data,
-                              const double* xprior, const nlpf_opts* o, double* cost_out, int* iters_out, int* status_out,
-                              double* hlin, int* counter, cudaStream_t st);
+                              double* xprior, const nlpf_opts* o, double* cost_out, int* iters_out, int* status_out,
+                              double* hlin, int* counter, int W, const double* phiDT, double* Zout, cudaStream_t st);
 extern "C" int nlpf_set_smem_attrs_gen(size_t bytes);
 extern "C" int nlpf_set_smem_attrs_pr(size_t bytes);
 
@@ -473,25 +473,50 @@ extern "C" int nlpf_factor_solve(nlpf_problem* p, int B, const double* H, const 
     return nlpf_launch_factor_solve(p, B, H, g, lam, dz_out, info_out, (cudaStream_t)stream);
 }
 
+// warp-per-window kernel (its own constant-H cache and work counter); W > 1 / phiDT: fused receding-horizon chains
+static bool ws_eligible(const nlpf_problem* p, const double* U, const double* xprior, const double* wshift) {
+    return p->ws_variant >= 0 && !wshift && (p->d.m == 0 || U) && (!p->d.has_prior || xprior);
+}
+
+static int ws_dispatch(nlpf_problem* p, int B, double* z, const double* U, const double* data, double* xprior,
+                       const nlpf_opts* opts, double* cost_out, int* iters_out, int* status_out, int W,
+                       const double* phiDT, double* Zout, cudaStream_t stream) {
+    const int nzp = p->d.nz;
+    const size_t need = p->d.lin_meas ? (size_t)B * (2 * ((nzp + 1) >> 1) * ((nzp + 2) >> 1)) : 0;   // padded packed rows
+    if (need > p->scratch_doubles) {
+        if (p->scratch) { cudaStreamSynchronize(stream); cudaFree(p->scratch); p->scratch = nullptr; p->scratch_doubles = 0; }
+        if (nlpf_check_cuda(cudaMalloc((void**)&p->scratch, need * sizeof(double)), "cudaMalloc(constant-H cache)")) return NLPF_E_CUDA;
+        p->scratch_doubles = need;
+    }
+    if (!p->counter && nlpf_check_cuda(cudaMalloc((void**)&p->counter, sizeof(int)), "cudaMalloc(work counter)")) return NLPF_E_CUDA;
+    return nlpf_ws_launch(p->ws_variant, p, B, z, U, data, xprior, opts, cost_out, iters_out, status_out, p->scratch,
+                          p->counter, W, phiDT, Zout, stream);
+}
+
+extern "C" int nlpf_problem_has_chain_kernel(const nlpf_problem* p) { return (p && p->ws_variant >= 0 && p->d.has_prior) ? 1 : 0; }
+
+extern "C" int nlpf_solve_chain(nlpf_problem* p, int B, int W, double* z, const double* U_all, const double* data_all,
+                                double* xprior, const double* phiDT, const nlpf_opts* opts, double* cost_out,
+                                int* iters_sum_out, int* bad_out, double* Z_out, void* stream) {
+    int rc = check_batch(p, B, z, data_all);
+    if (rc) return rc;
+    if (W < 1 || !xprior || !phiDT || !opts || !cost_out || !iters_sum_out || !bad_out) { nlpf_set_error("bad chain argument"); return NLPF_E_ARG; }
+    if (!p->d.has_prior || !ws_eligible(p, U_all, xprior, nullptr)) {
+        nlpf_set_error("no fused chain kernel for this problem class (loop nlpf_solve + nlpf_sample instead)");
+        return NLPF_E_ARG;
+    }
+    return ws_dispatch(p, B, z, U_all, data_all, xprior, opts, cost_out, iters_sum_out, bad_out, W, phiDT, Z_out, (cudaStream_t)stream);
+}
+
 extern "C" int nlpf_solve(nlpf_problem* p, int B, double* z, const double* U, const double* data, const double* xprior,
                           const double* wshift, const nlpf_opts* opts, double* cost_out, int* iters_out,
                           int* status_out, void* stream) {
     int rc = check_batch(p, B, z, data);
     if (rc) return rc;
     if (!opts || !cost_out || !iters_out || !status_out) { nlpf_set_error("null opts/output buffer"); return NLPF_E_ARG; }
-    if (p->ws_variant >= 0 && !wshift && (p->d.m == 0 || U) && (!p->d.has_prior || xprior)) {
-        // small linear-measurement class: warp-per-window kernel (its own constant-H cache and work counter)
-        const int nzp = p->d.nz;
-        const size_t need = p->d.lin_meas ? (size_t)B * (2 * ((nzp + 1) >> 1) * ((nzp + 2) >> 1)) : 0;   // padded packed rows
-        if (need > p->scratch_doubles) {
-            if (p->scratch) { cudaStreamSynchronize((cudaStream_t)stream); cudaFree(p->scratch); p->scratch = nullptr; p->scratch_doubles = 0; }
-            if (nlpf_check_cuda(cudaMalloc((void**)&p->scratch, need * sizeof(double)), "cudaMalloc(constant-H cache)")) return NLPF_E_CUDA;
-            p->scratch_doubles = need;
-        }
-        if (!p->counter && nlpf_check_cuda(cudaMalloc((void**)&p->counter, sizeof(int)), "cudaMalloc(work counter)")) return NLPF_E_CUDA;
-        return nlpf_ws_launch(p->ws_variant, p, B, z, U, data, xprior, opts, cost_out, iters_out, status_out, p->scratch,
-                              p->counter, (cudaStream_t)stream);
-    }
+    if (ws_eligible(p, U, xprior, wshift))
+        return ws_dispatch(p, B, z, U, data, const_cast<double*>(xprior), opts, cost_out, iters_out, status_out, 1, nullptr, nullptr,
+                           (cudaStream_t)stream);
     double* hlin = nullptr;
     if (p->d.lin_meas) {        // per-window constant-H cache (not shared between concurrent calls on one handle)
         const size_t need = (size_t)B * p->d.np;

@@ -193,6 +193,13 @@ struct WsConst {
     int c[4];                // MEAS 0: component of slot s (s < NM <= 4);  MEAS 1: (c0, c1, c2 | cb)
 };
 
+// receding-horizon chain arguments of the kernel (W = 1, null pointers: plain batch)
+struct WsChain {
+    int W;                   // windows per run; U and data are [W][B][...]
+    const double* phiDT;     // K: basis at t = DT (device)
+    double* Zout;            // [W][B][NZ] every window's estimate, or null
+};
+
 // objective J, merit = J/2 + barrier, first-order rounding bound of the merit and (FULL) H (packed,
 // shared memory), g.  merit = +inf flags an iterate outside the bounds or a non-finite objective.
 template <class C, bool FULL>
@@ -794,9 +801,9 @@ __device__ __forceinline__ bool ws_ldl(const uint16_t* __restrict__ ttab, const 
 template <class C>
 __global__ void __launch_bounds__(C::WARPS * 32, WsLayout<C>::CTAS)
 wsolve_kernel(const __grid_constant__ DevProb P, int B, double* __restrict__ z_io, const double* __restrict__ U,
-              const double* __restrict__ data, const double* __restrict__ xprior, nlpf_opts opt,
+              const double* __restrict__ data, double* xprior, nlpf_opts opt,
               double* __restrict__ cost_out, int* __restrict__ iters_out, int* __restrict__ status_out,
-              double* __restrict__ hlin_all, int* __restrict__ counter) {
+              double* __restrict__ hlin_all, int* __restrict__ counter, WsChain ch) {
     typedef WsLayout<C> L;
     constexpr int K = C::K, N = C::N, M = C::M, E = C::E, NM = C::NM;
     constexpr int NZ = L::NZ;
@@ -839,11 +846,18 @@ wsolve_kernel(const __grid_constant__ DevProb P, int B, double* __restrict__ z_i
         if (lane == 0) b = atomicAdd(counter, 1);
         b = __shfl_sync(0xffffffffu, b, 0);
         if (b >= B) break;
-        const double* Ug = U + (size_t)b * K * (M > 0 ? M : 1);
-        const double* dg = data + (size_t)b * P.Ldata;
         const double* xp = C::PRIOR ? xprior + (size_t)b * N : nullptr;
-        const double* hlin = P.Hcp;
         for (int i = lane; i < NZ; i += 32) zs[i] = z_io[(size_t)b * NZ + i];
+        // receding-horizon chain (autonomous-car.py:232-288): the W windows of run b back to back in this warp --
+        // warm start from the previous solution, arrival cost re-centred on x(DT) -- so no run waits at a
+        // per-window launch boundary for the slowest window of the batch.  W = 1: a plain batch of windows.
+        int it_sum = 0, nbad = 0, it_last = 0, st_last = NLPF_ST_MAXITER;
+        double J_last = 0.0;
+#pragma unroll 1
+        for (int w = 0; w < ch.W; ++w) {
+        const double* Ug = U + ((size_t)w * B + b) * K * (M > 0 ? M : 1);
+        const double* dg = data + ((size_t)w * B + b) * P.Ldata;
+        const double* hlin = P.Hcp;
         if (C::MEAS == 0) {
             // constant H of this window: Hc + sum_e (phi_e phi_e^T) (x) diag(w_e), kept in an L2-resident cache
             double* hl = hlin_all + (size_t)b * L::NP;
@@ -1026,20 +1040,39 @@ wsolve_kernel(const __grid_constant__ DevProb P, int B, double* __restrict__ z_i
             }
             if (finished) break;
         }
+        J_last = J;
+        it_last = iters;
+        st_last = status;
+        it_sum += iters;
+        nbad += (status > NLPF_ST_STALLED) ? 1 : 0;
+        if (ch.Zout) {
+            for (int i = lane; i < NZ; i += 32) ch.Zout[((size_t)w * B + b) * NZ + i] = zs[i];
+        }
+        if (ch.phiDT) {      // next arrival cost: x(DT) = sum_j phi_j(DT) X_j
+            __syncwarp();
+            for (int i = lane; i < N; i += 32) {
+                double sx = 0.0;
+#pragma unroll
+                for (int j = 0; j < K; ++j) sx = fma(ch.phiDT[j], zs[j * N + i], sx);
+                xprior[(size_t)b * N + i] = sx;
+            }
+            __syncwarp();
+        }
+        }   // windows of the chain
         for (int i = lane; i < NZ; i += 32) z_io[(size_t)b * NZ + i] = zs[i];
         if (lane == 0) {
-            cost_out[b] = J;
-            iters_out[b] = iters;
-            status_out[b] = status;
+            cost_out[b] = J_last;
+            iters_out[b] = ch.phiDT ? it_sum : it_last;          // chain: total iterations, windows not converged
+            status_out[b] = ch.phiDT ? nbad : st_last;
         }
         __syncwarp();
     }
 }
 
 template <class C>
-int ws_launch(nlpf_problem* p, int B, double* z, const double* U, const double* data, const double* xprior,
+int ws_launch(nlpf_problem* p, int B, double* z, const double* U, const double* data, double* xprior,
               const nlpf_opts* o, double* cost_out, int* iters_out, int* status_out, double* hlin, int* counter,
-              cudaStream_t st) {
+              WsChain ch, cudaStream_t st) {
     typedef WsLayout<C> L;
     auto kern = wsolve_kernel<C>;
     const size_t smem = sizeof(double) * L::TOTAL;
@@ -1053,7 +1086,7 @@ int ws_launch(nlpf_problem* p, int B, double* z, const double* U, const double* 
     int grid = 148 * L::CTAS;
     const int need = (B + C::WARPS - 1) / C::WARPS;
     if (grid > need) grid = need;
-    kern<<<grid, C::WARPS * 32, smem, st>>>(p->d, B, z, U, data, xprior, *o, cost_out, iters_out, status_out, hlin, counter);
+    kern<<<grid, C::WARPS * 32, smem, st>>>(p->d, B, z, U, data, xprior, *o, cost_out, iters_out, status_out, hlin, counter, ch);
     return nlpf_check_cuda(cudaGetLastError(), "wsolve_kernel launch");
 }
 
@@ -1086,14 +1119,18 @@ extern "C" int nlpf_ws_variant(int K, int N, int M, int E, int NM, int dyn, int 
 }
 
 extern "C" int nlpf_ws_launch(int variant, nlpf_problem* p, int B, double* z, const double* U, const double* data,
-                              const double* xprior, const nlpf_opts* o, double* cost_out, int* iters_out, int* status_out,
-                              double* hlin, int* counter, cudaStream_t st) {
+                              double* xprior, const nlpf_opts* o, double* cost_out, int* iters_out, int* status_out,
+                              double* hlin, int* counter, int W, const double* phiDT, double* Zout, cudaStream_t st) {
+    WsChain ch;
+    ch.W = W;
+    ch.phiDT = phiDT;
+    ch.Zout = Zout;
     switch (variant) {
-        case 0: return ws_launch<CfgVdp>(p, B, z, U, data, xprior, o, cost_out, iters_out, status_out, hlin, counter, st);
-        case 1: return ws_launch<CfgExample>(p, B, z, U, data, xprior, o, cost_out, iters_out, status_out, hlin, counter, st);
-        case 2: return ws_launch<CfgGnss>(p, B, z, U, data, xprior, o, cost_out, iters_out, status_out, hlin, counter, st);
-        case 3: return ws_launch<CfgCar>(p, B, z, U, data, xprior, o, cost_out, iters_out, status_out, hlin, counter, st);
-        case 4: return ws_launch<CfgCarHuber>(p, B, z, U, data, xprior, o, cost_out, iters_out, status_out, hlin, counter, st);
+        case 0: return ws_launch<CfgVdp>(p, B, z, U, data, xprior, o, cost_out, iters_out, status_out, hlin, counter, ch, st);
+        case 1: return ws_launch<CfgExample>(p, B, z, U, data, xprior, o, cost_out, iters_out, status_out, hlin, counter, ch, st);
+        case 2: return ws_launch<CfgGnss>(p, B, z, U, data, xprior, o, cost_out, iters_out, status_out, hlin, counter, ch, st);
+        case 3: return ws_launch<CfgCar>(p, B, z, U, data, xprior, o, cost_out, iters_out, status_out, hlin, counter, ch, st);
+        case 4: return ws_launch<CfgCarHuber>(p, B, z, U, data, xprior, o, cost_out, iters_out, status_out, hlin, counter, ch, st);
     }
     nlpf_set_error("unknown warp-solve variant %d", variant);
     return NLPF_E_ARG;

@@ -225,6 +225,20 @@ def solve_chain(prob, z, U_all, data_all, xprior, PhiDT, opts=None, keep=False):
     bad = torch.zeros((B,), dtype=torch.int64, device=z.device)
     Z = torch.empty((W, B, d.nz), dtype=torch.float64, device=z.device) if keep else None
     PhiDT = _f8(PhiDT, (-1, d.K))
+    fused = (os.environ.get("NLPF_CHAIN_LOOP") is None and prob._lib.nlpf_problem_has_chain_kernel(prob._h) == 1
+             and (d.m == 0 or U_all is not None) and z.is_contiguous() and data_all.is_contiguous()
+             and xprior.is_contiguous() and (U_all is None or U_all.is_contiguous()))
+    if fused:
+        # one launch: every run's W windows back to back in one warp (no per-window launch boundary where the
+        # whole batch waits for its slowest window)
+        copts = _capi.make_copts(opts or SolveOpts())
+        it32 = torch.empty((B,), dtype=torch.int32, device=z.device)
+        bad32 = torch.empty((B,), dtype=torch.int32, device=z.device)
+        _capi.check(prob._lib.nlpf_solve_chain(prob._h, B, W, _ptr(z), _ptr(U_all), _ptr(data_all), _ptr(xprior),
+                                               _ptr(PhiDT), ctypes.byref(copts), _ptr(cost), _ptr(it32), _ptr(bad32),
+                                               _ptr(Z), _stream()))
+        it_sum, bad = it32.to(torch.int64), bad32.to(torch.int64)
+        return (it_sum, bad, Z) if keep else (it_sum, bad)
     for w in range(W):
         prob.solve(z, None if U_all is None else U_all[w], data_all[w], xprior, None, opts, out=(cost, iters, status))
         xprior.copy_(prob.sample(z, PhiDT)[:, 0, :])

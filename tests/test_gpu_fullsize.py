@@ -5,6 +5,7 @@ the returned point; plus oracle parity on a random subset."""
 import numpy as np
 import pytest
 
+from nlp_filter_b200 import desc as D
 from nlp_filter_b200 import shapes, synth
 
 pytestmark = pytest.mark.gpu
@@ -129,3 +130,37 @@ def test_vehicle_chains_against_oracle_and_truth():
             assert np.max(np.abs(Vg[:, [0, 1, 8]] - Vo[:, [0, 1, 8]])) < 1e-3                  # positions within 1 mm
             assert np.max(np.abs(Vg - Vo) / (1 + np.abs(Vo))) < 1e-5
     prob.close()
+
+
+def test_fused_chain_kernel_equals_the_per_window_loop(monkeypatch):
+    """nlpf_solve_chain (every run's windows back to back in one warp) against the host loop of
+    nlpf_solve + nlpf_sample launches it replaces: same kernel code per window, so identical results."""
+    import torch
+    from nlp_filter_b200 import engine
+    for loss in (D.LOSS_L2, D.LOSS_HUBER):
+        d = shapes.car(loss=loss)
+        B, W = 96, 4
+        ch = synth.car_chain_batch(d, B, W, seed=23)
+        prob = engine.WindowProblem(d)
+        assert prob._lib.nlpf_problem_has_chain_kernel(prob._h) == 1
+        dev = lambda a: torch.as_tensor(np.ascontiguousarray(a)).cuda()
+        out = []
+        for loop in (False, True):
+            if loop:
+                monkeypatch.setenv("NLPF_CHAIN_LOOP", "1")
+            else:
+                monkeypatch.delenv("NLPF_CHAIN_LOOP", raising=False)
+            z = torch.zeros((B, d.nz), dtype=torch.float64, device="cuda")
+            xp = dev(ch["xhat0"])
+            it_sum, bad, Z = engine.solve_chain(prob, z, dev(ch["U"]), dev(ch["data"]), xp, ch["PhiDT"], keep=True)
+            torch.cuda.synchronize()
+            out.append((it_sum.cpu().numpy(), bad.cpu().numpy(), Z.cpu().numpy(), z.cpu().numpy(), xp.cpu().numpy()))
+        f, l = out
+        assert np.array_equal(f[0], l[0]) and np.array_equal(f[1], l[1])
+        assert np.array_equal(f[2], l[2]) and np.array_equal(f[3], l[3])
+        assert np.max(np.abs(f[4] - l[4])) <= 1e-12 * (1 + np.max(np.abs(l[4])))      # sampled by two different kernels
+        prob.close()
+    # a class without arrival cost has no chain kernel: the library says so instead of guessing
+    pv = engine.WindowProblem(shapes.vdp_mhe())
+    assert pv._lib.nlpf_problem_has_chain_kernel(pv._h) == 0
+    pv.close()
