@@ -410,11 +410,11 @@ def run_car(args):
             "e2e": {"value": units * args.steps / (ms_e2e * 1e-3), "unit": "windows/s",
                     "h2d_bytes_per_step": int(hU.numel() * 8 + hdata.numel() * 8), "d2h_bytes_per_step": int(h_out.numel() * 8),
                     "ms_per_step": ms_e2e / args.steps},
-            "gpu_launches": args.steps * W * 2,
-            "roofline": {"bound": "fp64", "kernel": "solve_kernel_pr", "achieved": achieved, "peak": peak_fp64, "unit": "TFLOP/s",
-                         "frac": achieved / peak_fp64, "traffic": None, "kernel_ms": ms_step / W,
-                         "peak_source": "FP64 FMA probe measured in this run",
-                         "note": "kernel_ms = step time / chained windows (solve + sample kernels per window)"},
+            "gpu_launches": args.steps * (W * 2 if os.environ.get("NLPF_CHAIN_LOOP") else 1),
+            "roofline": {"bound": "fp64", "kernel": "wsolve_kernel<CfgCar> (fused chain: all windows of a run in one warp, one launch per step)",
+                         "achieved": achieved, "peak": peak_fp64, "unit": "TFLOP/s",
+                         "frac": achieved / peak_fp64, "traffic": None, "kernel_ms": ms_step,
+                         "peak_source": "FP64 FMA probe measured in this run"},
             "clocks": clocks}
     if cpu_base is not None:
         line["cpu_baseline"] = cpu_base
