@@ -184,6 +184,12 @@ int nlpf_blocktri_solve(int B, int nblk, int bs, const double* Dg, const double*
 int nlpf_ecef2enu(long long n, const double* p_ecef, const double* R9_host, const double* ref3_host, int rotation_only,
                   double* out, void* stream);
 
+/* "Next" row: batched post-processing of estimates, local ENU -> ECEF -> geodetic.
+ * replaces: utils.enu2ecef + utils.ecef2lla per sample, utils/utils.py:87-104, 4-37 (autonomous-car.py:273-287).
+ * p_enu[n*3] device; lla_out[n*3] = [lat deg, lon deg, h m]; ecef_out[n*3] or NULL; R9_host / ref3_host as above. */
+int nlpf_enu2lla(long long n, const double* p_enu, const double* R9_host, const double* ref3_host, double* ecef_out,
+                 double* lla_out, void* stream);
+
 /* Receding-horizon chains of B independent runs in ONE launch (batch form of the window loop of
  * autonomous-car.py:232-288): for w = 0..W-1 solve window w of every run from the previous window's solution,
  * then centre the next arrival cost on that solution sampled at t = DT (phiDT[K], device).  U_all[W][B][K][m],

@@ -41,7 +41,7 @@ class COpts(ctypes.Structure):
 EXPORTS = ("nlpf_version", "nlpf_last_error", "nlpf_device_count", "nlpf_problem_create",
            "nlpf_problem_destroy", "nlpf_problem_nz", "nlpf_assemble", "nlpf_factor_solve", "nlpf_solve",
            "nlpf_sample", "nlpf_ekf_run", "nlpf_ls_solve", "nlpf_ls_vel", "nlpf_fp64_probe", "nlpf_dmma_probe", "nlpf_blocktri_solve",
-           "nlpf_problem_smem_bytes", "nlpf_ecef2enu", "nlpf_solve_chain",
+           "nlpf_problem_smem_bytes", "nlpf_ecef2enu", "nlpf_enu2lla", "nlpf_solve_chain",
            "nlpf_problem_has_chain_kernel")
 
 _lib = None
@@ -75,6 +75,7 @@ def lib():
     L.nlpf_blocktri_solve.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int, vp, vp, vp, vp, vp, ctypes.c_int, vp]
     L.nlpf_problem_has_chain_kernel.argtypes = [vp]
     L.nlpf_solve_chain.argtypes = [vp, ctypes.c_int, ctypes.c_int, vp, vp, vp, vp, vp, ctypes.POINTER(COpts), vp, vp, vp, vp, vp]
+    L.nlpf_enu2lla.argtypes = [ctypes.c_longlong, vp, c_double_p, c_double_p, vp, vp, vp]
     L.nlpf_ecef2enu.argtypes = [ctypes.c_longlong, vp, c_double_p, c_double_p, ctypes.c_int, vp, vp]
     L.nlpf_fp64_probe.argtypes = [ctypes.c_int, vp, ctypes.POINTER(ctypes.c_double), vp]
     L.nlpf_dmma_probe.argtypes = [ctypes.c_int, vp, ctypes.POINTER(ctypes.c_double), vp]

@@ -473,3 +473,57 @@ extern "C" int nlpf_ecef2enu(long long n, const double* p_ecef, const double* R9
                                                                   R[8], x0, y0, z0, out);
     return nlpf_check_cuda(cudaGetLastError(), "ecef2enu_kernel launch");
 }
+
+// Batched post-processing of the estimates: local ENU -> ECEF -> geodetic
+// [lat deg, lon deg, h m], the per-sample chain enu2ecef + ecef2lla of autonomous-car.py:273-287
+// (utils/utils.py:87-104, 4-37: WGS84, Bowring's iteration with the reference's stopping rule: at most 10
+// sweeps, |dlat| < 1e-6).  One thread per point; 72 B per point in + out (+24 B for the optional ECEF copy).
+__global__ void __launch_bounds__(256) enu2lla_kernel(size_t n, const double* __restrict__ p, double r00, double r01,
+                                                       double r02, double r10, double r11, double r12, double r20,
+                                                       double r21, double r22, double x0, double y0, double z0,
+                                                       double* __restrict__ ecef_out, double* __restrict__ lla_out) {
+    const double a = 6378137.0, f = 1.0 / 298.257223563;
+    const double e2 = 2.0 * f - f * f;
+    const double kk = e2 * (1.0 - f) / (1.0 - e2);
+    const double r2d = 57.29577951308232;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const double e = p[3 * i], nn = p[3 * i + 1], u = p[3 * i + 2];
+        const double x = r00 * e + r10 * nn + r20 * u + x0;          // R^T p + ref
+        const double y = r01 * e + r11 * nn + r21 * u + y0;
+        const double z = r02 * e + r12 * nn + r22 * u + z0;
+        if (ecef_out) { ecef_out[3 * i] = x; ecef_out[3 * i + 1] = y; ecef_out[3 * i + 2] = z; }
+        if (x == 0.0 && y == 0.0 && z == 0.0) {                      // utils.py:13-14
+            lla_out[3 * i] = lla_out[3 * i + 1] = lla_out[3 * i + 2] = nan("");
+            continue;
+        }
+        const double s = sqrt(x * x + y * y);
+        double sb, cb;
+        sincos(atan(z / ((1.0 - f) * s)), &sb, &cb);
+        double lat = atan((z + a * sb * sb * sb * kk) / (s - e2 * a * cb * cb * cb));
+        for (int it = 0; it < 10; ++it) {
+            const double prev = lat;
+            double sl, cl;
+            sincos(lat, &sl, &cl);
+            sincos(atan((1.0 - f) * sl / cl), &sb, &cb);
+            lat = atan((z + a * sb * sb * sb * kk) / (s - e2 * a * cb * cb * cb));
+            if (fabs(prev - lat) < 1e-6) break;
+        }
+        double sl, cl;
+        sincos(lat, &sl, &cl);
+        const double rn = a / sqrt(1.0 - e2 * sl * sl);
+        lla_out[3 * i] = lat * r2d;
+        lla_out[3 * i + 1] = atan2(y, x) * r2d;
+        lla_out[3 * i + 2] = s * cl + (z + e2 * rn * sl) * sl - rn;
+    }
+}
+
+extern "C" int nlpf_enu2lla(long long n, const double* p_enu, const double* R9_host, const double* ref3_host,
+                            double* ecef_out, double* lla_out, void* stream) {
+    if (n < 1 || !p_enu || !R9_host || !ref3_host || !lla_out) { nlpf_set_error("bad enu2lla argument"); return NLPF_E_ARG; }
+    const double* R = R9_host;
+    long long blocks = (n + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    enu2lla_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>((size_t)n, p_enu, R[0], R[1], R[2], R[3], R[4], R[5], R[6], R[7],
+                                                                 R[8], ref3_host[0], ref3_host[1], ref3_host[2], ecef_out, lla_out);
+    return nlpf_check_cuda(cudaGetLastError(), "enu2lla_kernel launch");
+}

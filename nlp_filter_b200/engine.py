@@ -331,6 +331,24 @@ def ecef2enu_batch(p_ecef, p_ref_ECEF, rotation_only=False):
     return out.reshape(shape)
 
 
+def enu2lla_batch(p_enu, p_ref_ECEF, want_ecef=False):
+    """[lat deg, lon deg, h m] (and optionally ECEF) of many local-ENU points in a single launch: the
+    enu2ecef + ecef2lla chain the reference applies per sample (utils/utils.py:87-104, 4-37)."""
+    _require_cuda()
+    from .utils.utils import _enu_rows
+    L = _capi.lib()
+    p = _f8(p_enu)
+    shape = p.shape
+    p = p.reshape(-1, 3).contiguous()
+    R = np.ascontiguousarray(_enu_rows(np.asarray(p_ref_ECEF, dtype=float)).reshape(-1))
+    ref = np.ascontiguousarray(np.asarray(p_ref_ECEF, dtype=float).reshape(3))
+    lla = torch.empty_like(p)
+    ecef = torch.empty_like(p) if want_ecef else None
+    _capi.check(L.nlpf_enu2lla(p.shape[0], _ptr(p), R.ctypes.data_as(_capi.c_double_p), ref.ctypes.data_as(_capi.c_double_p),
+                               _ptr(ecef), _ptr(lla), _stream()))
+    return (lla.reshape(shape), ecef.reshape(shape)) if want_ecef else lla.reshape(shape)
+
+
 BLOCKTRI_RICCATI = 0
 BLOCKTRI_CYCLIC = 1
 

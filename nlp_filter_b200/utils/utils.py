@@ -85,3 +85,10 @@ def ecef2enu_batch(p_ECEF, p_ref_ECEF, rotation_only=False):
     row of p_ECEF (N, 3) about one reference point.  Returns a NumPy array."""
     from .. import engine
     return engine.ecef2enu_batch(np.asarray(p_ECEF, dtype=float), p_ref_ECEF, rotation_only).cpu().numpy()
+
+
+def enu2lla_batch(p_ENU, p_ref_ECEF):
+    """Many points at once on the device (addition to the reference API): `ecef2lla(enu2ecef(p, ref))` for
+    every row of p_ENU (N, 3).  Returns a NumPy array of [lat deg, lon deg, h m] rows."""
+    from .. import engine
+    return engine.enu2lla_batch(np.asarray(p_ENU, dtype=float), p_ref_ECEF).cpu().numpy()

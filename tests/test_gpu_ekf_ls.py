@@ -127,3 +127,23 @@ def test_ecef2enu_batch_matches_reference_per_point(G):
     n = int(G["gs_nsat"][k])
     assert np.max(np.abs(out.reshape(51, 12, 3)[k, :n] - G["gs_sat_enu"][k, :n])) < 1e-7
     assert np.array_equal(utils.ecef2enu_batch(sats[:5], p_ref), out[:5])
+
+
+def test_enu2lla_batch_matches_reference_per_point(G):
+    """estimates ENU -> ECEF -> geodetic in one launch == enu2ecef + ecef2lla per sample."""
+    import utils.utils as utils
+    eng = _eng()
+    p_ref = G["p_ref_ECEF"]
+    rng = np.random.default_rng(5)
+    enu = rng.normal(size=(4096, 3)) * np.array([300.0, 300.0, 20.0])
+    enu[7] = utils.ecef2enu(np.zeros(3), p_ref)                       # maps back to the ECEF origin (to rounding)
+    lla, ecef = eng.enu2lla_batch(enu, p_ref, want_ecef=True)
+    lla, ecef = lla.cpu().numpy(), ecef.cpu().numpy()
+    for i in range(0, 4096, 41):
+        e = utils.enu2ecef(enu[i], p_ref)
+        ref = utils.ecef2lla(e)
+        assert np.max(np.abs(ecef[i] - e)) <= 1e-8                          # metres (6.4e6 m magnitudes: a few ulp)
+        assert abs(lla[i, 0] - ref[0]) <= 1e-12 and abs(lla[i, 1] - ref[1]) <= 1e-12   # degrees (1e-7 m)
+        assert abs(lla[i, 2] - ref[2]) <= 1e-8
+    assert np.all(np.isfinite(lla[np.arange(4096) != 7]))
+    assert np.array_equal(utils.enu2lla_batch(enu[:9], p_ref), lla[:9])
