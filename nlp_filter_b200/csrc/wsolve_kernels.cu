@@ -159,16 +159,23 @@ struct WsLayout {
     static constexpr int oG = oZT + ev(NZ);
     static constexpr int oDZ = oG + ev(NZ);
     static constexpr int oDS = oDZ + ev(NZ);
-    static constexpr int oDD = oDS + ev(NZ);
-    static constexpr int oLW = oDD + ev(NZ);
-    static constexpr int oFB = oLW + ev(NZ);
-    static constexpr int oWH = oFB + ev(NZ);
+    // Vectors that are never live together share storage (shared memory per window is what limits residency):
+    //  * dd (Gauss-Newton diagonal) = ds (diagonal of H) when H has no second-order or barrier part;
+    //  * lw (weighted defects: written and read inside the evaluation) = dz (the step: written by the
+    //    factorisation, consumed before the next evaluation);
+    //  * fb (node dynamics: dead after the defect phase) = the head of Q (written by the measurement phase).
+    static constexpr bool ALIAS_DS = C::HCONST && C::NB == 0;
+    static constexpr int oDD = ALIAS_DS ? oDS : oDS + ev(NZ);
+    static constexpr int oLW = oDZ;
+    static constexpr int oWH = oDD + ev(NZ);
     static constexpr int oF = oWH + ev(C::LOSS == NLPF_LOSS_HUBER ? NZ : 0);
     static constexpr int NBLK = C::HCONST ? 0 : K * N * N;       // per-node Jacobians only for nonlinear models
     static constexpr int oQ = oF + ev(NBLK);
+    static constexpr int oFB = oQ;
     static constexpr int NQ = (C::MEAS == 0) ? NR : E * 14;      // w*r per residual, or [G_e (10) | q_e (4)] per epoch
     static constexpr int NFQ = (ev(NBLK) + ev(NQ) > 4 * LDW) ? ev(NBLK) + ev(NQ) : 4 * LDW;   // F | Q, reused by the LDL
     static constexpr int PER_WARP = oF + NFQ;
+    static_assert(NQ >= NZ, "fb shares the head of Q");
     static constexpr int oDt = C::WARPS * PER_WARP;    // shared by the CTA
     static constexpr int NTILE = ((NZ + 2) / 2) * ((NZ + 2) / 4 + 1);   // bound on the tile table
     static constexpr int oTT = oDt + ev(K * K);        // tile table (uint16) and counts (int), as doubles
@@ -1090,19 +1097,25 @@ int ws_launch(nlpf_problem* p, int B, double* z, const double* U, const double* 
     return nlpf_check_cuda(cudaGetLastError(), "wsolve_kernel launch");
 }
 
-#ifndef WS_PR_WARPS
-#define WS_PR_WARPS 2     // windows per CTA of the pseudorange shapes: 4 CTAs = 8 windows per SM (shared memory).
-                          // Measured alternatives: 3x3 / 1x9 warps 4 % slower (4096 windows = 27.7 per SM: 4 rounds
-                          // either way); 32-epoch chunks of G_e to fit 10 windows per SM: chunking cost 12 %, net -4 %
+// windows (warps) per CTA.  Pseudorange shapes are limited by shared memory (about 21 KB per window):
+//  * GNSS: 2 CTAs x 5 = 10 windows per SM -- 4096 windows are 27.7 per SM, i.e. 3 rounds instead of the 4 of
+//    8 windows per SM (2.41 M -> 2.61 M windows/s; 1 x 10 warps: 2.59 M).  Storing G_e in 32-epoch chunks to
+//    get there without the aliased vectors cost more (-12 %) than it gave.
+//  * vehicle: 4 CTAs x 2 = 8 windows per SM; 10 per SM caps the kernel at 168 registers (spills): -6 %.
+#ifndef WS_GNSS_WARPS
+#define WS_GNSS_WARPS 5
+#endif
+#ifndef WS_CAR_WARPS
+#define WS_CAR_WARPS 2
 #endif
 #ifndef WS_LIN_WARPS
 #define WS_LIN_WARPS 8
 #endif
 typedef WsCfg<21, 2, 1, 50, 2, NLPF_DYN_VDP, 0, WS_LIN_WARPS> CfgVdp;          // van der Pol MHE (BASELINE configs[1])
 typedef WsCfg<21, 2, 2, 50, 2, NLPF_DYN_AFFINE, 0, WS_LIN_WARPS> CfgExample;   // estimation_example.py
-typedef WsCfg<11, 5, 3, 51, 12, NLPF_DYN_AFFINE, 1, WS_PR_WARPS> CfgGnss;     // gnss_stationary.py MHE (BASELINE configs[2])
-typedef WsCfg<6, 9, 2, 21, 11, NLPF_DYN_VEHICLE_GNSS, 1, WS_PR_WARPS, 2, true, NLPF_LOSS_L2> CfgCar;         // autonomous-car.py:184-220
-typedef WsCfg<6, 9, 2, 21, 11, NLPF_DYN_VEHICLE_GNSS, 1, WS_PR_WARPS, 2, true, NLPF_LOSS_HUBER> CfgCarHuber;  // autonomous-car.py:293-318
+typedef WsCfg<11, 5, 3, 51, 12, NLPF_DYN_AFFINE, 1, WS_GNSS_WARPS> CfgGnss;     // gnss_stationary.py MHE (BASELINE configs[2])
+typedef WsCfg<6, 9, 2, 21, 11, NLPF_DYN_VEHICLE_GNSS, 1, WS_CAR_WARPS, 2, true, NLPF_LOSS_L2> CfgCar;         // autonomous-car.py:184-220
+typedef WsCfg<6, 9, 2, 21, 11, NLPF_DYN_VEHICLE_GNSS, 1, WS_CAR_WARPS, 2, true, NLPF_LOSS_HUBER> CfgCarHuber;  // autonomous-car.py:293-318
 
 }  // namespace
 
