@@ -354,12 +354,12 @@ extern "C" int nlpf_problem_create(const nlpf_desc* D, nlpf_problem** out) {
     std::vector<double> Hcp((size_t)ppo(nz), 0.0);
     for (int r = 0; r < nz; ++r)
         for (int c = 0; c <= r; ++c) Hcp[(size_t)ppo(r) + c] = Hc[(size_t)r * (r + 1) / 2 + c];
-    std::vector<uint16_t> tile_tab;
+    std::vector<uint16_t> tile_tab;                // 4-row x 2-column tiles: row quad rq | column pair ct << 8
     std::vector<int> tile_cnt(nz + 2, 0);
-    for (int s = 0; s <= nz + 1; ++s) {            // rows di < s; row pair rp covers di = 2rp, 2rp+1
-        if (s >= 1 && (s - 1) % 2 == 0) {          // a new row pair starts at di = s-1
-            const int rp = (s - 1) / 2;
-            for (int ct = 0; 4 * ct <= 2 * rp + 1; ++ct) tile_tab.push_back((uint16_t)(rp | (ct << 8)));
+    for (int s = 0; s <= nz + 1; ++s) {            // rows di < s; row quad rq covers di = 4rq .. 4rq+3
+        if (s >= 1 && (s - 1) % 4 == 0) {          // a new row quad starts at di = s-1
+            const int rq = (s - 1) / 4;
+            for (int ct = 0; 2 * ct <= 4 * rq + 3; ++ct) tile_tab.push_back((uint16_t)(rq | (ct << 8)));
         }
         tile_cnt[s] = (int)tile_tab.size();
     }

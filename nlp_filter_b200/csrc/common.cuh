@@ -65,7 +65,7 @@ struct DevProb {
     const uint16_t* seg_tab;          // LDL trailing-update items of the generic triangle: di | (dk0/8)<<8
     const int* seg_cnt;               // nz+2  number of items of a trailing triangle with s rows
     // warp-per-window kernel: H in the row-padded packed layout (row r starts at 2*((r+1)/2)*((r+2)/2), so every
-    // row is 16-byte aligned), 2-row x 4-column trailing-update tiles rp | ct<<8 sorted by row pair
+    // row is 16-byte aligned), 4-row x 2-column trailing-update tiles rq | ct<<8 sorted by row quad
     const uint16_t* sym_tab;          // general H accumulation: (a | b0<<8) blocks of 4 entries of the lower triangle of G_e
     int nsym;
     const double* Hcp;                // Hc in the padded layout

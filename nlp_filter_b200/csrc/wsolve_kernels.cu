@@ -177,7 +177,7 @@ struct WsLayout {
     static constexpr int PER_WARP = oF + NFQ;
     static_assert(NQ >= NZ, "fb shares the head of Q");
     static constexpr int oDt = C::WARPS * PER_WARP;    // shared by the CTA
-    static constexpr int NTILE = ((NZ + 2) / 2) * ((NZ + 2) / 4 + 1);   // bound on the tile table
+    static constexpr int NTILE = ((NZ + 4) / 4) * ((NZ + 4) / 2 + 1);   // bound on the tile table (row quads x column pairs)
     static constexpr int oTT = oDt + ev(K * K);        // tile table (uint16) and counts (int), as doubles
     static constexpr int oTC = oTT + ev((NTILE + 3) / 4);
     // class constants staged once per CTA: interpolation matrix Phi (E x K), cw_k * qinv_i, node-pair table
@@ -315,12 +315,32 @@ __device__ __forceinline__ void ws_eval(const DevProb& P, double* sm, const WsCo
                         for (int k = 0; k < K; ++k) s1 = fma(Dt[k * K + j] * Dt[k * K + l], wh[k * N + a], s1);
                     }
                     const double wla = whv(l, a);
+                    if constexpr (N % 2 == 0) {
+                        // column pairs as 16-byte read-modify-writes (row starts and l*N are even): neighbouring
+                        // lanes then touch contiguous 16-byte pieces instead of 8 bytes every 16 (2-way conflicts).
+                        // In a diagonal node block the partner of the diagonal entry is the row's padding slot.
 #pragma unroll
-                    for (int b = 0; b < N; ++b) {
-                        if (j == l && b > a) continue;
-                        double s = -djl * whv(j, b) * Fm[j * N * N + b * N + a] - dlj * wla * Fm[l * N * N + a * N + b];
-                        if (HUB && a == b) s += s1;
-                        Hp[pk(j * N + a, l * N + b)] += s;
+                        for (int b = 0; b < N; b += 2) {
+                            if (j == l && b > a) continue;
+                            const double2 fl = *reinterpret_cast<const double2*>(Fm + l * N * N + a * N + b);
+                            double s0 = -djl * whv(j, b) * Fm[j * N * N + b * N + a] - dlj * wla * fl.x;
+                            double s1b = -djl * whv(j, b + 1) * Fm[j * N * N + (b + 1) * N + a] - dlj * wla * fl.y;
+                            if (HUB && a == b) s0 += s1;
+                            if (HUB && a == b + 1) s1b += s1;
+                            double2* hp = reinterpret_cast<double2*>(Hp + pk(j * N + a, l * N + b));
+                            double2 hv = *hp;
+                            hv.x += s0;
+                            hv.y += s1b;
+                            *hp = hv;
+                        }
+                    } else {
+#pragma unroll
+                        for (int b = 0; b < N; ++b) {
+                            if (j == l && b > a) continue;
+                            double s = -djl * whv(j, b) * Fm[j * N * N + b * N + a] - dlj * wla * Fm[l * N * N + a * N + b];
+                            if (HUB && a == b) s += s1;
+                            Hp[pk(j * N + a, l * N + b)] += s;
+                        }
                     }
                 }
             }
@@ -635,9 +655,11 @@ __device__ __forceinline__ void ws_eval(const DevProb& P, double* sm, const WsCo
 //   1. every lane factors the 4x4 diagonal block redundantly in registers (frcp pivots);
 //   2. one lane per row below: w = a L11^-T by substitution; W^T goes to a side buffer, the SCALED
 //      l = w / d is stored in place (so the backward sweep needs no pivots);
-//   3. the trailing triangle is updated in 2-row x 4-column register tiles from a table (32 independent
+//   3. the trailing triangle is updated in 4-row x 2-column register tiles from a table (32 independent
 //      FMAs per tile, all shared-memory traffic as 16-byte accesses; the per-entry loop this replaces
-//      took 30 % of the kernel: 16 instructions and a load->4 FMA->store chain per entry);
+//      took 30 % of the kernel: 16 instructions and a load->4 FMA->store chain per entry).  Column PAIRS
+//      per lane keep the tile and W^T accesses of neighbouring lanes contiguous: the 2-row x 4-column
+//      shape had them 32 bytes apart, a 2-way bank conflict on every access;
 //   4. the diagonal block is overwritten with the strict lower part of L11^-1, which turns the 4x4
 //      triangular solve of the backward sweep into independent dot products.
 template <int NZ, int LDW>
@@ -728,39 +750,35 @@ __device__ __forceinline__ bool ws_ldl(const uint16_t* __restrict__ ttab, const 
         const int nitem = tcnt[NZ + 1 - j1];
         for (int it = lane; it < nitem; it += 32) {
             const int e = ttab[it];
-            const int i = j1 + ((e & 255) << 1);          // even row; its partner i+1 follows at + i + 2
-            const int k0 = j1 + ((e >> 8) << 2);
-            double* R0 = Hp + po(i);
-            double* R1 = R0 + i + 2;
-            double2 la[2], lb[2], x0[2], x1[2];
-            la[0] = *reinterpret_cast<const double2*>(R0 + j0);
-            lb[0] = *reinterpret_cast<const double2*>(R0 + j0 + 2);
-            la[1] = *reinterpret_cast<const double2*>(R1 + j0);
-            lb[1] = *reinterpret_cast<const double2*>(R1 + j0 + 2);
-            x0[0] = *reinterpret_cast<const double2*>(R0 + k0);
-            x1[0] = *reinterpret_cast<const double2*>(R0 + k0 + 2);
-            x0[1] = *reinterpret_cast<const double2*>(R1 + k0);
-            x1[1] = *reinterpret_cast<const double2*>(R1 + k0 + 2);
-            const double* Wk = Wt + k0;
+            const int i = j1 + ((e & 255) << 2);          // first row of the quad (a multiple of 4)
+            const int k0 = j1 + ((e >> 8) << 1);          // column pair
+            double* R[4];
+            R[0] = Hp + po(i);
+            R[1] = R[0] + i + 2;                          // padded row lengths: i+2, i+2, i+4
+            R[2] = R[1] + i + 2;
+            R[3] = R[2] + i + 4;
+            double2 x[4];
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                const double2 wa = *reinterpret_cast<const double2*>(Wk + c * LDW);
-                const double2 wb = *reinterpret_cast<const double2*>(Wk + c * LDW + 2);
+            for (int r = 0; r < 4; ++r) x[r] = *reinterpret_cast<const double2*>(R[r] + k0);
+            double2 wv[4];
 #pragma unroll
-                for (int r = 0; r < 2; ++r) {
-                    const double lv = (c == 0) ? la[r].x : (c == 1) ? la[r].y : (c == 2) ? lb[r].x : lb[r].y;
-                    x0[r].x = fma(-lv, wa.x, x0[r].x);
-                    x0[r].y = fma(-lv, wa.y, x0[r].y);
-                    x1[r].x = fma(-lv, wb.x, x1[r].x);
-                    x1[r].y = fma(-lv, wb.y, x1[r].y);
-                }
+            for (int c = 0; c < 4; ++c) wv[c] = *reinterpret_cast<const double2*>(Wt + c * LDW + k0);
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                const double2 la = *reinterpret_cast<const double2*>(R[r] + j0);
+                const double2 lb = *reinterpret_cast<const double2*>(R[r] + j0 + 2);
+                x[r].x = fma(-la.x, wv[0].x, x[r].x);
+                x[r].y = fma(-la.x, wv[0].y, x[r].y);
+                x[r].x = fma(-la.y, wv[1].x, x[r].x);
+                x[r].y = fma(-la.y, wv[1].y, x[r].y);
+                x[r].x = fma(-lb.x, wv[2].x, x[r].x);
+                x[r].y = fma(-lb.x, wv[2].y, x[r].y);
+                x[r].x = fma(-lb.y, wv[3].x, x[r].x);
+                x[r].y = fma(-lb.y, wv[3].y, x[r].y);
             }
-            if (k0 <= i) *reinterpret_cast<double2*>(R0 + k0) = x0[0];
-            if (k0 + 2 <= i) *reinterpret_cast<double2*>(R0 + k0 + 2) = x1[0];
-            if (i + 1 <= NZ) {
-                if (k0 <= i + 1) *reinterpret_cast<double2*>(R1 + k0) = x0[1];
-                if (k0 + 2 <= i + 1) *reinterpret_cast<double2*>(R1 + k0 + 2) = x1[1];
-            }
+#pragma unroll
+            for (int r = 0; r < 4; ++r)
+                if (k0 <= i + r && i + r <= NZ) *reinterpret_cast<double2*>(R[r] + k0) = x[r];
         }
     }
     __syncwarp();
