@@ -42,6 +42,17 @@ extern "C" int nlpf_ws_launch(int variant, nlpf_problem* p, int B, double* z, co
                               double* hlin, int* counter, int W, const double* phiDT, double* Zout, cudaStream_t st);
 extern "C" int nlpf_set_smem_attrs_gen(size_t bytes);
 extern "C" int nlpf_set_smem_attrs_pr(size_t bytes);
+// BIG instantiations (nls_kernels_*_big.cu): 128-register cap for classes with <= 5 windows per SM
+extern "C" int nlpf_launch_assemble_genb(nlpf_problem*, int, const double*, const double*, const double*, const double*,
+                                         const double*, double, double*, double*, double*, cudaStream_t);
+extern "C" int nlpf_launch_assemble_prb(nlpf_problem*, int, const double*, const double*, const double*, const double*,
+                                        const double*, double, double*, double*, double*, cudaStream_t);
+extern "C" int nlpf_launch_solve_genb(nlpf_problem*, int, double*, const double*, const double*, const double*,
+                                      const double*, const nlpf_opts*, double*, int*, int*, double*, cudaStream_t);
+extern "C" int nlpf_launch_solve_prb(nlpf_problem*, int, double*, const double*, const double*, const double*,
+                                     const double*, const nlpf_opts*, double*, int*, int*, double*, cudaStream_t);
+extern "C" int nlpf_set_smem_attrs_genb(size_t bytes);
+extern "C" int nlpf_set_smem_attrs_prb(size_t bytes);
 
 extern "C" int nlpf_version(void) { return NLPF_VERSION; }
 extern "C" const char* nlpf_last_error(void) { return g_err; }
@@ -433,7 +444,12 @@ extern "C" int nlpf_problem_create(const nlpf_desc* D, nlpf_problem** out) {
         nlpf_set_error("problem needs %zu bytes of shared memory per window (limit 232448)", p->smem_bytes);
         cudaFree(p->blob); delete p; return NLPF_E_ARG;
     }
-    if (nlpf_set_smem_attrs_gen(227 * 1024) != NLPF_OK || nlpf_set_smem_attrs_pr(227 * 1024) != NLPF_OK) { cudaFree(p->blob); delete p; return NLPF_E_CUDA; }
+    // shared memory allows at most 5 windows per SM: the 128-register instantiation loses no residency
+    p->use_big = ((227 * 1024) / (p->smem_bytes + 1024) <= 5 && !getenv("NLPF_NO_BIG_KERNEL")) ? 1 : 0;
+    if (nlpf_set_smem_attrs_gen(227 * 1024) != NLPF_OK || nlpf_set_smem_attrs_pr(227 * 1024) != NLPF_OK ||
+        nlpf_set_smem_attrs_genb(227 * 1024) != NLPF_OK || nlpf_set_smem_attrs_prb(227 * 1024) != NLPF_OK) {
+        cudaFree(p->blob); delete p; return NLPF_E_CUDA;
+    }
     *out = p;
     return NLPF_OK;
 }
@@ -464,7 +480,9 @@ extern "C" int nlpf_assemble(nlpf_problem* p, int B, const double* z, const doub
     int rc = check_batch(p, B, z, data);
     if (rc) return rc;
     if (!H_out || !g_out || !cost_out) { nlpf_set_error("null output buffer"); return NLPF_E_ARG; }
-    return (p->use_pr ? nlpf_launch_assemble_pr : nlpf_launch_assemble_gen)(p, B, z, U, data, xprior, wshift, mu, H_out, g_out, cost_out, (cudaStream_t)stream);
+    auto launch = p->use_big ? (p->use_pr ? nlpf_launch_assemble_prb : nlpf_launch_assemble_genb)
+                             : (p->use_pr ? nlpf_launch_assemble_pr : nlpf_launch_assemble_gen);
+    return launch(p, B, z, U, data, xprior, wshift, mu, H_out, g_out, cost_out, (cudaStream_t)stream);
 }
 
 extern "C" int nlpf_factor_solve(nlpf_problem* p, int B, const double* H, const double* g, double lam, double* dz_out,
@@ -527,7 +545,9 @@ extern "C" int nlpf_solve(nlpf_problem* p, int B, double* z, const double* U, co
         }
         hlin = p->scratch;
     }
-    return (p->use_pr ? nlpf_launch_solve_pr : nlpf_launch_solve_gen)(p, B, z, U, data, xprior, wshift, opts, cost_out, iters_out, status_out, hlin, (cudaStream_t)stream);
+    auto launch = p->use_big ? (p->use_pr ? nlpf_launch_solve_prb : nlpf_launch_solve_genb)
+                             : (p->use_pr ? nlpf_launch_solve_pr : nlpf_launch_solve_gen);
+    return launch(p, B, z, U, data, xprior, wshift, opts, cost_out, iters_out, status_out, hlin, (cudaStream_t)stream);
 }
 
 extern "C" int nlpf_sample(nlpf_problem* p, int B, const double* z, int nt, const double* PhiT, double* out, void* stream) {

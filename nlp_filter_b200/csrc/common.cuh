@@ -84,6 +84,7 @@ struct nlpf_problem {
     size_t blob_bytes;
     size_t smem_bytes;
     int use_pr;          // 1: problem has pseudorange runs -> *_pr kernels
+    int use_big;         // 1: <= 5 windows per SM by shared memory -> 128-register instantiations (*_genb / *_prb)
     int ws_variant;      // >= 0: small linear-measurement class served by the warp-per-window kernel
     int* counter;        // device work counter of the warp-per-window kernel
     int device;

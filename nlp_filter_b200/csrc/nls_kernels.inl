@@ -23,10 +23,26 @@
 #ifndef NLPF_PR_RUNS
 #error "include through nls_kernels_gen.cu / nls_kernels_pr.cu"
 #endif
+// NLPF_BIG = 1 (nls_kernels_*_big.cu): the same kernels for problem classes whose shared memory allows at most 5
+// windows per SM anyway (two-receiver, RC, multi-receiver shapes): min 4 CTAs per SM, i.e. a 128-register cap
+// instead of 64 (two-receiver batch: 85 k -> 97 k windows/s).
+#ifndef NLPF_BIG
+#define NLPF_BIG 0
+#endif
+#if NLPF_BIG
+#undef NLPF_MIN_CTAS
+#define NLPF_MIN_CTAS 4
+#if NLPF_PR_RUNS
+#define VN(name) name##_prb
+#else
+#define VN(name) name##_genb
+#endif
+#else
 #if NLPF_PR_RUNS
 #define VN(name) name##_pr
 #else
 #define VN(name) name##_gen
+#endif
 #endif
 
 namespace VN(nlpf_ns) {      // both instantiations define the same helper names
@@ -1094,7 +1110,7 @@ VN(assemble_kernel)(DevProb P, int B, const double* __restrict__ z, const double
     }
 }
 
-#if !NLPF_PR_RUNS
+#if !NLPF_PR_RUNS && !NLPF_BIG
 // ------------------------------------------------------------------------------------------
 // nlpf_factor_solve: kernel (3) alone
 // ------------------------------------------------------------------------------------------
@@ -1347,7 +1363,7 @@ VN(solve_kernel)(const __grid_constant__ DevProb P, int B, double* __restrict__ 
     }
 }
 
-#if !NLPF_PR_RUNS
+#if !NLPF_PR_RUNS && !NLPF_BIG
 // ------------------------------------------------------------------------------------------
 // nlpf_sample: x(t) = Phi(t) X, nlp.py:99-119
 // ------------------------------------------------------------------------------------------
@@ -1383,7 +1399,7 @@ extern "C" int VN(nlpf_launch_assemble)(nlpf_problem* p, int B, const double* z,
     return nlpf_check_cuda(cudaGetLastError(), "assemble_kernel launch");
 }
 
-#if !NLPF_PR_RUNS
+#if !NLPF_PR_RUNS && !NLPF_BIG
 extern "C" int nlpf_launch_factor_solve(nlpf_problem* p, int B, const double* H, const double* g, double lam,
                                         double* dz_out, int* info_out, cudaStream_t st) {
     factor_solve_kernel<<<grid_for(B), NLPF_NT, p->smem_bytes, st>>>(p->d, B, H, g, lam, dz_out, info_out);
@@ -1399,7 +1415,7 @@ extern "C" int VN(nlpf_launch_solve)(nlpf_problem* p, int B, double* z, const do
     return nlpf_check_cuda(cudaGetLastError(), "solve_kernel launch");
 }
 
-#if !NLPF_PR_RUNS
+#if !NLPF_PR_RUNS && !NLPF_BIG
 extern "C" int nlpf_launch_sample(nlpf_problem* p, int B, const double* z, int nt, const double* PhiT, double* out,
                                   cudaStream_t st) {
     const size_t total = (size_t)B * nt * p->d.n;
@@ -1416,7 +1432,7 @@ extern "C" int VN(nlpf_set_smem_attrs)(size_t bytes) {
     cudaError_t e;
     e = cudaFuncSetAttribute(VN(assemble_kernel), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
     if (e != cudaSuccess) return nlpf_check_cuda(e, "smem attr assemble");
-#if !NLPF_PR_RUNS
+#if !NLPF_PR_RUNS && !NLPF_BIG
     e = cudaFuncSetAttribute(factor_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
     if (e != cudaSuccess) return nlpf_check_cuda(e, "smem attr factor");
 #endif
