@@ -375,6 +375,14 @@ extern "C" int nlpf_problem_create(const nlpf_desc* D, nlpf_problem** out) {
         tile_cnt[s] = (int)tile_tab.size();
     }
 
+    // sum over the epochs of phi_ej phi_el per node pair (order of ptab)
+    std::vector<double> PtP(ptab.size(), 0.0);
+    for (size_t pr = 0; pr < ptab.size(); ++pr) {
+        const int j = ptab[pr] & 255, l = ptab[pr] >> 8;
+        double acc = 0.0;
+        for (int e = 0; e < E; ++e) acc += D->Phi[(size_t)e * K + j] * D->Phi[(size_t)e * K + l];
+        PtP[pr] = acc;
+    }
     // general measurement-Hessian accumulation: G_e is symmetric, so only b <= a is summed, in blocks of 4
     std::vector<uint16_t> sym_tab;
     for (int a = 0; a < na; ++a)
@@ -394,7 +402,7 @@ extern "C" int nlpf_problem_create(const nlpf_desc* D, nlpf_problem** out) {
                  oPh = B.add(D->Phi, sizeof(double) * E * K), ort = B.addv(rtype_s), orl = B.addv(rloc_s),
                  oro = B.addv(roff_s), oes = B.addv(estart), oac = B.addv(act), oHc = B.addv(Hc), oFc = B.addv(Fc),
                  otb = B.addv(tab), opt = B.addv(ptab), osg = B.addv(seg_tab), osc = B.addv(seg_cnt),
-                 oPT = B.addv(PhiT), oHp = B.addv(Hcp), osy = B.addv(sym_tab), ott = B.addv(tile_tab), otc = B.addv(tile_cnt), oms = B.addv(mslot), ogs = B.addv(gstart), oer = B.addv(erun), ors = B.addv(run_start), orn = B.addv(run_len), orc = B.addv(run_loc);
+                 oPT = B.addv(PhiT), oHp = B.addv(Hcp), oPP = B.addv(PtP), osy = B.addv(sym_tab), ott = B.addv(tile_tab), otc = B.addv(tile_cnt), oms = B.addv(mslot), ogs = B.addv(gstart), oer = B.addv(erun), ors = B.addv(run_start), orn = B.addv(run_len), orc = B.addv(run_loc);
     B.add(zero1.data(), 16);
     p->blob_bytes = B.host.size();
     cudaGetDevice(&p->device);
@@ -413,6 +421,7 @@ extern "C" int nlpf_problem_create(const nlpf_desc* D, nlpf_problem** out) {
     P.Fc = (const double*)(base + oFc); P.tab = (const uint32_t*)(base + otb); P.ptab = (const uint16_t*)(base + opt);
     P.seg_tab = (const uint16_t*)(base + osg); P.seg_cnt = (const int*)(base + osc);
     P.sym_tab = (const uint16_t*)(base + osy);
+    P.PtP = (const double*)(base + oPP);
     P.Hcp = (const double*)(base + oHp); P.tile_tab = (const uint16_t*)(base + ott); P.tile_cnt = (const int*)(base + otc);
     P.PhiT = (const double*)(base + oPT); P.mslot = (const int*)(base + oms);
     P.gstart = (const int*)(base + ogs); P.erun = (const int*)(base + oer); P.run_start = (const int*)(base + ors);

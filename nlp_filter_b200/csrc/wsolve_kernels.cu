@@ -890,7 +890,24 @@ wsolve_kernel(const __grid_constant__ DevProb P, int B, double* __restrict__ z_i
             for (int p = lane; p < L::NP; p += 32) Hp[p] = P.Hcp[p];
             double* wts = sm + L::oQ;
             for (int t = lane; t < L::NR; t += 32) wts[t] = dg[2 * t + 1];
+            // the usual case -- the same weight at every epoch (constant measurement covariance) -- needs no sum
+            // over the epochs: sum_e phi_ej phi_el is a class constant (P.PtP, built on the host)
+            bool same = true;
+            for (int t = lane; t < L::NR; t += 32) same = same && (dg[2 * t + 1] == dg[2 * (t % NM) + 1]);
+            same = __all_sync(0xffffffffu, same);
             __syncwarp();
+            if (same) {
+                for (int pr = lane; pr < K * (K + 1) / 2; pr += 32) {
+                    const int pe = cs.ptab[pr];
+                    const int j = pe & 255, l = pe >> 8;
+                    const double pp = P.PtP[pr];
+#pragma unroll
+                    for (int s = 0; s < NM; ++s) {
+                        const int c = cs.c[s < 4 ? s : 3];
+                        Hp[pk(j * N + c, l * N + c)] += pp * wts[s];
+                    }
+                }
+            } else
             for (int pr = lane; pr < K * (K + 1) / 2; pr += 32) {
                 const int pe = cs.ptab[pr];
                 const int j = pe & 255, l = pe >> 8;

@@ -136,6 +136,19 @@ def test_solve_vdp_matches_oracle():
     _solve_both(d, bt, 24)
 
 
+def test_solve_vdp_epoch_dependent_and_missing_measurements():
+    """Weights that change from epoch to epoch (and weight 0 = missing measurement) take the summed form of the
+    measurement Hessian in the warp kernel; constant weights take its precomputed sum over the epochs."""
+    d = shapes.vdp_mhe()
+    bt = synth.vdp_mhe_batch(d, 12, seed=22)
+    rng = np.random.default_rng(3)
+    w = bt["data"].reshape(12, -1, 2)
+    w[:, :, 1] *= rng.uniform(0.25, 4.0, size=w.shape[:2])
+    w[:, :, 1][rng.uniform(size=w.shape[:2]) < 0.1] = 0.0
+    w[0, :, 1] = bt["data"].reshape(12, -1, 2)[0, 0, 1]            # one window back to constant weights
+    _solve_both(d, bt, 12)
+
+
 def test_solve_gnss_matches_oracle_1mm():
     d = shapes.gnss()
     bt = synth.gnss_batch(d, 12, seed=22)
