@@ -339,6 +339,15 @@ def cpu_car_windows_per_sec(runs, windows, cores):
     return runs * windows / dt, float(np.sum(its)) / (runs * windows)
 
 
+def _traffic(workload):
+    """dram bytes per launch of the dominant kernel from the committed ncu --set full summary, or None"""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic_%s.json" % workload)) as f:
+            return float(json.load(f)["dram_bytes_per_launch"])
+    except Exception:
+        return None
+
+
 def run_car(args):
     cores = os.cpu_count() or 1
     cpu_base = None
@@ -413,7 +422,7 @@ def run_car(args):
             "gpu_launches": args.steps * (W * 2 if os.environ.get("NLPF_CHAIN_LOOP") else 1),
             "roofline": {"bound": "fp64", "kernel": "wsolve_kernel<CfgCar> (fused chain: all windows of a run in one warp, one launch per step)",
                          "achieved": achieved, "peak": peak_fp64, "unit": "TFLOP/s",
-                         "frac": achieved / peak_fp64, "traffic": None, "kernel_ms": ms_step,
+                         "frac": achieved / peak_fp64, "traffic": _traffic("car") if (B, W) == (2048, 25) else None, "kernel_ms": ms_step,
                          "peak_source": "FP64 FMA probe measured in this run"},
             "clocks": clocks}
     if cpu_base is not None:
@@ -507,7 +516,7 @@ def run_ours(args):
     def step_e2e():
         hb.run()
         if world > 1:
-            dist.all_gather_into_tensor(gathered, hb.d_z)
+            dist.all_gather_into_tensor(gathered, hb.device_z())
 
     def timed(step_fn, kernel_events=False):
         for _ in range(args.warmup):

@@ -130,7 +130,9 @@ class HostBatch(object):
     The batch is cut into `nchunk` contiguous chunks, each with its own stream and problem handle:
     chunk c+1's host-to-device copy overlaps chunk c's solve and chunk c-1's device-to-host copy
     (a GNSS window carries 25 KB of measurement records: 103 MB per 4096 windows, as long on PCIe
-    as the solve itself)."""
+    as the solve itself).  Every chunk's inputs [z | U | data | xprior] sit back to back in ONE pinned
+    buffer and one device buffer, its outputs [cost | iters | status] in another: one H2D and two D2H
+    copies per chunk instead of eight small ones (the launch overhead of those was a tenth of a VDP step)."""
 
     def __init__(self, prob, B, nchunk=None):
         d = prob.desc
@@ -147,53 +149,67 @@ class HostBatch(object):
         self.chunks = [(cuts[c], cuts[c + 1]) for c in range(self.nchunk)]
         self.probs = [prob] + [WindowProblem(d) for _ in range(self.nchunk - 1)]
         self.streams = [torch.cuda.Stream() for _ in range(self.nchunk)] if self.nchunk > 1 else [None]
-        mk = lambda *s: torch.empty(s, dtype=torch.float64).pin_memory()
-        self.h_z = mk(B, d.nz)
-        self.h_U = mk(B, d.K, max(d.m, 1)) if d.m > 0 else None
-        self.h_data = mk(B, max(d.Ldata, 1))
-        self.h_xp = mk(B, d.n) if d.has_prior else None
-        dev = lambda t: torch.empty_like(t, device="cuda") if t is not None else None
-        self.d_z, self.d_U, self.d_data, self.d_xp = dev(self.h_z), dev(self.h_U), dev(self.h_data), dev(self.h_xp)
-        self.d_cost = torch.empty((B,), dtype=torch.float64, device="cuda")
-        self.d_iters = torch.empty((B,), dtype=torch.int32, device="cuda")
-        self.d_status = torch.empty((B,), dtype=torch.int32, device="cuda")
-        self.h_out = mk(B, d.nz)
-        self.h_cost = mk(B)
-        self.h_iters = torch.empty((B,), dtype=torch.int32).pin_memory()
-        self.h_status = torch.empty((B,), dtype=torch.int32).pin_memory()
-        self.h2d_bytes = sum(t.numel() * t.element_size() for t in (self.h_z, self.h_U, self.h_data, self.h_xp) if t is not None)
-        self.d2h_bytes = sum(t.numel() * t.element_size() for t in (self.h_out, self.h_cost, self.h_iters, self.h_status))
+        mU = d.K * d.m if d.m > 0 else 0
+        Ld = max(d.Ldata, 1)
+        nx = d.n if d.has_prior else 0
+        self._nz, self._mU, self._Ld, self._nx = d.nz, mU, Ld, nx
+        self.h_in, self.d_in, self.h_meta, self.d_meta, self.h_zout = [], [], [], [], []
+        for lo, hi in self.chunks:
+            nb = hi - lo
+            n_in = nb * (d.nz + mU + Ld + nx)
+            self.h_in.append(torch.zeros((n_in,), dtype=torch.float64).pin_memory())
+            self.d_in.append(torch.empty((n_in,), dtype=torch.float64, device="cuda"))
+            self.h_meta.append(torch.zeros((2 * nb,), dtype=torch.float64).pin_memory())
+            self.d_meta.append(torch.empty((2 * nb,), dtype=torch.float64, device="cuda"))
+            self.h_zout.append(torch.zeros((nb, d.nz), dtype=torch.float64).pin_memory())
+        self.h2d_bytes = sum(t.numel() * 8 for t in self.h_in)
+        self.d2h_bytes = sum(t.numel() * 8 for t in self.h_meta) + sum(t.numel() * 8 for t in self.h_zout)
+
+    def _views(self, buf, c):
+        """(z, U, data, xprior) views of chunk c's packed input buffer (host or device)."""
+        lo, hi = self.chunks[c]
+        nb = hi - lo
+        d = self.prob.desc
+        o = 0
+        z = buf[o:o + nb * self._nz].view(nb, self._nz); o += nb * self._nz
+        U = buf[o:o + nb * self._mU].view(nb, d.K, d.m) if self._mU else None; o += nb * self._mU
+        data = buf[o:o + nb * self._Ld].view(nb, self._Ld); o += nb * self._Ld
+        xp = buf[o:o + nb * self._nx].view(nb, self._nx) if self._nx else None
+        return z, U, data, xp
+
+    def _meta(self, buf, c):
+        lo, hi = self.chunks[c]
+        nb = hi - lo
+        ints = buf[nb:].view(torch.int32)
+        return buf[:nb], ints[:nb], ints[nb:2 * nb]
 
     def load(self, z0, U=None, data=None, xprior=None):
-        self.h_z.copy_(torch.as_tensor(np.asarray(z0, dtype=np.float64).reshape(self.h_z.shape)))
-        if self.h_U is not None:
-            self.h_U.copy_(torch.as_tensor(np.asarray(U, dtype=np.float64).reshape(self.h_U.shape)))
-        if data is not None:
-            self.h_data.copy_(torch.as_tensor(np.asarray(data, dtype=np.float64).reshape(self.h_data.shape)))
-        if self.h_xp is not None:
-            self.h_xp.copy_(torch.as_tensor(np.asarray(xprior, dtype=np.float64).reshape(self.h_xp.shape)))
+        d = self.prob.desc
+        z0 = torch.as_tensor(np.asarray(z0, dtype=np.float64).reshape(self.B, d.nz))
+        U = None if not self._mU else torch.as_tensor(np.asarray(U, dtype=np.float64).reshape(self.B, d.K, d.m))
+        data = None if data is None else torch.as_tensor(np.asarray(data, dtype=np.float64).reshape(self.B, self._Ld))
+        xprior = None if not self._nx else torch.as_tensor(np.asarray(xprior, dtype=np.float64).reshape(self.B, d.n))
+        for c, (lo, hi) in enumerate(self.chunks):
+            hz, hU, hd, hx = self._views(self.h_in[c], c)
+            hz.copy_(z0[lo:hi])
+            if hU is not None:
+                hU.copy_(U[lo:hi])
+            if data is not None:
+                hd.copy_(data[lo:hi])
+            if hx is not None:
+                hx.copy_(xprior[lo:hi])
 
     def _run_chunk(self, c, opts):
-        lo, hi = self.chunks[c]
-        sl = slice(lo, hi)
-        self.d_z[sl].copy_(self.h_z[sl], non_blocking=True)
-        if self.h_U is not None:
-            self.d_U[sl].copy_(self.h_U[sl], non_blocking=True)
-        self.d_data[sl].copy_(self.h_data[sl], non_blocking=True)
-        if self.h_xp is not None:
-            self.d_xp[sl].copy_(self.h_xp[sl], non_blocking=True)
-        self.probs[c].solve(self.d_z[sl], None if self.d_U is None else self.d_U[sl], self.d_data[sl],
-                            None if self.d_xp is None else self.d_xp[sl], None, opts,
-                            out=(self.d_cost[sl], self.d_iters[sl], self.d_status[sl]))
-        self.h_out[sl].copy_(self.d_z[sl], non_blocking=True)
-        self.h_cost[sl].copy_(self.d_cost[sl], non_blocking=True)
-        self.h_iters[sl].copy_(self.d_iters[sl], non_blocking=True)
-        self.h_status[sl].copy_(self.d_status[sl], non_blocking=True)
+        self.d_in[c].copy_(self.h_in[c], non_blocking=True)
+        z, U, data, xp = self._views(self.d_in[c], c)
+        self.probs[c].solve(z, U, data, xp, None, opts, out=self._meta(self.d_meta[c], c))
+        self.h_zout[c].copy_(z, non_blocking=True)
+        self.h_meta[c].copy_(self.d_meta[c], non_blocking=True)
 
     def run(self, opts=None):
         """H2D of the staged inputs, solve, D2H of the estimates, chunk-pipelined.  Asynchronous with
         respect to the host: the current stream waits for every chunk; call
-        torch.cuda.synchronize() (or wait on an event of the current stream) before reading h_out."""
+        torch.cuda.synchronize() (or wait on an event of the current stream) before reading results()."""
         if self.nchunk == 1:
             self._run_chunk(0, opts)
             return
@@ -208,6 +224,20 @@ class HostBatch(object):
                 done = torch.cuda.Event()
                 done.record(st)
             cur.wait_event(done)
+
+    def results(self):
+        """(z, cost, iters, status) NumPy arrays of the last run (synchronise first)."""
+        z = np.concatenate([t.numpy() for t in self.h_zout], 0)
+        metas = [self._meta(self.h_meta[c], c) for c in range(self.nchunk)]
+        cost = np.concatenate([m[0].numpy() for m in metas])
+        iters = np.concatenate([m[1].numpy() for m in metas])
+        status = np.concatenate([m[2].numpy() for m in metas])
+        return z, cost, iters, status
+
+    def device_z(self):
+        """(B, nz) contiguous device tensor of the estimates of the last run (for a collective)."""
+        zs = [self._views(self.d_in[c], c)[0] for c in range(self.nchunk)]
+        return zs[0] if self.nchunk == 1 else torch.cat(zs, 0)
 
 
 def solve_chain(prob, z, U_all, data_all, xprior, PhiDT, opts=None, keep=False):
@@ -256,7 +286,8 @@ def solve_windows_host(prob, z0, U=None, data=None, xprior=None, opts=None):
     hb.load(z0, U, data, xprior)
     hb.run(opts)
     torch.cuda.synchronize()
-    return hb.h_out.numpy().copy(), hb.h_cost.numpy().copy(), hb.h_iters.numpy().copy(), hb.h_status.numpy().copy()
+    z, cost, iters, status = hb.results()
+    return z.copy(), cost.copy(), iters.copy(), status.copy()
 
 
 # ---------------------------------------------------------------------------------------------
