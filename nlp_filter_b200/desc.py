@@ -140,7 +140,7 @@ class ProblemDesc(object):
 class SolveOpts(object):
     """Options of the damped Gauss-Newton / log-barrier iteration (see DESIGN.md "Solver")."""
 
-    def __init__(self, max_iter=300, tol_step=1e-11, lam0=1e-3, mu0=0.1, mu_min=1e-9,
+    def __init__(self, max_iter=300, tol_step=1e-9, lam0=1e-3, mu0=0.1, mu_min=1e-9,
                  bound_push=0.01, tau_ftb=0.99, max_stage_iter=300):
         self.max_iter = int(max_iter)
         self.tol_step = float(tol_step)
