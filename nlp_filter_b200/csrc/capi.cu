@@ -388,6 +388,24 @@ extern "C" int nlpf_problem_create(const nlpf_desc* D, nlpf_problem** out) {
     for (int a = 0; a < na; ++a)
         for (int b0 = 0; b0 <= a; b0 += 4) sym_tab.push_back((uint16_t)(a | (b0 << 8)));
     P.nsym = (int)sym_tab.size();
+    // ... and only at the epochs where a residual couples a with one of the block's columns (two-receiver shape:
+    // 15 of the 45 entries at a range/heading epoch, 19 at a pseudorange epoch)
+    std::vector<uint8_t> gnz((size_t)(P.nsym > 0 ? P.nsym : 1) * (E > 0 ? E : 1), 0);
+    {
+        std::vector<int> item_start(na + 1, 0);
+        for (int a = 0; a < na; ++a) item_start[a + 1] = item_start[a] + a / 4 + 1;
+        for (int e = 0; e < E; ++e)
+            for (int r = estart[e]; r < estart[e + 1]; ++r) {
+                int comps[NLPF_NIDX], nc = 0;
+                for (int s2 = 0; s2 < NLPF_NIDX; ++s2) {
+                    const int v = rloc_s[(size_t)r * NLPF_NIDX + s2];
+                    if (v >= 0 && v < na) comps[nc++] = v;
+                }
+                for (int x = 0; x < nc; ++x)
+                    for (int y = 0; y < nc; ++y)
+                        if (comps[y] <= comps[x]) gnz[(size_t)(item_start[comps[x]] + comps[y] / 4) * E + e] = 1;
+            }
+    }
 
     // ---- blob ----
     Blob B;
@@ -402,7 +420,7 @@ extern "C" int nlpf_problem_create(const nlpf_desc* D, nlpf_problem** out) {
                  oPh = B.add(D->Phi, sizeof(double) * E * K), ort = B.addv(rtype_s), orl = B.addv(rloc_s),
                  oro = B.addv(roff_s), oes = B.addv(estart), oac = B.addv(act), oHc = B.addv(Hc), oFc = B.addv(Fc),
                  otb = B.addv(tab), opt = B.addv(ptab), osg = B.addv(seg_tab), osc = B.addv(seg_cnt),
-                 oPT = B.addv(PhiT), oHp = B.addv(Hcp), oPP = B.addv(PtP), osy = B.addv(sym_tab), ott = B.addv(tile_tab), otc = B.addv(tile_cnt), oms = B.addv(mslot), ogs = B.addv(gstart), oer = B.addv(erun), ors = B.addv(run_start), orn = B.addv(run_len), orc = B.addv(run_loc);
+                 oPT = B.addv(PhiT), oHp = B.addv(Hcp), oPP = B.addv(PtP), osy = B.addv(sym_tab), ogz = B.addv(gnz), ott = B.addv(tile_tab), otc = B.addv(tile_cnt), oms = B.addv(mslot), ogs = B.addv(gstart), oer = B.addv(erun), ors = B.addv(run_start), orn = B.addv(run_len), orc = B.addv(run_loc);
     B.add(zero1.data(), 16);
     p->blob_bytes = B.host.size();
     cudaGetDevice(&p->device);
@@ -420,7 +438,7 @@ extern "C" int nlpf_problem_create(const nlpf_desc* D, nlpf_problem** out) {
     P.estart = (const int*)(base + oes); P.act = (const int*)(base + oac); P.Hc = (const double*)(base + oHc);
     P.Fc = (const double*)(base + oFc); P.tab = (const uint32_t*)(base + otb); P.ptab = (const uint16_t*)(base + opt);
     P.seg_tab = (const uint16_t*)(base + osg); P.seg_cnt = (const int*)(base + osc);
-    P.sym_tab = (const uint16_t*)(base + osy);
+    P.sym_tab = (const uint16_t*)(base + osy); P.gnz = (const uint8_t*)(base + ogz);
     P.PtP = (const double*)(base + oPP);
     P.Hcp = (const double*)(base + oHp); P.tile_tab = (const uint16_t*)(base + ott); P.tile_cnt = (const int*)(base + otc);
     P.PhiT = (const double*)(base + oPT); P.mslot = (const int*)(base + oms);

@@ -68,6 +68,7 @@ struct DevProb {
     // row is 16-byte aligned), 4-row x 2-column trailing-update tiles rq | ct<<8 sorted by row quad
     const uint16_t* sym_tab;          // general H accumulation: (a | b0<<8) blocks of 4 entries of the lower triangle of G_e
     int nsym;
+    const uint8_t* gnz;               // nsym*E  1: the block is structurally non-zero at that epoch
     const double* PtP;                // npair  sum_e phi_ej phi_el per node pair (constant-weight measurement Hessian)
     const double* Hcp;                // Hc in the padded layout
     const uint16_t* tile_tab;

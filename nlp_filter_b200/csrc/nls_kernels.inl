@@ -794,9 +794,13 @@ __device__ void eval_window(const DevProb& P, double* sm, const double* zc, cons
                 // G_e is symmetric, so block (j,l) of H is too and entry (a,b) also serves (b,a).  (The version
                 // that summed all na x na entries in predicated blocks of 8 was 37 % of the two-receiver kernel.)
                 const int nsym = accH ? P.nsym : 0;
+                // Threads of a warp share the block (consecutive wk = consecutive node pairs), so skipping the epochs
+                // at which the block is structurally zero (P.gnz) is a warp-uniform branch.
                 for (int wk = tid; wk < P.npair * nsym; wk += NLPF_NT) {
-                    const int pr = wk / nsym;
-                    const int se = P.sym_tab[wk - pr * nsym];
+                    const int item = wk / P.npair;
+                    const int pr = wk - item * P.npair;
+                    const int se = P.sym_tab[item];
+                    const uint8_t* nzp = P.gnz + (size_t)item * P.E + c0;
                     const int a = se & 255, b0 = se >> 8;
                     const int pe = P.ptab[pr];
                     const int j = pe & 255, l = pe >> 8;
@@ -805,23 +809,21 @@ __device__ void eval_window(const DevProb& P, double* sm, const double* zc, cons
                     const double* Ga = G + a * nat + b0;
                     const int nb4 = (a - b0 + 1 < 4) ? a - b0 + 1 : 4;
                     if (nb4 == 4) {
-                        for (int el = 0; el < ne; ++el) {
+                        for (int el = 0; el < ne; ++el, ph += K, Ga += nat * nat) {
+                            if (!nzp[el]) continue;
                             const double pp = ph[j] * ph[l];
                             acc[0] = fma(pp, Ga[0], acc[0]);
                             acc[1] = fma(pp, Ga[1], acc[1]);
                             acc[2] = fma(pp, Ga[2], acc[2]);
                             acc[3] = fma(pp, Ga[3], acc[3]);
-                            ph += K;
-                            Ga += nat * nat;
                         }
                     } else {
-                        for (int el = 0; el < ne; ++el) {
+                        for (int el = 0; el < ne; ++el, ph += K, Ga += nat * nat) {
+                            if (!nzp[el]) continue;
                             const double pp = ph[j] * ph[l];
                             acc[0] = fma(pp, Ga[0], acc[0]);
                             if (nb4 > 1) acc[1] = fma(pp, Ga[1], acc[1]);
                             if (nb4 > 2) acc[2] = fma(pp, Ga[2], acc[2]);
-                            ph += K;
-                            Ga += nat * nat;
                         }
                     }
                     const int ca = P.act[a];
