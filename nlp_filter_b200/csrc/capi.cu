@@ -458,6 +458,8 @@ extern "C" int nlpf_problem_create(const nlpf_desc* D, nlpf_problem** out) {
     P.o_Ve = take(P.ec * (na > 0 ? na : 1));
     P.o_G = take(P.ec * P.nat * P.nat);
     P.o_q = take(P.ec * P.nat);
+    // the evaluation scratch [o_f, here) doubles as the W^T side buffer of the tiled LDL^T (BIG instantiation)
+    if (o - P.o_f < 4 * ((nz + 5) & ~1) + 8) take(4 * ((nz + 5) & ~1) + 8 - (o - P.o_f));
     {   // class constants staged in shared memory (default) or read through L1 (NLPF_CONST_SMEM=0: experiments)
         const char* ev = getenv("NLPF_CONST_SMEM");
         P.const_smem = ev ? atoi(ev) : 1;

@@ -963,6 +963,119 @@ __device__ __noinline__ void eval_window_cold(const DevProb& P, double* sm, cons
 //      registers, 4 FMAs per 6 shared-memory accesses instead of 1 per 3.
 // Two barriers per 4 columns; no square roots.
 // ------------------------------------------------------------------------------------------
+#if NLPF_BIG
+// 128-register instantiation: the tiled variant of the warp-per-window kernel (wsolve_kernels.cu: ws_ldl) on the
+// plain packed layout -- scaled factors l = w / d in place, the unscaled panel W^T in a side buffer (the
+// evaluation's scratch, free during the factorisation), 4-row x 2-column register tiles for the trailing
+// update (32 independent FMAs per tile instead of a load -> 4 FMA -> store chain per entry), and a backward
+// sweep without divisions.  The 64-register instantiation keeps the per-entry version below (tiles spill there).
+__device__ bool ldl_solve(const DevProb& P, int nz, double* Hp, double* xs) {
+    const int tid = threadIdx.x;
+    double* Wt = Hp + (P.o_f - P.o_H);
+    const int LD = (nz + 5) & ~1;
+    bool ok = true;
+    for (int j0 = 0; j0 < nz; j0 += 4) {
+        const int pw = min(4, nz - j0);
+        __syncthreads();
+        double a[4][4], l[4][4], d[4], rd[4];
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+#pragma unroll
+            for (int c = 0; c <= r; ++c) a[r][c] = (r < pw) ? Hp[pk(j0 + r, j0 + c)] : (r == c ? 1.0 : 0.0);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+#pragma unroll
+            for (int r = c; r < 4; ++r) {
+                double w = a[r][c];
+#pragma unroll
+                for (int q = 0; q < c; ++q) w = fma(-a[r][q], l[c][q], w);
+                a[r][c] = w;
+            }
+            d[c] = a[c][c];
+            rd[c] = 1.0 / d[c];
+#pragma unroll
+            for (int r = c + 1; r < 4; ++r) l[r][c] = a[r][c] * rd[c];
+        }
+        bool good = true;
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+            if (c < pw && (!(d[c] > 0.0) || !isfinite(d[c]))) good = false;
+        if (!good) { ok = false; break; }
+        const int j1 = j0 + pw;
+        for (int i = j1 + tid; i <= nz; i += NLPF_NT) {
+            double* Hi = Hp + pk(i, j0);
+            double w[4];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                if (c < pw) {
+                    double v = Hi[c];
+#pragma unroll
+                    for (int q = 0; q < c; ++q) v = fma(-w[q], l[c][q], v);
+                    w[c] = v;
+                    Hi[c] = v * rd[c];
+                } else w[c] = 0.0;
+                Wt[c * LD + i] = w[c];
+            }
+        }
+        __syncthreads();
+        if (tid == NLPF_NT - 1) {       // the block in the scaled convention: unit-lower l below the diagonal
+#pragma unroll
+            for (int r = 1; r < 4; ++r)
+#pragma unroll
+                for (int c = 0; c < r; ++c)
+                    if (r < pw) Hp[pk(j0 + r, j0 + c)] = l[r][c];
+        }
+        if (j1 >= nz) continue;
+        const int nitem = P.tile_cnt[nz + 1 - j1];
+        for (int it = tid; it < nitem; it += NLPF_NT) {
+            const int e = P.tile_tab[it];
+            const int i = j1 + ((e & 255) << 2);
+            const int k0 = j1 + ((e >> 8) << 1);
+            double* R[4];
+            R[0] = Hp + pk(i, 0);
+            R[1] = R[0] + i + 1;
+            R[2] = R[1] + i + 2;
+            R[3] = R[2] + i + 3;
+            double x[4][2], wv[4][2];
+#pragma unroll
+            for (int r = 0; r < 4; ++r) { x[r][0] = R[r][k0]; x[r][1] = R[r][k0 + 1]; }
+#pragma unroll
+            for (int c = 0; c < 4; ++c) { wv[c][0] = Wt[c * LD + k0]; wv[c][1] = Wt[c * LD + k0 + 1]; }
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    const double lv = R[r][j0 + c];
+                    x[r][0] = fma(-lv, wv[c][0], x[r][0]);
+                    x[r][1] = fma(-lv, wv[c][1], x[r][1]);
+                }
+            }
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                if (i + r <= nz) {
+                    if (k0 <= i + r && k0 < nz) R[r][k0] = x[r][0];
+                    if (k0 + 1 <= i + r && k0 + 1 < nz) R[r][k0 + 1] = x[r][1];
+                }
+            }
+        }
+    }
+    __syncthreads();
+    if (!ok) return false;
+    // backward sweep by the first warp: y = scaled appended row; x_j = y_j, y_i -= l_ji x_j (i < j)
+    double* y = Hp + pk(nz, 0);
+    if (tid < 32) {
+        for (int j = nz - 1; j >= 0; --j) {
+            const double* Hj = Hp + pk(j, 0);
+            const double xj = y[j];
+            for (int i = tid; i < j; i += 32) y[i] = fma(-Hj[i], xj, y[i]);
+            if (tid == 0) xs[j] = xj;
+            __syncwarp();
+        }
+    }
+    __syncthreads();
+    return true;
+}
+#else
 __device__ bool ldl_solve(const DevProb& P, int nz, double* Hp, double* xs) {
     const int tid = threadIdx.x;
     bool ok = true;
@@ -1059,6 +1172,7 @@ __device__ bool ldl_solve(const DevProb& P, int nz, double* Hp, double* xs) {
     __syncthreads();
     return true;
 }
+#endif
 
 // ------------------------------------------------------------------------------------------
 // shared-memory staging common to the kernels

@@ -202,7 +202,8 @@ class NLP(object):
         dev = lambda a: None if a is None else torch.as_tensor(np.ascontiguousarray(a, dtype=np.float64).reshape(1, -1)).cuda()
         z = dev(z0)
         if opts is None:            # a single problem may iterate as long as IPOPT would (its max_iter default is 3000)
-            opts = D.SolveOpts(max_iter=self.MAX_ITER, max_stage_iter=self.MAX_ITER)
+            # a single problem is latency-, not throughput-bound: the tight step tolerance (the batch default is 1e-9)
+            opts = D.SolveOpts(max_iter=self.MAX_ITER, max_stage_iter=self.MAX_ITER, tol_step=1e-11)
         _, cost, iters, status = prob.solve(z, dev(U), dev(data), dev(xprior), dev(wshift), opts)
         torch.cuda.synchronize()
         return z.cpu().numpy()[0], dict(J=float(cost.item()), iters=int(iters.item()), status=int(status.item()))

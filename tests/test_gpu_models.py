@@ -107,11 +107,16 @@ def test_multi_receiver_shape_with_global_unknowns():
     zr = z0 + rng.normal(0, 0.5, z0.shape)
     _compare(d, zr, np.zeros((B, d.K, 1)), data, loss_tol=1e-9)
     prob = engine.WindowProblem(d)
+    # This class has a nearly flat valley (multi-receiver.py needs 538 iterations; here ~200): both runs end
+    # at the rounding floor of the objective (pseudoranges of 2e7 m squared: 4e-9 absolute on J = 49), and along
+    # the valley a relative change of 1e-10 in J is a relative change of 1e-5 in z.  So the objectives must
+    # agree to the rounding bound, the estimates to what that bound can resolve.
     z, J, iters, status = engine.solve_windows_host(prob, z0, None, data)
     assert np.all(status <= 1)
     for b in range(B):
         zo, info = nls.solve(d, nls.Window(d, data=data[b]), z0[b])
-        assert np.max(np.abs(z[b] - zo) / (1 + np.abs(zo))) < 1e-6
+        assert abs(J[b] - info["J"]) <= 1e-9 * abs(info["J"])
+        assert np.max(np.abs(z[b] - zo) / (1 + np.abs(zo))) < 1e-4
         assert z[b][-1] == 0.0                     # XA[2] never enters the cost and must not move
     prob.close()
 
