@@ -1144,7 +1144,7 @@ int ws_launch(nlpf_problem* p, int B, double* z, const double* U, const double* 
 #define WS_CAR_WARPS 2
 #endif
 #ifndef WS_LIN_WARPS
-#define WS_LIN_WARPS 8
+#define WS_LIN_WARPS 5     // 3 CTAs = 15 windows per SM (measured 5, 6, 7, 8 warps per CTA: 5.29, 5.22, 5.18, 5.12 M windows/s)
 #endif
 typedef WsCfg<21, 2, 1, 50, 2, NLPF_DYN_VDP, 0, WS_LIN_WARPS> CfgVdp;          // van der Pol MHE (BASELINE configs[1])
 typedef WsCfg<21, 2, 2, 50, 2, NLPF_DYN_AFFINE, 0, WS_LIN_WARPS> CfgExample;   // estimation_example.py
