@@ -129,6 +129,48 @@ __device__ __forceinline__ void ws_dyn(const DevProb& P, const double* x, const 
     }
 }
 
+// structural sparsity of the model Jacobian F = df/dx (row r, column c), known at compile time.  The vehicle
+// model has 17 non-zeros of 81; its Hessian terms only visit the entries they can change.
+template <int DYN, int N>
+struct FPat {
+    static constexpr bool SPARSE = false;
+    __host__ __device__ static constexpr bool nz(int, int) { return true; }
+    static constexpr int NFTF = 0;
+    static constexpr unsigned long long FTF_LO = 0;
+    static constexpr unsigned long long FTF_HI = 0;
+};
+template <>
+struct FPat<NLPF_DYN_VEHICLE_GNSS, 9> {
+    static constexpr bool SPARSE = true;
+    __host__ __device__ static constexpr bool nz(int r, int c) {       // the entries ws_dyn writes (dynamics.py:148-174)
+        return (r == 0 || r == 1) ? (c >= 2 && c <= 4) : (r == 2) ? (c == 5) : (r >= 3 && r <= 5) ? (c >= 3 && c <= 5)
+                                                                             : (r == 6) ? (c == 7) : false;
+    }
+    // pairs (a, b <= a) of columns that share a non-zero row: the only entries of F^T Lambda F; a | b << 4, a byte each
+    static constexpr int NFTF = 10;
+    static constexpr unsigned long long FTF_LO = 0x22ULL | (0x23ULL << 8) | (0x24ULL << 16) | (0x33ULL << 24) | (0x34ULL << 32) |
+                                                 (0x44ULL << 40) | (0x35ULL << 48) | (0x45ULL << 56);
+    static constexpr unsigned long long FTF_HI = 0x55ULL | (0x77ULL << 8);
+};
+constexpr bool fpat_check_vehicle() {               // FTF list == { (a,b): exists i with nz(i,a) && nz(i,b) }
+    typedef FPat<NLPF_DYN_VEHICLE_GNSS, 9> P;
+    int cnt = 0;
+    for (int a = 0; a < 9; ++a)
+        for (int b = 0; b <= a; ++b) {
+            bool sh = false;
+            for (int i = 0; i < 9; ++i) sh = sh || (P::nz(i, a) && P::nz(i, b));
+            bool listed = false;
+            for (int p = 0; p < P::NFTF; ++p) {
+                const unsigned code = (unsigned)(((p < 8) ? (P::FTF_LO >> (8 * p)) : (P::FTF_HI >> (8 * (p - 8)))) & 255);
+                if ((int)(code & 15) == a && (int)(code >> 4) == b) listed = true;
+            }
+            if (sh != listed) return false;
+            cnt += sh ? 1 : 0;
+        }
+    return cnt == P::NFTF;
+}
+static_assert(fpat_check_vehicle(), "F^T Lambda F pair list does not match the Jacobian pattern");
+
 // compile-time description of one problem class
 template <int K_, int N_, int M_, int E_, int NM_, int DYN_, int MEAS_, int WARPS_, int NB_ = 0, bool PRIOR_ = false,
           int LOSS_ = NLPF_LOSS_L2>
@@ -307,6 +349,28 @@ __device__ __forceinline__ void ws_eval(const DevProb& P, double* sm, const WsCo
                 const int pe = cs.ptab[pr];
                 const int j = pe & 255, l = pe >> 8;
                 const double djl = Dt[j * K + l], dlj = Dt[l * K + j];
+                if constexpr (FPat<DYN, N>::SPARSE) {
+                    typedef FPat<DYN, N> FP;
+#pragma unroll
+                    for (int a = 0; a < N; ++a) {
+                        double s1 = 0.0;
+                        if (HUB) {
+#pragma unroll
+                            for (int k = 0; k < K; ++k) s1 = fma(Dt[k * K + j] * Dt[k * K + l], wh[k * N + a], s1);
+                        }
+                        const double wla = whv(l, a);
+#pragma unroll
+                        for (int b = 0; b < N; ++b) {
+                            if (!(FP::nz(b, a) || FP::nz(a, b) || (HUB && a == b))) continue;     // folds after unrolling
+                            if (j == l && b > a) continue;
+                            double s = 0.0;
+                            if (FP::nz(b, a)) s = fma(-djl * whv(j, b), Fm[j * N * N + b * N + a], s);
+                            if (FP::nz(a, b)) s = fma(-dlj * wla, Fm[l * N * N + a * N + b], s);
+                            if (HUB && a == b) s += s1;
+                            Hp[pk(j * N + a, l * N + b)] += s;
+                        }
+                    }
+                } else
 #pragma unroll 3
                 for (int a = 0; a < N; ++a) {
                     double s1 = 0.0;
@@ -346,6 +410,19 @@ __device__ __forceinline__ void ws_eval(const DevProb& P, double* sm, const WsCo
             }
             __syncwarp();
             // diagonal blocks: + F_k^T Lambda_k F_k
+            if constexpr (FPat<DYN, N>::SPARSE) {
+                typedef FPat<DYN, N> FP;
+                for (int t = lane; t < K * FP::NFTF; t += 32) {
+                    const int k = t / FP::NFTF, p = t - k * FP::NFTF;
+                    const unsigned code = (unsigned)(((p < 8) ? (FP::FTF_LO >> (8 * p)) : (FP::FTF_HI >> (8 * (p - 8)))) & 255);
+                    const int a = code & 15, b = code >> 4;
+                    const double* Fk = Fm + k * N * N;
+                    double s = 0.0;
+#pragma unroll
+                    for (int i = 0; i < N; ++i) s = fma(Fk[i * N + a] * whv(k, i), Fk[i * N + b], s);
+                    Hp[pk(k * N + a, k * N + b)] += s;
+                }
+            } else
             for (int t = lane; t < K * N * N; t += 32) {
                 const int k = t / (N * N), rem = t - k * N * N, a = rem / N, b = rem - a * N;
                 if (b > a) continue;
