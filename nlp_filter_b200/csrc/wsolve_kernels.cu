@@ -135,9 +135,6 @@ template <int DYN, int N>
 struct FPat {
     static constexpr bool SPARSE = false;
     __host__ __device__ static constexpr bool nz(int, int) { return true; }
-    static constexpr int NFTF = 0;
-    static constexpr unsigned long long FTF_LO = 0;
-    static constexpr unsigned long long FTF_HI = 0;
 };
 template <>
 struct FPat<NLPF_DYN_VEHICLE_GNSS, 9> {
