@@ -100,23 +100,28 @@ __device__ void ekf_dyn_car9(double* x, const double* u, double dt, const double
     J[6 * 9 + 7] += dt;
 }
 
+// MODEL is a template parameter: n and m are compile-time (index arithmetic of the small matrix products folds,
+// loops unroll); the number of warps per CTA is the launch's blockDim (small batches: one filter per CTA so that
+// 256 filters spread over all SMs instead of 64 of them).
+template <int MODEL>
 __global__ void __launch_bounds__(EKF_WARPS * 32)
-ekf_kernel(int model, int B, int steps, int smax, double* __restrict__ mu_io, double* __restrict__ S_io,
+ekf_kernel(int B, int steps, int smax, double* __restrict__ mu_io, double* __restrict__ S_io,
            const double* __restrict__ u, const double* __restrict__ z, const double* __restrict__ sat,
            const int* __restrict__ nsat, const double* __restrict__ Q, double rvar, double dt,
            const double* __restrict__ par, double* __restrict__ traj) {
     extern __shared__ double ekf_sm_raw[];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wpc = blockDim.x >> 5;
     EkfSm& W = reinterpret_cast<EkfSm*>(ekf_sm_raw)[warp];
-    const int n = (model == NLPF_EKF_GNSS5) ? 5 : 9;
-    const int m = (model == NLPF_EKF_GNSS5) ? 3 : 2;
+    constexpr int model = MODEL;
+    constexpr int n = (MODEL == NLPF_EKF_GNSS5) ? 5 : 9;
+    constexpr int m = (MODEL == NLPF_EKF_GNSS5) ? 3 : 2;
     // position / bias columns of the pseudorange model inside the state
     // GNSS5: x,y,z,b = 0,1,2,3 (utils/gnss.py:4-21); CAR9: x,y,z,b = 0,1,8,6 (autonomous-car.py:58-79)
-    const int ix = 0, iy = 1, iz = (model == NLPF_EKF_GNSS5) ? 2 : 8, ib = (model == NLPF_EKF_GNSS5) ? 3 : 6;
+    constexpr int ix = 0, iy = 1, iz = (MODEL == NLPF_EKF_GNSS5) ? 2 : 8, ib = (MODEL == NLPF_EKF_GNSS5) ? 3 : 6;
     double cpar[NLPF_NDYNPAR];
     for (int i = 0; i < NLPF_NDYNPAR; ++i) cpar[i] = par ? par[i] : 0.0;
 
-    for (int f = blockIdx.x * EKF_WARPS + warp; f < B; f += gridDim.x * EKF_WARPS) {
+    for (int f = blockIdx.x * wpc + warp; f < B; f += gridDim.x * wpc) {
         for (int i = lane; i < n; i += 32) W.mu[i] = mu_io[(size_t)f * n + i];
         for (int i = lane; i < n * n; i += 32) W.S[i] = S_io[(size_t)f * n * n + i];
         __syncwarp();
@@ -173,7 +178,8 @@ ekf_kernel(int model, int B, int steps, int smax, double* __restrict__ mu_io, do
                     W.P[s * (EKF_SMAX + 1) + s2] = acc + ((s == s2) ? rvar : 0.0);
                 }
                 __syncwarp();
-                // Cholesky P = L L^T in place (lower), lane = row
+                // Cholesky P = L L^T in place (lower), lane = row.  (A register-resident variant -- rows in registers, the
+                // eliminated column by shuffles, loops unrolled to EKF_SMAX -- was measured at 0.65x of this one.)
                 for (int j = 0; j < ns; ++j) {
                     double djj = sqrt(W.P[j * (EKF_SMAX + 1) + j]);
                     __syncwarp();
@@ -235,15 +241,22 @@ extern "C" int nlpf_ekf_run(int model, int B, int steps, int smax, double* mu_in
     if (B < 1 || steps < 1 || smax < 1 || smax > EKF_SMAX) { nlpf_set_error("bad EKF sizes B=%d steps=%d smax=%d (smax<=%d)", B, steps, smax, EKF_SMAX); return NLPF_E_ARG; }
     if (!mu_inout || !S_inout || !u || !z || !sat || !nsat || !Q) { nlpf_set_error("null EKF buffer"); return NLPF_E_ARG; }
     if (model == NLPF_EKF_CAR9 && !par) { nlpf_set_error("vehicle EKF needs the car constants"); return NLPF_E_ARG; }
-    const size_t smem = sizeof(EkfSm) * EKF_WARPS;
     static bool attr_done = false;
     if (!attr_done) {
-        if (nlpf_check_cuda(cudaFuncSetAttribute(ekf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "ekf smem attr")) return NLPF_E_CUDA;
+        const int full = (int)(sizeof(EkfSm) * EKF_WARPS);
+        if (nlpf_check_cuda(cudaFuncSetAttribute(ekf_kernel<NLPF_EKF_GNSS5>, cudaFuncAttributeMaxDynamicSharedMemorySize, full), "ekf smem attr")) return NLPF_E_CUDA;
+        if (nlpf_check_cuda(cudaFuncSetAttribute(ekf_kernel<NLPF_EKF_CAR9>, cudaFuncAttributeMaxDynamicSharedMemorySize, full), "ekf smem attr")) return NLPF_E_CUDA;
         attr_done = true;
     }
-    int blocks = (B + EKF_WARPS - 1) / EKF_WARPS;
-    ekf_kernel<<<blocks, EKF_WARPS * 32, smem, (cudaStream_t)stream>>>(model, B, steps, smax, mu_inout, S_inout, u, z, sat, nsat,
-                                                                        Q, r, dt, par, mu_traj_out);
+    // filters per CTA: 1 until every SM has a few CTAs, then up to EKF_WARPS
+    int wpc = 1;
+    while (wpc < EKF_WARPS && (B + wpc - 1) / wpc > 148 * 4) wpc *= 2;
+    const size_t smem = sizeof(EkfSm) * wpc;
+    const int blocks = (B + wpc - 1) / wpc;
+    if (model == NLPF_EKF_GNSS5)
+        ekf_kernel<NLPF_EKF_GNSS5><<<blocks, wpc * 32, smem, (cudaStream_t)stream>>>(B, steps, smax, mu_inout, S_inout, u, z, sat, nsat, Q, r, dt, par, mu_traj_out);
+    else
+        ekf_kernel<NLPF_EKF_CAR9><<<blocks, wpc * 32, smem, (cudaStream_t)stream>>>(B, steps, smax, mu_inout, S_inout, u, z, sat, nsat, Q, r, dt, par, mu_traj_out);
     return nlpf_check_cuda(cudaGetLastError(), "ekf_kernel launch");
 }
 
