@@ -1,4 +1,4 @@
-// nls_kernels.cu -- one CTA per estimation window: residual/Jacobian evaluation, structured
+// nls_kernels.inl -- one CTA per estimation window: residual/Jacobian evaluation, structured
 // assembly of the normal equations, in-shared-memory LDL^T and the damped Gauss-Newton /
 // log-barrier iteration, all on chip (fp64).
 //
@@ -16,7 +16,7 @@
 #include "common.cuh"
 #include <math.h>
 
-// This file is compiled twice (nls_kernels_gen.cu, nls_kernels_pr.cu): NLPF_PR_RUNS = 1 adds the
+// This file is compiled four times (nls_kernels_{gen,pr}.cu and their _big twins): NLPF_PR_RUNS = 1 adds the
 // lane-group / register-accumulation path for pseudorange runs.  Keeping it out of the other
 // instantiation matters: with the 64-register cap its 14 accumulators cost the van der Pol
 // kernel 21 % (measured) although that problem class has no pseudoranges at all.

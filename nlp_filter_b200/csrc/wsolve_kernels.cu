@@ -9,7 +9,8 @@
 // tables, 128 threads of which <= 42 had work in most phases, ~70 block barriers per iteration, a
 // 64-register cap.  Here every size is a template parameter (loops unroll, indices fold), one
 // warp owns one window (only __syncwarp), windows are handed out through an atomic counter (no
-// tail behind slow windows), and <= 16 warps/SM leave 128 registers per thread.
+// tail behind slow windows), and <= 16 warps/SM leave 128 registers per thread.  A receding-horizon
+// run (W chained windows) stays in its warp from the first window to the last (WsChain).
 //
 // Same algorithm and decisions as solve_kernel (nls_kernels.inl) and oracle/nls.py: damped
 // Gauss-Newton with the exact second-order dynamics term where the model has one, monotone log
