@@ -226,3 +226,29 @@ def test_empty_measurement_set_and_error_paths():
     bad.resize_nv(30)          # nz = 630 exceeds the shared-memory-resident limit
     with pytest.raises(_capi.NlpfError):
         eng.WindowProblem(bad)
+
+
+@pytest.mark.parametrize("shape", ["vdp", "gnss"])
+def test_bad_window_is_reported_and_does_not_disturb_its_neighbours(shape):
+    """A window with a non-finite measurement gets status NUMERIC (3); the other windows of the batch -- solved
+    by neighbouring warps / CTAs of the same launch -- still match a run without it."""
+    eng = _engine()
+    if shape == "vdp":
+        d = shapes.vdp_mhe()
+        bt = synth.vdp_mhe_batch(d, 40, seed=31)
+    else:
+        d = shapes.gnss()
+        bt = synth.gnss_batch(d, 40, seed=32)
+    prob = eng.WindowProblem(d)
+    ref = eng.solve_windows_host(prob, bt["z0"], bt.get("U"), bt["data"], bt.get("xprior"))
+    data = bt["data"].copy()
+    data[7, 0] = np.nan
+    data[23, 0] = np.inf
+    z, J, iters, status = eng.solve_windows_host(prob, bt["z0"], bt.get("U"), data, bt.get("xprior"))
+    assert status[7] == 3 and status[23] == 3
+    ok = np.ones(40, dtype=bool)
+    ok[[7, 23]] = False
+    assert np.all(status[ok] <= 1)
+    assert np.array_equal(z[ok], ref[0][ok]) and np.array_equal(iters[ok], ref[2][ok])
+    assert np.array_equal(z[7], bt["z0"].reshape(40, -1)[7])          # the start point is returned untouched
+    prob.close()
