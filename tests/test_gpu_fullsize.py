@@ -164,3 +164,33 @@ def test_fused_chain_kernel_equals_the_per_window_loop(monkeypatch):
     pv = engine.WindowProblem(shapes.vdp_mhe())
     assert pv._lib.nlpf_problem_has_chain_kernel(pv._h) == 0
     pv.close()
+
+
+def test_chunked_end_to_end_batches_equal_the_single_chunk_run():
+    """HostBatch cuts a batch into chunks with their own streams, handles and packed staging buffers (what
+    bench.py's e2e leg uses at 4096 windows); chunking must not change a bit of the results."""
+    import torch
+    from nlp_filter_b200 import engine
+    for d, bt in ((shapes.vdp_mhe(), None), (shapes.car(), None)):
+        B = 50
+        if d.has_prior:
+            ch = synth.car_chain_batch(d, B, 1, seed=41)
+            z0, U, data, xp = np.zeros((B, d.nz)), ch["U"][0], ch["data"][0], ch["xhat0"]
+        else:
+            b2 = synth.vdp_mhe_batch(d, B, seed=42)
+            z0, U, data, xp = b2["z0"], b2["U"], b2["data"], None
+        prob = engine.WindowProblem(d)
+        outs = []
+        for nchunk in (1, 3, 7):
+            hb = engine.HostBatch(prob, B, nchunk=nchunk)
+            assert hb.nchunk == nchunk
+            hb.load(z0, U, data, xp)
+            hb.run()
+            hb.run()                                   # staged inputs survive a run
+            torch.cuda.synchronize()
+            outs.append([a.copy() for a in hb.results()] + [hb.device_z().cpu().numpy()])
+        for o in outs[1:]:
+            for a, b in zip(o, outs[0]):
+                assert np.array_equal(a, b)
+        assert np.array_equal(outs[0][0], outs[0][4]) and np.all(outs[0][3] <= 1)
+        prob.close()
