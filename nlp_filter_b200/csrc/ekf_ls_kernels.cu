@@ -193,7 +193,9 @@ ekf_kernel(int B, int steps, int smax, double* __restrict__ mu_io, double* __res
                     }
                     __syncwarp();
                 }
-                // K^T = P^-1 (H S_pred): one right-hand-side column per lane (K = S_pred H^T P^-1)
+                // K^T = P^-1 (H S_pred): one right-hand-side column per lane (K = S_pred H^T P^-1).  (Column-oriented
+                // substitutions with lane = row were measured at 0.74x: the pivot's n divisions then run one after the
+                // other in a single lane instead of side by side in n lanes.)
                 for (int c = lane; c < n; c += 32) {
                     for (int s = 0; s < ns; ++s) {
                         double acc = W.HS[s * n + c];
