@@ -446,29 +446,50 @@ extern "C" int nlpf_problem_create(const nlpf_desc* D, nlpf_problem** out) {
     P.run_len = (const int*)(base + orn); P.run_loc = (const int*)(base + orc);
 
     // ---- shared-memory layout (doubles) ----
-    int o = 0;
-    auto take = [&](int cnt) { int r = o; o += (cnt + 1) & ~1; return r; };
-    P.o_H = take((nz + 1) * (nz + 2) / 2);
-    P.o_z = take(nz); P.o_zt = take(nz); P.o_g = take(nz); P.o_ds = take(nz); P.o_dd = take(nz); P.o_dz = take(nz);
-    P.o_f = take(K * n); P.o_lw = take(K * n); P.o_wh = take(K * n); P.o_slw = take(K * nv); P.o_whs = take(K * nv);
-    const bool needF = !P.hconst;
-    P.o_F = take(needF ? K * n * nv : 0);
-    P.o_GF = take(needF ? K * nv * nv : 0);
-    P.o_FF = take(needF ? K * nv * nv : 0);
-    P.o_Ve = take(P.ec * (na > 0 ? na : 1));
-    P.o_G = take(P.ec * P.nat * P.nat);
-    P.o_q = take(P.ec * P.nat);
-    // the evaluation scratch [o_f, here) doubles as the W^T side buffer of the tiled LDL^T (BIG instantiation)
-    if (o - P.o_f < 4 * ((nz + 5) & ~1) + 8) take(4 * ((nz + 5) & ~1) + 8 - (o - P.o_f));
-    {   // class constants staged in shared memory (default) or read through L1 (NLPF_CONST_SMEM=0: experiments)
-        const char* ev = getenv("NLPF_CONST_SMEM");
-        P.const_smem = ev ? atoi(ev) : 1;
+    auto do_layout = [&]() {
+        int o = 0;
+        auto take = [&](int cnt) { int r = o; o += (cnt + 1) & ~1; return r; };
+        P.o_H = take((nz + 1) * (nz + 2) / 2);
+        P.o_z = take(nz); P.o_zt = take(nz); P.o_g = take(nz); P.o_ds = take(nz); P.o_dd = take(nz); P.o_dz = take(nz);
+        P.o_f = take(K * n); P.o_lw = take(K * n); P.o_wh = take(K * n); P.o_slw = take(K * nv); P.o_whs = take(K * nv);
+        const bool needF = !P.hconst;
+        P.o_F = take(needF ? K * n * nv : 0);
+        P.o_GF = take(needF ? K * nv * nv : 0);
+        P.o_FF = take(needF ? K * nv * nv : 0);
+        P.o_Ve = take(P.ec * (na > 0 ? na : 1));
+        P.o_G = take(P.ec * P.nat * P.nat);
+        P.o_q = take(P.ec * P.nat);
+        // the evaluation scratch [o_f, here) doubles as the W^T side buffer of the tiled LDL^T (BIG instantiation)
+        if (o - P.o_f < 4 * ((nz + 5) & ~1) + 8) take(4 * ((nz + 5) & ~1) + 8 - (o - P.o_f));
+        {   // class constants staged in shared memory (default) or read through L1 (NLPF_CONST_SMEM=0: experiments)
+            const char* ev = getenv("NLPF_CONST_SMEM");
+            P.const_smem = ev ? atoi(ev) : 1;
+        }
+        P.o_Phi = take(P.const_smem ? E * K : 0);
+        P.o_Dt = take(P.const_smem ? K * K : 0);
+        P.o_red = take(32);
+        P.smem_doubles = o;
+        p->smem_bytes = (size_t)o * sizeof(double);
+    };
+    do_layout();
+    // Classes that fit at most 5 windows per SM anyway (two-receiver, RC, multi-receiver): spend the shared memory
+    // a 4-window residency leaves on longer epoch chunks -- fewer passes (barriers, read-modify-writes of H) over
+    // the measurement phase.
+    if ((227 * 1024) / (p->smem_bytes + 1024) <= 5 && E > 0) {
+        const int ctas0 = (int)((227 * 1024) / (p->smem_bytes + 1024));
+        const int keep = ctas0 < 4 ? ctas0 : 4;
+        const int ec0 = P.ec;
+        int best = ec0;
+        for (int ec = ec0 + 1; ec <= E && ec <= NLPF_NT; ++ec) {
+            P.ec = ec;
+            do_layout();
+            if ((int)((227 * 1024) / (p->smem_bytes + 1024)) >= keep && keep >= 1) best = ec; else break;
+        }
+        // whole chunks of equal size: the smallest chunk length with the same number of chunks
+        const int nch = (E + best - 1) / best;
+        P.ec = (E + nch - 1) / nch;
+        do_layout();
     }
-    P.o_Phi = take(P.const_smem ? E * K : 0);
-    P.o_Dt = take(P.const_smem ? K * K : 0);
-    P.o_red = take(32);
-    P.smem_doubles = o;
-    p->smem_bytes = (size_t)o * sizeof(double);
     if (p->smem_bytes > 227 * 1024) {
         nlpf_set_error("problem needs %zu bytes of shared memory per window (limit 232448)", p->smem_bytes);
         cudaFree(p->blob); delete p; return NLPF_E_ARG;
