@@ -503,7 +503,9 @@ __device__ __forceinline__ void ws_eval(const DevProb& P, double* sm, const WsCo
             double g00 = 0, g10 = 0, g11 = 0, g20 = 0, g21 = 0, g22 = 0, g30 = 0, g31 = 0, g32 = 0, g33 = 0;
             // records of the epoch's slots are fetched four at a time before any arithmetic (20 loads in
             // flight per lane: the slot-by-slot version spent a third of the kernel waiting on L2)
-#pragma unroll
+            // (not unrolled over the batches: with all 12 slots in straight-line code the vehicle kernel was 1.7 %
+            // and the GNSS kernel 0.7 % slower -- instruction fetch, see the no_instructions stalls in profiles/)
+#pragma unroll 1
             for (int s0 = 0; s0 < NM; s0 += 4) {
                 double ry[4], rw[4], rx[4], rY[4], rz[4];
 #pragma unroll
