@@ -299,7 +299,7 @@ def run_aux(args):
             "e2e": {"value": units * args.steps / (ms_e2e * 1e-3), "unit": unit, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": args.steps,
-            "roofline": {"bound": "fp64", "kernel": "ekf_kernel" if args.workload == "ekf" else "ls_kernel<4>",
+            "roofline": {"bound": "fp64", "bound_note": "compute-bound on the FP64 FMA pipe; the contract's vocabulary is hbm|tensor: B200 has no FP64 tcgen05 kind and its FP64 mma.sync peak (nlpf_dmma_probe: 36.7 TFLOP/s) equals the vector peak used here", "kernel": "ekf_kernel" if args.workload == "ekf" else "ls_kernel<4>",
                          "achieved": achieved, "peak": peak_fp64, "unit": "TFLOP/s", "frac": achieved / peak_fp64,
                          "traffic": None, "kernel_ms": ms_kernel,
                          "peak_source": "FP64 FMA probe measured in this run",
@@ -420,7 +420,7 @@ def run_car(args):
                     "h2d_bytes_per_step": int(hU.numel() * 8 + hdata.numel() * 8), "d2h_bytes_per_step": int(h_out.numel() * 8),
                     "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": args.steps * (W * 2 if os.environ.get("NLPF_CHAIN_LOOP") else 1),
-            "roofline": {"bound": "fp64", "kernel": "wsolve_kernel<CfgCar> (fused chain: all windows of a run in one warp, one launch per step)",
+            "roofline": {"bound": "fp64", "bound_note": "compute-bound on the FP64 FMA pipe; the contract's vocabulary is hbm|tensor: B200 has no FP64 tcgen05 kind and its FP64 mma.sync peak (nlpf_dmma_probe: 36.7 TFLOP/s) equals the vector peak used here", "kernel": "wsolve_kernel<CfgCar> (fused chain: all windows of a run in one warp, one launch per step)",
                          "achieved": achieved, "peak": peak_fp64, "unit": "TFLOP/s",
                          "frac": achieved / peak_fp64, "traffic": _traffic("car") if (B, W) == (2048, 25) else None, "kernel_ms": ms_step,
                          "peak_source": "FP64 FMA probe measured in this run"},
@@ -639,7 +639,7 @@ def run_ours(args):
             "e2e": {"value": e2e, "unit": "windows/s", "h2d_bytes_per_step": hb.h2d_bytes, "d2h_bytes_per_step": hb.d2h_bytes,
                     "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": args.steps,
-            "roofline": {"bound": "fp64", "kernel": {"vdp": "wsolve_kernel<CfgVdp>", "gnss": "wsolve_kernel<CfgGnss>", "2rx": "solve_kernel_pr"}[args.workload], "achieved": achieved, "peak": peak_fp64,
+            "roofline": {"bound": "fp64", "bound_note": "compute-bound on the FP64 FMA pipe; the contract's vocabulary is hbm|tensor: B200 has no FP64 tcgen05 kind and its FP64 mma.sync peak (nlpf_dmma_probe: 36.7 TFLOP/s) equals the vector peak used here", "kernel": {"vdp": "wsolve_kernel<CfgVdp>", "gnss": "wsolve_kernel<CfgGnss>", "2rx": "solve_kernel_prb"}[args.workload], "achieved": achieved, "peak": peak_fp64,
                          "unit": "TFLOP/s", "frac": achieved / peak_fp64 if peak_fp64 > 0 else None,
                          "traffic": traffic, "kernel_ms": ms_kernel,
                          "peak_source": "FP64 FMA probe (nlpf_fp64_probe) measured in this run; MEASURED_PEAKS.json "
