@@ -135,8 +135,11 @@ def test_vehicle_chains_against_oracle_and_truth():
 def test_fused_chain_kernel_equals_the_per_window_loop(monkeypatch):
     """nlpf_solve_chain (every run's windows back to back in one warp) against the host loop of
     nlpf_solve + nlpf_sample launches it replaces: same kernel code per window, so identical results."""
+    import os
     import torch
     from nlp_filter_b200 import engine
+    if os.environ.get("NLPF_NO_WARP_KERNEL"):
+        pytest.skip("the fused chain lives in the warp-per-window kernel, which this run disables")
     for loss in (D.LOSS_L2, D.LOSS_HUBER):
         d = shapes.car(loss=loss)
         B, W = 96, 4
