@@ -43,3 +43,29 @@ def test_version_and_loud_failure_without_gpu():
     h = ctypes.c_void_p()
     rc = L.nlpf_problem_create(ctypes.byref(cdesc), ctypes.byref(h))
     assert rc == -3 and b"no CUDA device" in L.nlpf_last_error()
+
+
+def test_ctypes_struct_mirrors_match_the_header_layout(tmp_path):
+    """sizeof / offsetof of nlpf_desc and nlpf_opts as the C compiler sees them in include/nlpfilter.h against
+    the ctypes mirrors in _capi.py (the binding INTEGRATION.md shows relies on exactly this layout)."""
+    import shutil
+    import subprocess
+    if shutil.which("gcc") is None:
+        pytest.skip("no C compiler")
+    fields_d = [f[0] for f in _capi.CDesc._fields_]
+    fields_o = [f[0] for f in _capi.COpts._fields_]
+    src = ['#include <stdio.h>', '#include <stddef.h>', '#include "nlpfilter.h"', 'int main(void) {',
+           '  printf("desc %zu\\n", sizeof(nlpf_desc)); printf("opts %zu\\n", sizeof(nlpf_opts));']
+    src += ['  printf("d.%s %%zu\\n", offsetof(nlpf_desc, %s));' % (f, f) for f in fields_d]
+    src += ['  printf("o.%s %%zu\\n", offsetof(nlpf_opts, %s));' % (f, f) for f in fields_o]
+    src += ['  return 0; }']
+    c = tmp_path / "layout.c"
+    c.write_text("\n".join(src))
+    exe = tmp_path / "layout"
+    subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(c), "-o", str(exe)], check=True)
+    out = dict(l.split() for l in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.splitlines())
+    assert int(out["desc"]) == ctypes.sizeof(_capi.CDesc) and int(out["opts"]) == ctypes.sizeof(_capi.COpts)
+    for f in fields_d:
+        assert int(out["d." + f]) == getattr(_capi.CDesc, f).offset, f
+    for f in fields_o:
+        assert int(out["o." + f]) == getattr(_capi.COpts, f).offset, f
