@@ -22,10 +22,11 @@
 #include <math.h>
 
 #ifndef WS_DMMA
-#define WS_DMMA 0         // 1: measurement Hessian of the pseudorange shapes on the FP64 tensor cores (mma.sync
-                          // m8n8k4).  Measured on B200: DMMA peak 36.7 TFLOP/s = the vector FMA peak (36.1), and the
-                          // GNSS batch runs at 2.37 M windows/s with it against 2.38 M without (parity tests pass either
-                          // way), so the vector path stays the default (BASELINE.json: "DMMA only if it benefits").
+#define WS_DMMA 1         // measurement Hessian of the pseudorange shapes on the FP64 tensor cores (mma.sync m8n8k4).
+                          // Measured on B200: DMMA peak 36.7 TFLOP/s = the vector FMA peak (36.1) -- same pipe -- so the
+                          // gain is issue slots only: GNSS batch 3.17-3.18 M windows/s with it, 3.12-3.13 M without
+                          // (+1.6 %, two alternating runs each; neutral when first tried on a slower kernel); vehicle
+                          // chains unchanged.  BASELINE.json: "DMMA only if the contraction benefits" -- it does, a little.
 #endif
 
 namespace {
