@@ -54,9 +54,14 @@ extern "C" {
 
 /* solve status per window */
 #define NLPF_ST_CONVERGED 0
-#define NLPF_ST_STALLED 1     /* no damping produced a decrease: stationary to rounding */
+#define NLPF_ST_STALLED 1     /* no damping produced a decrease AND the point is stationary to rounding:
+                                 max_i |g_i| / H_ii (the diagonally scaled gradient step) < 1e-6 (1 + |z|_inf) */
 #define NLPF_ST_MAXITER 2
 #define NLPF_ST_NUMERIC 3     /* non-finite objective at the starting point */
+#define NLPF_ST_NOSTEP 4      /* no damping produced a decrease at a point that is NOT stationary (every
+                                 factorisation failed or every step was non-finite): a failure, where
+                                 opti.solve() of the reference would raise (nlp/nlp.py:82) */
+#define NLPF_STALL_GTOL 1e-6
 
 /* Problem class = everything the reference fixes when a script has finished calling
  * addVariables/addDynamics/addDynamicsCost/addResidualCost/addInitialCost/addVarBounds/

@@ -181,6 +181,17 @@ extern "C" int nlpf_problem_create(const nlpf_desc* D, nlpf_problem** out) {
             nlpf_set_error("residual %d: range dimension must be 1..3", i); delete p; return NLPF_E_ARG;
         }
     }
+    for (int i = 0; i < M; ++i) {          // state / global indices, before anything dereferences cmap[ridx[..]]
+        int is_state[NLPF_NIDX], is_glob[NLPF_NIDX];
+        const int* idx = D->ridx + i * NLPF_NIDX;
+        slot_roles(D->rtype[i], idx, is_state, is_glob);
+        for (int s = 0; s < NLPF_NIDX; ++s) {
+            if (is_state[s] && (idx[s] < 0 || idx[s] >= n)) { nlpf_set_error("residual %d: state index %d out of range", i, idx[s]); delete p; return NLPF_E_ARG; }
+            if (is_glob[s] && idx[s] >= ng) { nlpf_set_error("residual %d: global index out of range", i); delete p; return NLPF_E_ARG; }
+        }
+    }
+    for (int i = 0; i < n; ++i)
+        if (D->cmap[i] < 0 || D->cmap[i] >= nv) { nlpf_set_error("cmap[%d] = %d outside the %d node variables", i, D->cmap[i], nv); delete p; return NLPF_E_ARG; }
     // order: by epoch; inside an epoch pseudoranges first, grouped by their index quadruple (runs), then the rest
     auto key = [&](int i, int s) { return D->rtype[i] == NLPF_RT_PR ? D->cmap[D->ridx[i * NLPF_NIDX + s]] : 0; };
     std::stable_sort(order.begin(), order.end(), [&](int a, int b) {

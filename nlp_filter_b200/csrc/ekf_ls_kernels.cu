@@ -149,7 +149,7 @@ ekf_kernel(int B, int steps, int smax, double* __restrict__ mu_io, double* __res
                 W.Sp[e] = s + ((i == j) ? Q[i] : 0.0);
             }
             __syncwarp();
-            const int ns = nsat[ft];
+            const int ns = min(max(nsat[ft], 0), smax);      // counts come from device memory: never index past the slots
             if (ns > 0) {
                 // ---- correct (ekf.py:46-61) ----
                 for (int s = lane; s < ns; s += 32) {
@@ -306,7 +306,7 @@ ls_kernel(int B, int smax, const double* __restrict__ sat, const double* __restr
     for (int e = wglob; e < B; e += nwarps) {
         double x[NU];
         for (int i = 0; i < NU; ++i) x[i] = x_io[(size_t)e * NU + i];
-        const int ns = nsat[e];
+        const int ns = min(max(nsat[e], 0), smax);
         const double* se = sat + (size_t)e * smax * 3;
         const double* pe = pr + (size_t)e * smax;
         const double* te = tcol ? tcol + (size_t)e * smax : nullptr;
@@ -372,7 +372,7 @@ ls_vel_kernel(int B, int smax, const double* __restrict__ sat, const double* __r
     const int wglob = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int nwarps = (gridDim.x * blockDim.x) >> 5;
     for (int e = wglob; e < B; e += nwarps) {
-        const int ns = nsat[e];
+        const int ns = min(max(nsat[e], 0), smax);
         const double* se = sat + (size_t)e * smax * 3;
         const double* ve = satvel + (size_t)e * smax * 3;
         const double* pe = prr + (size_t)e * smax;

@@ -1437,10 +1437,27 @@ VN(solve_kernel)(const __grid_constant__ DevProb P, int B, double* __restrict__ 
                     }
                     if (!accepted) {
                         status = NLPF_ST_STALLED;
-                        if (!h_valid) {   // leave H, g consistent with z for a following stage
+                        if (!h_valid) {   // leave H, g consistent with z for the stationarity test and a following stage
                             double Jd, md, nd;
                             eval_window_cold(P, sm, zs, wp, mu, Jd, md, nd, hmode);
                         }
+                        // "stalled" is a success only at a stationary point: the diagonally scaled gradient step must
+                        // be below NLPF_STALL_GTOL (NaN fails the test); otherwise the window is reported as failed
+                        double sg = 0.0, zmx = 0.0, nang = 0.0;
+                        for (int i = tid; i < nz; i += NLPF_NT) {
+                            const double q = fabs(g[i]) / (dd[i] + 1e-14 * dm + 1e-300);
+                            if (!(q == q)) nang = 1.0;
+                            sg = fmax(sg, q);
+                            zmx = fmax(zmx, fabs(zs[i]));
+                        }
+                        {
+                            double rv[3] = {sg, zmx, nang};
+                            block_reduce<0, 3>(rv, red);
+                            sg = rv[0];
+                            zmx = rv[1];
+                            nang = rv[2];
+                        }
+                        if (nang > 0.0 || !(sg <= NLPF_STALL_GTOL * (1.0 + zmx))) status = NLPF_ST_NOSTEP;
                         break;
                     }
                     const double step = alpha * dzmax;

@@ -1035,7 +1035,7 @@ wsolve_kernel(const __grid_constant__ DevProb P, int B, double* __restrict__ z_i
         //   EV_TRIAL  at the trial point z - alpha dz          EV_RESTORE / EV_STALL  H, g back at z after a
         //                                                       rejected step (the factorisation overwrote H)
         enum { EV_FIRST, EV_STAGE, EV_TRIAL, EV_RESTORE, EV_STALL };
-        enum { PC_STAGE_INIT, PC_ITER_TOP, PC_LAM_TOP, PC_SOLVE, PC_AFTER_TRIAL, PC_STAGE_END };
+        enum { PC_STAGE_INIT, PC_ITER_TOP, PC_LAM_TOP, PC_SOLVE, PC_AFTER_TRIAL, PC_STALL_CHECK, PC_STAGE_END };
         double mu = BND ? opt.mu0 : 0.0;
         int iters = 0, status = NLPF_ST_MAXITER, stage_steps = 0, floor_steps = 0;
         double lam = opt.lam0, J = 0.0, merit = 0.0, nse0 = 0.0;
@@ -1050,7 +1050,7 @@ wsolve_kernel(const __grid_constant__ DevProb P, int B, double* __restrict__ z_i
                 else if (ev == EV_FIRST || ev == EV_STAGE) { J = Je; merit = me; nse0 = ne; }
             }
             if (ev == EV_FIRST && !isfinite(merit)) { status = NLPF_ST_NUMERIC; break; }
-            int pc = (ev == EV_TRIAL) ? PC_AFTER_TRIAL : (ev == EV_RESTORE) ? PC_SOLVE : (ev == EV_STALL) ? PC_STAGE_END : PC_STAGE_INIT;
+            int pc = (ev == EV_TRIAL) ? PC_AFTER_TRIAL : (ev == EV_RESTORE) ? PC_SOLVE : (ev == EV_STALL) ? PC_STALL_CHECK : PC_STAGE_INIT;
             bool need_eval = false, finished = false;
             while (!need_eval) {
                 if (pc == PC_STAGE_INIT) {
@@ -1078,8 +1078,8 @@ wsolve_kernel(const __grid_constant__ DevProb P, int B, double* __restrict__ z_i
                 } else if (pc == PC_LAM_TOP) {
                     if (!(lam <= 1e18)) {   // no acceptable step
                         status = NLPF_ST_STALLED;
-                        if (BND && !h_valid) { ev = EV_STALL; need_eval = true; continue; }   // H, g consistent for a following stage
-                        pc = PC_STAGE_END;
+                        if (!h_valid) { ev = EV_STALL; need_eval = true; continue; }   // H, g back at z (stationarity test, next stage)
+                        pc = PC_STALL_CHECK;
                         continue;
                     }
                     if (!h_valid) { h_valid = true; ev = EV_RESTORE; need_eval = true; continue; }
@@ -1151,6 +1151,22 @@ wsolve_kernel(const __grid_constant__ DevProb P, int B, double* __restrict__ z_i
                     pc = PC_ITER_TOP;
                     if (step < opt.tol_step * (1.0 + zm)) { status = NLPF_ST_CONVERGED; pc = PC_STAGE_END; }
                     else if (at_floor && ++floor_steps >= 5) { status = NLPF_ST_CONVERGED; pc = PC_STAGE_END; }
+                } else if (pc == PC_STALL_CHECK) {
+                    // "stalled" is a success only at a stationary point: the diagonally scaled gradient step must be
+                    // below NLPF_STALL_GTOL (NaN fails the test); otherwise the window is reported as failed
+                    double sg = 0.0, zm = 0.0;
+                    bool nan_g = false;
+                    for (int i = lane; i < NZ; i += 32) {
+                        const double q = fabs(g[i]) / (dd[i] + 1e-14 * dm + 1e-300);
+                        nan_g = nan_g || !(q == q);
+                        sg = fmax(sg, q);
+                        zm = fmax(zm, fabs(zs[i]));
+                    }
+                    sg = wmax(sg);
+                    zm = wmax(zm);
+                    nan_g = __any_sync(0xffffffffu, nan_g);
+                    if (nan_g || !(sg <= NLPF_STALL_GTOL * (1.0 + zm))) status = NLPF_ST_NOSTEP;
+                    pc = PC_STAGE_END;
                 } else {   // PC_STAGE_END
                     if (!BND || mu <= opt.mu_min || iters >= opt.max_iter) { finished = true; break; }
                     mu = fmax(opt.mu_min, fmin(0.2 * mu, mu * sqrt(mu)));

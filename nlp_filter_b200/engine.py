@@ -36,6 +36,19 @@ def _stream():
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
+def _want(name, t, shape):
+    """Raise on a wrong dtype / device / element count before a raw pointer reaches the library (a wrong shape
+    would otherwise be a silent out-of-bounds access on the device)."""
+    if t is None:
+        raise _capi.NlpfError("%s is required for this problem class (expected shape %s)" % (name, shape))
+    if not (isinstance(t, torch.Tensor) and t.is_cuda and t.dtype == torch.float64 and t.is_contiguous()):
+        raise _capi.NlpfError("%s must be a contiguous float64 CUDA tensor" % name)
+    want = int(np.prod(shape))
+    if t.numel() != want:
+        raise _capi.NlpfError("%s has %d elements, expected %s = %d" % (name, t.numel(), "x".join(map(str, shape)), want))
+    return t
+
+
 def _f8(t, shape=None):
     if t is None:
         return None
@@ -78,6 +91,7 @@ class WindowProblem(object):
         z = _f8(z, (-1, d.nz))
         B = z.shape[0]
         U, data, xprior, wshift = _f8(U), _f8(data), _f8(xprior), _f8(wshift)
+        self._check_inputs(B, U, data, xprior, wshift)
         H = torch.empty((B, d.nz, d.nz), dtype=torch.float64, device=z.device)
         g = torch.empty((B, d.nz), dtype=torch.float64, device=z.device)
         cost = torch.empty((B, 2), dtype=torch.float64, device=z.device)
@@ -101,8 +115,11 @@ class WindowProblem(object):
         """z (B, nz) CUDA tensor: initial guess in, minimiser out (in place).
         Returns (z, cost, iters, status) device tensors; nothing is synchronised."""
         d = self.desc
-        assert z.is_cuda and z.dtype == torch.float64 and z.is_contiguous()
+        if z.dim() != 2 or z.shape[1] != d.nz:
+            raise _capi.NlpfError("z must have shape (B, %d), got %s" % (d.nz, tuple(z.shape)))
         B = z.shape[0]
+        _want("z", z, (B, d.nz))
+        self._check_inputs(B, U, data, xprior, wshift)
         copts = _capi.make_copts(opts or SolveOpts())
         if out is None:
             cost = torch.empty((B,), dtype=torch.float64, device=z.device)
@@ -113,6 +130,17 @@ class WindowProblem(object):
         _capi.check(self._lib.nlpf_solve(self._h, B, _ptr(z), _ptr(U), _ptr(data), _ptr(xprior), _ptr(wshift),
                                          ctypes.byref(copts), _ptr(cost), _ptr(iters), _ptr(status), _stream()))
         return z, cost, iters, status
+
+    def _check_inputs(self, B, U, data, xprior, wshift, W=1):
+        d = self.desc
+        if d.m > 0 and any(c < 0 for c in np.asarray(d.ucol).reshape(-1)[:d.m]):   # parameter controls
+            _want("U", U, (W, B, d.K, d.m) if W > 1 else (B, d.K, d.m))
+        if d.Ldata > 0:
+            _want("data", data, (W, B, d.Ldata) if W > 1 else (B, d.Ldata))
+        if d.has_prior:
+            _want("xprior", xprior, (B, d.n))
+        if wshift is not None:
+            _want("wshift", wshift, (B, d.K, d.n))
 
     def sample(self, z, PhiT):
         d = self.desc
@@ -248,6 +276,13 @@ def solve_chain(prob, z, U_all, data_all, xprior, PhiDT, opts=None, keep=False):
     Returns (iters_sum (B,), bad (B,) windows that did not converge[, Z (W, B, nz)])."""
     d = prob.desc
     W, B = data_all.shape[0], z.shape[0]
+    _want("z", z, (B, d.nz))
+    if not (xprior.is_cuda and xprior.dtype == torch.float64 and xprior.numel() == B * d.n):
+        raise _capi.NlpfError("xprior must be a float64 CUDA tensor of shape (%d, %d)" % (B, d.n))
+    if data_all.dim() != 3 or data_all.shape[1] != B or data_all.shape[2] != max(d.Ldata, 1):
+        raise _capi.NlpfError("data_all must have shape (W, %d, %d), got %s" % (B, d.Ldata, tuple(data_all.shape)))
+    if d.m > 0 and U_all is not None and tuple(U_all.shape) != (W, B, d.K, d.m):
+        raise _capi.NlpfError("U_all must have shape (%d, %d, %d, %d), got %s" % (W, B, d.K, d.m, tuple(U_all.shape)))
     cost = torch.empty((B,), dtype=torch.float64, device=z.device)
     iters = torch.empty((B,), dtype=torch.int32, device=z.device)
     status = torch.empty((B,), dtype=torch.int32, device=z.device)
@@ -307,7 +342,16 @@ def ekf_run(model, mu, S, u, z, sat, nsat, Q, r, dt, par=None, want_traj=True):
     B, n = mu.shape
     u, z, sat = _f8(u), _f8(z), _f8(sat)
     steps, smax = z.shape[1], z.shape[2]
+    if smax > 16:
+        raise _capi.NlpfError("ekf_run: at most 16 satellite slots per step, got %d" % smax)
+    if isinstance(nsat, np.ndarray) and nsat.size and (nsat.max() > smax or nsat.min() < 0):
+        raise _capi.NlpfError("ekf_run: nsat outside [0, %d]" % smax)
     nsat = torch.as_tensor(nsat).to(device=mu.device, dtype=torch.int32).contiguous()
+    for name, t, shape in (("S", S, (B, n, n)), ("z", z, (B, steps, smax)), ("sat", sat, (B, steps, smax, 3)),
+                           ("Q", _f8(Q), (n,))):
+        _want(name, t, shape)
+    if nsat.numel() != B * steps:
+        raise _capi.NlpfError("ekf_run: nsat has %d entries, expected %d" % (nsat.numel(), B * steps))
     Q = _f8(Q)
     par_t = _f8(np.concatenate([np.asarray(par, float), np.zeros(16 - len(par))])) if par is not None else None
     traj = torch.empty((B, steps, n), dtype=torch.float64, device=mu.device) if want_traj else None
@@ -323,7 +367,12 @@ def ls_solve(sat, pr, nsat, x0=None, tcol=None, maxiter=100, tol=1e-7):
     L = _capi.lib()
     sat, pr = _f8(sat), _f8(pr)
     B, smax = pr.shape
+    if isinstance(nsat, np.ndarray) and nsat.size and (nsat.max() > smax or nsat.min() < 0):
+        raise _capi.NlpfError("ls_solve: nsat outside [0, %d]" % smax)
     nsat = torch.as_tensor(nsat).to(device=sat.device, dtype=torch.int32).contiguous()
+    _want("sat", sat, (B, smax, 3))
+    if nsat.numel() != B:
+        raise _capi.NlpfError("ls_solve: nsat has %d entries, expected %d" % (nsat.numel(), B))
     nu = 5 if tcol is not None else 4
     x = torch.zeros((B, nu), dtype=torch.float64, device=sat.device) if x0 is None else _f8(x0, (B, nu)).clone()
     tc = _f8(tcol) if tcol is not None else None

@@ -154,9 +154,13 @@ class NLP(object):
         t0 = time.perf_counter()
         z, info = self._solve_device(z0)
         wall = time.perf_counter() - t0
+        # 0 converged; 1 stalled AT a stationary point (the kernel checked the scaled gradient); 2 iteration limit;
+        # 3 non-finite objective at the start; 4 no acceptable step at a non-stationary point -- IPOPT's names
         ok = info["status"] in (0, 1)
+        names = {0: "Solve_Succeeded", 1: "Solve_Succeeded", 2: "Maximum_Iterations_Exceeded",
+                 3: "Invalid_Number_Detected", 4: "Error_In_Step_Computation"}
         self.solver = {"t_wall_total": wall, "t_proc_total": wall, "iter_count": int(info["iters"]),
-                       "return_status": "Solve_Succeeded" if ok else "Maximum_Iterations_Exceeded",
+                       "return_status": names.get(int(info["status"]), "Internal_Error"),
                        "success": bool(ok), "objective": float(info["J"])}
         if not ok:
             raise RuntimeError("solver did not converge (status %d after %d iterations)" % (info["status"], info["iters"]))
@@ -316,9 +320,9 @@ class fixedTimeOptimalControlNLP(NLP):
         V = z.reshape(K, n + m)
         W = (2.0 / self.T) * (self.CPM.D @ V[:, :n])
         for k in range(K):
-            f = func(V[k, :n], V[k, n:] if m > 1 or func in (_dyn.single_integrator,) else V[k, n], params) \
-                if params is not None else func(V[k, :n], V[k, n:] if m > 1 else V[k, n])
-            W[k] -= np.asarray(f, dtype=float).reshape(-1)
+            # u is always handed over as a 1-D array, as the reference's MX.sym('U', m) is (nlp.py:143-148) and as
+            # _lower_dynamics probed the callable
+            W[k] -= _call_dyn(func, V[k, :n], V[k, n:], m, params)
         return W
 
     def _solve_device(self, z0):
@@ -483,10 +487,21 @@ class fixedTimeOptimalEstimationNLP(NLP):
                     raise NotImplementedError("only equalities X_k[a] - X_k[b] == 0 on the node states are lowered")
                 node = items[0][0][0].index
                 pairs.setdefault((items[0][0][1], items[1][0][1]), set()).add(node)
+            # union-find over the components: chained pairs (a,b), (b,c) end in one class whatever their order
+            root = list(range(n))
+
+            def find(i):
+                while root[i] != i:
+                    root[i] = root[root[i]]
+                    i = root[i]
+                return i
             for (a, b), nodes in pairs.items():
                 if nodes != set(range(K)):
                     raise NotImplementedError("an equality must be imposed at every node to be folded")
-                cmap[b] = cmap[a]
+                ra, rb = find(a), find(b)
+                if ra != rb:
+                    root[max(ra, rb)] = min(ra, rb)
+            cmap = np.array([find(i) for i in range(n)], dtype=np.int32)
             used = sorted(set(cmap.tolist()))
             remap = {c: i for i, c in enumerate(used)}
             cmap = np.array([remap[c] for c in cmap], dtype=np.int32)
@@ -739,7 +754,7 @@ def _lower_dynamics(d, func, n, m, params):
 def _diag_quadratic(func, n, m, params):
     """Stage cost l(x,u) = sum_i s_i v_i^2 (both reference stage costs, cost_functions.py:5-12)."""
     nv = n + m
-    call = lambda v: float(func(v[:n], v[n:] if m > 1 else v[n], params))
+    call = lambda v: float(np.asarray(func(v[:n], v[n:], params), dtype=float).reshape(-1)[0])
     if abs(call(np.zeros(nv))) > 0:
         raise NotImplementedError("the stage cost must vanish at the origin")
     s = np.array([call(np.eye(nv)[i]) for i in range(nv)])

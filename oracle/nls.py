@@ -35,6 +35,8 @@ ST_CONVERGED = 0        # step below tolerance
 ST_STALLED = 1          # no damping value produced a decrease (rounding-level stationarity)
 ST_MAXITER = 2
 ST_NUMERIC = 3          # non-finite cost at the starting point
+ST_NOSTEP = 4           # no damping value produced a decrease at a NON-stationary point (failure)
+STALL_GTOL = 1e-6       # stalled counts as stationary when max |g_i| / H_ii < STALL_GTOL (1 + |z|_inf)
 
 
 class Window(object):
@@ -396,6 +398,10 @@ def solve(desc, win, z0, opts=None):
                 lam *= 10.0
             if not accepted:
                 status = ST_STALLED
+                with np.errstate(all="ignore"):
+                    sg = np.max(np.abs(g) / (dg + 1e-300))
+                if not (sg <= STALL_GTOL * (1.0 + float(np.max(np.abs(z))))):
+                    status = ST_NOSTEP
                 break
             step = a * float(np.max(np.abs(dz)))
             z = zt

@@ -147,3 +147,30 @@ def test_enu2lla_batch_matches_reference_per_point(G):
         assert abs(lla[i, 2] - ref[2]) <= 1e-8
     assert np.all(np.isfinite(lla[np.arange(4096) != 7]))
     assert np.array_equal(utils.enu2lla_batch(enu[:9], p_ref), lla[:9])
+
+
+def test_coordinate_kernels_match_values_stored_by_the_reference():
+    """nlpf_ecef2enu / nlpf_enu2lla against numbers the REFERENCE produced (not this repo's host port):
+    data/autonomous-car/filtering/leastsquares.pkl (tests/golden/car.npz["ls"]) stores, per epoch, the LS fix in
+    ECEF, the same point through the reference's utils.ecef2enu, and lat/lon/h through its utils.ecef2lla
+    (autonomous-car.py:141-160).  911 epochs."""
+    eng = _eng()
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "car.npz"))
+    ls, p_ref = g["ls"], g["p_ref_ECEF"]
+    ecef, enu_ref, lla_ref = ls[:, :3], ls[:, 4:7], ls[:, 7:10]
+    enu = eng.ecef2enu_batch(np.ascontiguousarray(ecef), p_ref).cpu().numpy()
+    assert np.max(np.abs(enu - enu_ref)) < 1e-8                      # metres; the difference of 6.4e6 m numbers
+    lla, back = eng.enu2lla_batch(np.ascontiguousarray(enu_ref), p_ref, want_ecef=True)
+    lla, back = lla.cpu().numpy(), back.cpu().numpy()
+    assert np.max(np.abs(back - ecef)) < 1e-8                        # ENU -> ECEF returns the stored ECEF fix
+    assert np.max(np.abs(lla[:, :2] - lla_ref[:, :2])) < 1e-12       # degrees (1e-7 m on the ground)
+    assert np.max(np.abs(lla[:, 2] - lla_ref[:, 2])) < 1e-8          # metres
+    # every satellite of the gnss_stationary log: the reference's own ecef2enu output is in the golden file
+    G = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ekf_ls.npz"))
+    out = eng.ecef2enu_batch(G["gs_sat_ecef"].reshape(-1, 3), G["p_ref_ECEF"]).cpu().numpy().reshape(51, 12, 3)
+    for k in range(51):
+        n = int(G["gs_nsat"][k])
+        assert np.max(np.abs(out[k, :n] - G["gs_sat_enu"][k, :n])) < 1e-7      # 2.6e7 m magnitudes: 4e-15 relative
+    # the car's satellites too (autonomous-car.py:152-154)
+    out = eng.ecef2enu_batch(np.ascontiguousarray(g["sat_ecef"]), p_ref).cpu().numpy()
+    assert np.max(np.abs(out - g["sat_enu"])) < 1e-7

@@ -171,8 +171,9 @@ def test_solve_two_receiver_matches_oracle():
 
 @pytest.mark.parametrize("loss,key", [(D.LOSS_L2, "nlp_l2"), (D.LOSS_HUBER, "nlp_huber")])
 def test_car_chain_reproduces_stored_ipopt_outputs(loss, key):
-    """Receding-horizon chain of autonomous-car.py:232-288 (first 30 windows) against the
-    reference's stored IPOPT results: positions within 1 mm."""
+    """Receding-horizon chain of autonomous-car.py:232-288, all 90 windows the reference stored, against its
+    IPOPT results: every component within 0.2 mm (L2) / 0.3 mm (pseudo-Huber); the CPU oracle's own distance
+    to the pickles is 7.7e-5 / 1.8e-4 (tests/test_oracle_car_golden.py)."""
     eng = _engine()
     d = shapes.car(loss=loss)
     g = helpers.car_golden()
@@ -183,15 +184,15 @@ def test_car_chain_reproduces_stored_ipopt_outputs(loss, key):
     z = np.zeros((1, d.nz))
     PhiDT = d.cpm.basisMatrix([1.0])
     worst = np.zeros(7)
-    for step in range(30):
+    for step in range(90):
         U, data = helpers.car_window_inputs(d, g, float(step))
         z, J, iters, status = eng.solve_windows_host(prob, z, U[None], data[None], xhat0[None])
-        assert status[0] <= 1
+        assert status[0] <= 1, (step, status)
         est = helpers.car_extract(d, z[0], ts)
         worst = np.maximum(worst, np.max(np.abs(est - gold[step * 10:(step + 1) * 10]), 0))
         xhat0 = (PhiDT @ z[0].reshape(d.K, d.nv))[0]
-    assert np.all(worst[:3] < 1e-3), worst          # x, y, z within 1 mm of the pickle
-    assert worst[3] < 1e-3 and worst[4] < 1e-3 and np.all(worst[5:] < 5e-3), worst
+    assert np.all(worst[:5] < 2e-4), worst          # x, y, z, clock bias [m], psi [rad]
+    assert np.all(worst[5:] < (2e-4 if loss == D.LOSS_L2 else 3e-4)), worst      # vx, vy [m/s]
     prob.close()
 
 

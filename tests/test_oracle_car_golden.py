@@ -29,16 +29,18 @@ def _chain(loss, key, nwin):
     return worst, Js
 
 
-def test_l2_chain_first_windows_within_1mm_of_ipopt():
-    worst, Js = _chain(D.LOSS_L2, "nlp_l2", 8)
-    assert np.all(worst[:4] < 1e-3), worst            # x, y, z, clock bias [m]
-    assert worst[4] < 1e-3 and np.all(worst[5:] < 2e-3), worst
+def test_l2_chain_all_90_windows_within_a_fifth_of_a_millimetre_of_ipopt():
+    """Every window the reference stored (90 chained solves, 10 samples x 7 components each).  Measured:
+    worst 7.7e-5 over all components (x, y, z, clock bias [m], psi [rad], vx, vy [m/s])."""
+    worst, Js = _chain(D.LOSS_L2, "nlp_l2", 90)
+    assert np.all(worst < 2e-4), worst
     assert abs(Js[0] - 22.0979603177) < 1e-6          # SURVEY.md App. D.3
 
 
-def test_huber_chain_first_windows_within_1mm_of_ipopt():
-    worst, Js = _chain(D.LOSS_HUBER, "nlp_huber", 6)
-    assert np.all(worst[:4] < 1e-3), worst
+def test_huber_chain_all_90_windows_within_a_third_of_a_millimetre_of_ipopt():
+    """Measured: positions / clock bias <= 9.3e-5 m, psi 2.4e-5 rad, vx 1.8e-4, vy 1.5e-4 m/s."""
+    worst, Js = _chain(D.LOSS_HUBER, "nlp_huber", 90)
+    assert np.all(worst[:5] < 2e-4) and np.all(worst[5:] < 3e-4), worst
     assert abs(Js[0] - 22.09346978) < 1e-5            # a different optimum from the L2 one (6 cm away)
 
 
