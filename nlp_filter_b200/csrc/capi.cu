@@ -325,6 +325,9 @@ extern "C" int nlpf_problem_create(const nlpf_desc* D, nlpf_problem** out) {
     std::vector<int> mslot(n, -1);
     p->ws_variant = -1;
     p->counter = nullptr;
+    p->order = nullptr;
+    p->keys = nullptr;
+    p->order_cap = 0;
     {
         bool ident = (nv == n) && (ng == 0);
         for (int i = 0; i < n; ++i) if (D->cmap[i] != i) ident = false;
@@ -520,6 +523,9 @@ extern "C" int nlpf_problem_destroy(nlpf_problem* p) {
     cudaFree(p->blob);
     if (p->scratch) cudaFree(p->scratch);
     if (p->counter) cudaFree(p->counter);
+    if (p->order) cudaFree(p->order);
+    if (p->prof) cudaFree(p->prof);
+    if (p->keys) cudaFree(p->keys);
     delete p;
     return NLPF_OK;
 }
@@ -568,8 +574,36 @@ static int ws_dispatch(nlpf_problem* p, int B, double* z, const double* U, const
         p->scratch_doubles = need;
     }
     if (!p->counter && nlpf_check_cuda(cudaMalloc((void**)&p->counter, sizeof(int)), "cudaMalloc(work counter)")) return NLPF_E_CUDA;
+    if (W == 1 && (size_t)B > p->order_cap && B <= 16384) {      // hand-out order of the batch (wsolve_kernels.cu: ws_key_kernel)
+        if (p->order) { cudaStreamSynchronize(stream); cudaFree(p->order); cudaFree(p->keys); p->order = nullptr; p->keys = nullptr; p->order_cap = 0; }
+        if (nlpf_check_cuda(cudaMalloc((void**)&p->order, (size_t)B * sizeof(int)), "cudaMalloc(hand-out order)")) return NLPF_E_CUDA;
+        if (nlpf_check_cuda(cudaMalloc((void**)&p->keys, (size_t)B * sizeof(double)), "cudaMalloc(hand-out keys)")) return NLPF_E_CUDA;
+        p->order_cap = (size_t)B;
+    }
     return nlpf_ws_launch(p->ws_variant, p, B, z, U, data, xprior, opts, cost_out, iters_out, status_out, p->scratch,
                           p->counter, W, phiDT, Zout, stream);
+}
+
+// Per-phase clock counters of the warp-per-window kernel (bench.py: roofline.eval_frac / ldl_frac).  enable != 0
+// allocates and zeroes five device counters that every following nlpf_solve / nlpf_solve_chain on this handle adds
+// to; out (host, 5 values, may be null) receives [warp-cycles in the evaluation, warp-cycles in factorisation +
+// sweep, evaluations, factorisations, warp-cycles on windows] accumulated so far (synchronises the device);
+// enable == 0 switches the counters off again.
+extern "C" int nlpf_problem_profile(nlpf_problem* p, int enable, unsigned long long* out) {
+    if (!p) { nlpf_set_error("null problem handle"); return NLPF_E_ARG; }
+    if (out) {
+        for (int i = 0; i < 5; ++i) out[i] = 0;
+        if (p->prof && nlpf_check_cuda(cudaMemcpy(out, p->prof, 5 * sizeof(unsigned long long), cudaMemcpyDeviceToHost), "profile read")) return NLPF_E_CUDA;
+    }
+    if (enable) {
+        if (!p->prof && nlpf_check_cuda(cudaMalloc((void**)&p->prof, 5 * sizeof(unsigned long long)), "cudaMalloc(profile)")) return NLPF_E_CUDA;
+        if (nlpf_check_cuda(cudaMemset(p->prof, 0, 5 * sizeof(unsigned long long)), "profile reset")) return NLPF_E_CUDA;
+    } else if (p->prof) {
+        cudaDeviceSynchronize();
+        cudaFree(p->prof);
+        p->prof = nullptr;
+    }
+    return NLPF_OK;
 }
 
 extern "C" int nlpf_problem_has_chain_kernel(const nlpf_problem* p) { return (p && p->ws_variant >= 0 && p->d.has_prior) ? 1 : 0; }

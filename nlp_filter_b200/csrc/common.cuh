@@ -89,6 +89,10 @@ struct nlpf_problem {
     int use_big;         // 1: <= 5 windows per SM by shared memory -> 128-register instantiations (*_genb / *_prb)
     int ws_variant;      // >= 0: small linear-measurement class served by the warp-per-window kernel
     int* counter;        // device work counter of the warp-per-window kernel
+    int* order;          // longest-first hand-out of the warp-per-window kernel: window indices by descending start cost
+    double* keys;        // ... and the start costs
+    size_t order_cap;
+    unsigned long long* prof;   // nlpf_problem_profile: [eval cycles, LDL cycles, evaluations, factorisations, window cycles] or null
     int device;
 };
 

@@ -20,6 +20,7 @@
 // (NM state components, or NM pseudorange slots with one index quadruple).
 #include "common.cuh"
 #include <math.h>
+#include <stdlib.h>
 
 #ifndef WS_DMMA
 #define WS_DMMA 1         // measurement Hessian of the pseudorange shapes on the FP64 tensor cores (mma.sync m8n8k4).
@@ -172,8 +173,10 @@ static_assert(fpat_check_vehicle(), "F^T Lambda F pair list does not match the J
 
 // compile-time description of one problem class
 template <int K_, int N_, int M_, int E_, int NM_, int DYN_, int MEAS_, int WARPS_, int NB_ = 0, bool PRIOR_ = false,
-          int LOSS_ = NLPF_LOSS_L2>
+          int LOSS_ = NLPF_LOSS_L2, bool MMA_ = false, int MAXW_ = 16>
 struct WsCfg {
+    static constexpr bool MMA = MMA_;       // LDL^T with the matrix in registers as FP64 tensor-core tiles (ws_ldl_mma)
+    static constexpr int MAXW = MAXW_;      // warps per SM the register budget allows (16: 128 registers, 12: 168)
     static constexpr int K = K_, N = N_, M = M_, E = E_;
     static constexpr int NM = NM_;          // records per epoch: measured components (MEAS 0) or satellite slots (MEAS 1)
     static constexpr int DYN = DYN_;
@@ -214,7 +217,8 @@ struct WsLayout {
     static constexpr int oQ = oF + ev(NBLK);
     static constexpr int oFB = oQ;
     static constexpr int NQ = (C::MEAS == 0) ? NR : E * 14;      // w*r per residual, or [G_e (10) | q_e (4)] per epoch
-    static constexpr int NFQ = (ev(NBLK) + ev(NQ) > 4 * LDW) ? ev(NBLK) + ev(NQ) : 4 * LDW;   // F | Q, reused by the LDL
+    static constexpr int NPB = C::MMA ? 32 * ((NZ + 8) / 8) : 4 * LDW;      // LDL side buffer: panel rows x 4 (ws_ldl_mma) or W^T
+    static constexpr int NFQ = (ev(NBLK) + ev(NQ) > NPB) ? ev(NBLK) + ev(NQ) : NPB;   // F | Q, reused by the LDL
     static constexpr int PER_WARP = oF + NFQ;
     static_assert(NQ >= NZ, "fb shares the head of Q");
     static constexpr int oDt = C::WARPS * PER_WARP;    // shared by the CTA
@@ -229,7 +233,7 @@ struct WsLayout {
     // resident CTAs per SM: shared memory (227 KB, 1 KB reserved per CTA) or 16 warps, whichever is smaller;
     // the register cap follows from it (GNSS / vehicle shapes: 8 warps per SM, so up to 255 registers)
     static constexpr int CTAS_SMEM = (227 * 1024) / (TOTAL * 8 + 1024);
-    static constexpr int CTAS = (CTAS_SMEM < 512 / (C::WARPS * 32)) ? (CTAS_SMEM < 1 ? 1 : CTAS_SMEM) : 512 / (C::WARPS * 32);
+    static constexpr int CTAS = (CTAS_SMEM < C::MAXW / C::WARPS) ? (CTAS_SMEM < 1 ? 1 : CTAS_SMEM) : C::MAXW / C::WARPS;
 };
 
 // CTA-shared class constants (shared memory) and the measured components (registers)
@@ -247,6 +251,37 @@ struct WsChain {
     const double* phiDT;     // K: basis at t = DT (device)
     double* Zout;            // [W][B][NZ] every window's estimate, or null
 };
+
+// class constants of the CTA: D~, the tile tables of the table-driven LDL, Phi, cw_k * qinv_i, the node-pair table
+// (the caller synchronises the CTA before the first use)
+template <class C>
+__device__ __forceinline__ WsConst ws_stage(const DevProb& P, double* smem) {
+    typedef WsLayout<C> L;
+    constexpr int K = C::K, N = C::N, E = C::E, NM = C::NM, NZ = L::NZ;
+    double* Dt = smem + L::oDt;
+    for (int i = threadIdx.x; i < K * K; i += C::WARPS * 32) Dt[i] = P.Dt[i];
+    uint16_t* ttab = reinterpret_cast<uint16_t*>(smem + L::oTT);
+    int* tcnt = reinterpret_cast<int*>(smem + L::oTC);
+    if (!C::MMA) {
+        for (int i = threadIdx.x; i < P.tile_cnt[NZ + 1]; i += C::WARPS * 32) ttab[i] = P.tile_tab[i];
+        for (int i = threadIdx.x; i < NZ + 2; i += C::WARPS * 32) tcnt[i] = P.tile_cnt[i];
+    }
+    uint16_t* ptab_s = reinterpret_cast<uint16_t*>(smem + L::oPT);
+    for (int i = threadIdx.x; i < E * K; i += C::WARPS * 32) smem[L::oPhi + i] = P.Phi[i];
+    for (int i = threadIdx.x; i < NZ; i += C::WARPS * 32) smem[L::oCW + i] = P.cw[i / N] * P.qinv[i % N];
+    for (int i = threadIdx.x; i < K * (K + 1) / 2; i += C::WARPS * 32) ptab_s[i] = P.ptab[i];
+    WsConst cs;
+    cs.Dt = Dt;
+    cs.Phi = smem + L::oPhi;
+    cs.cwq = smem + L::oCW;
+    cs.ptab = ptab_s;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        if (C::MEAS == 0) cs.c[q] = (q < NM) ? P.act[P.rloc[q * NLPF_NIDX]] : -1;
+        else cs.c[q] = P.act[P.run_loc[q]];
+    }
+    return cs;
+}
 
 // objective J, merit = J/2 + barrier, first-order rounding bound of the merit and (FULL) H (packed,
 // shared memory), g.  merit = +inf flags an iterate outside the bounds or a non-finite objective.
@@ -728,6 +763,95 @@ __device__ __forceinline__ void ws_eval(const DevProb& P, double* sm, const WsCo
     __syncwarp();
 }
 
+// ---- longest-first hand-out -----------------------------------------------------------------------------------
+// ncu of round 1 (profiles/r1_vdp_wsolve_kernel_full.json): smsp_cycles_active_avg / sm_cycles_elapsed_max = 0.65.
+// Windows were handed out in index order; 4096 windows are 1.85 rounds of the resident warps, iteration counts run
+// 5..17 (97 % within 5..9), and the launch ended on whichever warp drew one of the few long windows late.  The
+// objective at the start point predicts those: on 640 oracle solves every window with >= 10 iterations is in the
+// top third by J(z0) (Spearman 0.66 with the iteration count).  So: one cost-only evaluation per window (a few
+// per cent of one iteration), windows ranked by it (counting rank, B^2 / 32 compares per warp), and the atomic
+// counter hands them out in descending order -- the long ones start in the first round.
+template <class C>
+__global__ void __launch_bounds__(C::WARPS * 32, WsLayout<C>::CTAS)
+ws_key_kernel(const __grid_constant__ DevProb P, int B, const double* __restrict__ z_in, const double* __restrict__ U,
+              const double* __restrict__ data, const double* __restrict__ xprior, nlpf_opts opt, double* __restrict__ keys) {
+    typedef WsLayout<C> L;
+    constexpr int K = C::K, N = C::N, M = C::M, NZ = L::NZ;
+    extern __shared__ __align__(16) double smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const WsConst cs = ws_stage<C>(P, smem);
+    __syncthreads();
+    double* sm = smem + warp * L::PER_WARP;
+    double* zs = sm + L::oZ;
+    for (int b = blockIdx.x * C::WARPS + warp; b < B; b += gridDim.x * C::WARPS) {
+        for (int i = lane; i < NZ; i += 32) zs[i] = z_in[(size_t)b * NZ + i];
+        __syncwarp();
+        double J, merit, nse;
+        ws_eval<C, false>(P, sm, cs, zs, U + (size_t)b * K * (M > 0 ? M : 1), data + (size_t)b * P.Ldata,
+                          C::PRIOR ? xprior + (size_t)b * N : nullptr, nullptr, (C::NB > 0) ? opt.mu0 : 0.0, J, merit, nse);
+        if (lane == 0) keys[b] = (J == J && J < 1e300) ? J : 1e300;      // non-finite start points first (they end at once)
+        __syncwarp();
+    }
+}
+
+// order[rank] = b with rank = number of windows with a larger key (ties: lower index first); one warp per window
+__global__ void __launch_bounds__(256) ws_rank_kernel(int B, const double* __restrict__ keys, int* __restrict__ order) {
+    const int lane = threadIdx.x & 31;
+    const int b = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (b >= B) return;
+    const double kb = keys[b];
+    int cnt = 0;
+    for (int i = lane; i < B; i += 32) {
+        const double k = keys[i];
+        cnt += (k > kb || (k == kb && i < b)) ? 1 : 0;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    if (lane == 0) order[cnt] = b;
+}
+
+// backward sweep L^T x = y (y = the scaled appended row), one panel per step: x_B = L11^-T y_B as four
+// independent dot products with the stored inverse, then y_i -= sum_c l_(j0+c),i x_c for the rows above
+template <int NZ>
+__device__ __forceinline__ void ws_backsub(double* Hp, double* xs) {
+    const int lane = threadIdx.x & 31;
+    double* y = Hp + pk(NZ, 0);
+#pragma unroll 1
+    for (int j0 = ((NZ - 1) >> 2) << 2; j0 >= 0; j0 -= 4) {
+        const int pw = (NZ - j0 < 4) ? NZ - j0 : 4;
+        const double2 y01 = *reinterpret_cast<const double2*>(y + j0);
+        const double2 y23 = *reinterpret_cast<const double2*>(y + j0 + 2);
+        const double m10 = Hp[pk(j0 + 1, j0)];
+        const double2 m2 = *reinterpret_cast<const double2*>(Hp + pk(j0 + 2, j0));
+        const double2 m3 = *reinterpret_cast<const double2*>(Hp + pk(j0 + 3, j0));
+        const double m32 = Hp[pk(j0 + 3, j0 + 2)];
+        double x[4];
+        if (pw == 4) {
+            x[3] = y23.y;
+            x[2] = fma(m32, y23.y, y23.x);
+            x[1] = fma(m3.y, y23.y, fma(m2.y, y23.x, y01.y));
+            x[0] = fma(m3.x, y23.y, fma(m2.x, y23.x, fma(m10, y01.y, y01.x)));
+        } else {
+            x[3] = 0.0;
+            x[2] = (pw > 2) ? y23.x : 0.0;
+            x[1] = (pw > 1) ? ((pw > 2) ? fma(m2.y, y23.x, y01.y) : y01.y) : 0.0;
+            x[0] = y01.x;
+            if (pw > 1) x[0] = fma(m10, y01.y, x[0]);
+            if (pw > 2) x[0] = fma(m2.x, y23.x, x[0]);
+        }
+        for (int i = lane; i < j0; i += 32) {
+            double v = y[i];
+            v = fma(-Hp[pk(j0, i)], x[0], v);
+            if (pw > 1) v = fma(-Hp[pk(j0 + 1, i)], x[1], v);
+            if (pw > 2) v = fma(-Hp[pk(j0 + 2, i)], x[2], v);
+            if (pw > 3) v = fma(-Hp[pk(j0 + 3, i)], x[3], v);
+            y[i] = v;
+        }
+        if (lane < pw) xs[j0 + lane] = (lane == 0) ? x[0] : (lane == 1) ? x[1] : (lane == 2) ? x[2] : x[3];
+        __syncwarp();
+    }
+}
+
 // LDL^T of the packed matrix with the right-hand side appended as row NZ, then the backward sweep.
 // Right-looking, panels of 4 columns:
 //   1. every lane factors the 4x4 diagonal block redundantly in registers (frcp pivots);
@@ -861,43 +985,152 @@ __device__ __forceinline__ bool ws_ldl(const uint16_t* __restrict__ ttab, const 
     }
     __syncwarp();
     if (!ok) return false;
-    // backward sweep L^T x = y (y = the scaled appended row), one panel per step: x_B = L11^-T y_B as four
-    // independent dot products with the stored inverse, then y_i -= sum_c l_(j0+c),i x_c for the rows above
-    double* y = Hp + pk(NZ, 0);
-#pragma unroll 1
-    for (int j0 = ((NZ - 1) >> 2) << 2; j0 >= 0; j0 -= 4) {
+    ws_backsub<NZ>(Hp, xs);
+    return true;
+}
+
+// ---- LDL^T with the matrix in REGISTERS as FP64 tensor-core accumulator tiles --------------------------------
+// ncu of the table-driven version below (profiles/r1_vdp_wsolve_*): the kernel is bound by the shared-memory
+// crossbar (132 M wavefronts in 0.75 ms = 0.93 per active cycle per SM), and the trailing update moves most of
+// them: every 4 x 2 register tile reads and writes its C entries and reads 12 operands for 32 FMAs.  Here the
+// whole (NZ+1) x (NZ+1) lower triangle lives in registers in the accumulator layout of mma.sync.m8n8k4.f64 --
+// 8 x 8 tiles, lane (g = lane/4, t = lane%4) holds C[g][2t], C[g][2t+1] -- for the entire factorisation: a rank-4
+// panel update of a tile is ONE instruction with one operand per lane for A and B, and C never moves.  Shared
+// memory only carries the panel: its 4 columns go to a small buffer (rows x 4), the diagonal block is factored
+// redundantly per lane as before, one lane per row below substitutes (w) and stores the scaled l = w / d into the
+// packed matrix for the backward sweep, and the SAME buffer then feeds both fragments of the update
+//     C[I][J] -= L_I D L_J^T :   A[g][k] = -w[8I+g][k] / d_k,   B[k][n] = w[8J+n][k]   (one 8-byte load per tile index).
+// Rows NZ+1.. of the last tile row are padding (unit diagonal), row NZ is the appended right-hand side.
+__device__ __forceinline__ void dmma884(double2& c, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(c.x), "+d"(c.y) : "d"(a), "d"(b));
+}
+
+template <int NZ, int LDW>
+__device__ __forceinline__ bool ws_ldl_mma(double* Hp, double* xs, double* PB) {
+    constexpr int NB = (NZ + 8) / 8;                 // tile rows covering rows 0..NZ
+    constexpr int NPANEL = (NZ + 3) / 4;
+    // PB: 32 * NB doubles (WsLayout::NPB)
+    const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+    double2 c[NB * (NB + 1) / 2];
+#pragma unroll
+    for (int I = 0; I < NB; ++I)
+#pragma unroll
+        for (int J = 0; J <= I; ++J) {
+            const int r = 8 * I + g, cc = 8 * J + 2 * t;
+            double2 v = make_double2(0.0, 0.0);
+            if (r <= NZ && cc <= r) {                // (always true off the diagonal tiles for r <= NZ)
+                v = *reinterpret_cast<const double2*>(Hp + po(r) + cc);
+                if (cc == r) v.y = 0.0;              // upper triangle / row padding
+            }
+            if (r >= NZ) {                           // unit pivots for the appended row and the padding rows
+                if (cc == r) v.x = 1.0;
+                if (cc + 1 == r) v.y = 1.0;
+            }
+            c[I * (I + 1) / 2 + J] = v;
+        }
+    bool ok = true;
+#pragma unroll
+    for (int p = 0; p < NPANEL; ++p) {
+        const int j0 = 4 * p, J = p >> 1, h = p & 1;
         const int pw = (NZ - j0 < 4) ? NZ - j0 : 4;
-        const double2 y01 = *reinterpret_cast<const double2*>(y + j0);
-        const double2 y23 = *reinterpret_cast<const double2*>(y + j0 + 2);
-        const double m10 = Hp[pk(j0 + 1, j0)];
-        const double2 m2 = *reinterpret_cast<const double2*>(Hp + pk(j0 + 2, j0));
-        const double2 m3 = *reinterpret_cast<const double2*>(Hp + pk(j0 + 3, j0));
-        const double m32 = Hp[pk(j0 + 3, j0 + 2)];
-        double x[4];
-        if (pw == 4) {
-            x[3] = y23.y;
-            x[2] = fma(m32, y23.y, y23.x);
-            x[1] = fma(m3.y, y23.y, fma(m2.y, y23.x, y01.y));
-            x[0] = fma(m3.x, y23.y, fma(m2.x, y23.x, fma(m10, y01.y, y01.x)));
-        } else {
-            x[3] = 0.0;
-            x[2] = (pw > 2) ? y23.x : 0.0;
-            x[1] = (pw > 1) ? ((pw > 2) ? fma(m2.y, y23.x, y01.y) : y01.y) : 0.0;
-            x[0] = y01.x;
-            if (pw > 1) x[0] = fma(m10, y01.y, x[0]);
-            if (pw > 2) x[0] = fma(m2.x, y23.x, x[0]);
+        const int j1 = j0 + pw;
+        double l[4][4], rd[4];
+        if (ok) {
+            __syncwarp();                            // the previous panel's fragment loads are done
+            if ((t >> 1) == h) {                     // the lanes that hold columns j0..j0+3 of tile column J
+#pragma unroll
+                for (int I = J; I < NB; ++I)
+                    *reinterpret_cast<double2*>(PB + (8 * I + g) * 4 + 2 * (t & 1)) = c[I * (I + 1) / 2 + J];
+            }
+            __syncwarp();
+            double a[4][4], d[4];
+            {
+                const double* r0 = PB + j0 * 4;
+                const double2 v1 = *reinterpret_cast<const double2*>(r0 + 4);
+                const double2 v2a = *reinterpret_cast<const double2*>(r0 + 8);
+                const double2 v2b = *reinterpret_cast<const double2*>(r0 + 10);
+                const double2 v3a = *reinterpret_cast<const double2*>(r0 + 12);
+                const double2 v3b = *reinterpret_cast<const double2*>(r0 + 14);
+                a[0][0] = r0[0];
+                a[1][0] = v1.x; a[1][1] = v1.y;
+                a[2][0] = v2a.x; a[2][1] = v2a.y; a[2][2] = v2b.x;
+                a[3][0] = v3a.x; a[3][1] = v3a.y; a[3][2] = v3b.x; a[3][3] = v3b.y;
+                if (pw < 4) {
+#pragma unroll
+                    for (int r = 1; r < 4; ++r)
+#pragma unroll
+                        for (int q = 0; q <= r; ++q)
+                            if (r >= pw) a[r][q] = (r == q) ? 1.0 : 0.0;
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+#pragma unroll
+                for (int r = q; r < 4; ++r) {
+                    double w = a[r][q];
+#pragma unroll
+                    for (int u = 0; u < q; ++u) w = fma(-a[r][u], l[q][u], w);
+                    a[r][q] = w;
+                }
+                d[q] = a[q][q];
+                rd[q] = frcp(d[q]);
+#pragma unroll
+                for (int r = q + 1; r < 4; ++r) l[r][q] = a[r][q] * rd[q];
+            }
+            if (!((rd[0] > 0.0) & (rd[1] > 0.0) & (rd[2] > 0.0) & (rd[3] > 0.0))) ok = false;   // see ws_ldl
         }
-        for (int i = lane; i < j0; i += 32) {
-            double v = y[i];
-            v = fma(-Hp[pk(j0, i)], x[0], v);
-            if (pw > 1) v = fma(-Hp[pk(j0 + 1, i)], x[1], v);
-            if (pw > 2) v = fma(-Hp[pk(j0 + 2, i)], x[2], v);
-            if (pw > 3) v = fma(-Hp[pk(j0 + 3, i)], x[3], v);
-            y[i] = v;
+        if (ok) {
+            for (int i = j1 + lane; i <= NZ; i += 32) {
+                double* Pi = PB + i * 4;
+                const double2 u01 = *reinterpret_cast<const double2*>(Pi);
+                const double2 u23 = *reinterpret_cast<const double2*>(Pi + 2);
+                const double w0 = u01.x;
+                const double w1 = fma(-w0, l[1][0], u01.y);
+                const double w2 = fma(-w1, l[2][1], fma(-w0, l[2][0], u23.x));
+                const double w3 = fma(-w2, l[3][2], fma(-w1, l[3][1], fma(-w0, l[3][0], u23.y)));
+                *reinterpret_cast<double2*>(Pi) = make_double2(w0, w1);
+                *reinterpret_cast<double2*>(Pi + 2) = make_double2(w2, w3);
+                double* Hi = Hp + pk(i, j0);
+                if (pw == 4) {
+                    *reinterpret_cast<double2*>(Hi) = make_double2(w0 * rd[0], w1 * rd[1]);
+                    *reinterpret_cast<double2*>(Hi + 2) = make_double2(w2 * rd[2], w3 * rd[3]);
+                } else {
+                    Hi[0] = w0 * rd[0];
+                    if (pw > 1) Hi[1] = w1 * rd[1];
+                    if (pw > 2) Hi[2] = w2 * rd[2];
+                }
+            }
+            if (lane == 31) {       // strict lower part of L11^-1 for the backward sweep (rows/columns >= pw are identity)
+                const double m10 = -l[1][0], m21 = -l[2][1], m32 = -l[3][2];
+                const double m20 = fma(-l[2][1], m10, -l[2][0]);
+                const double m31 = fma(-l[3][2], m21, -l[3][1]);
+                const double m30 = fma(-l[3][2], m20, fma(-l[3][1], m10, -l[3][0]));
+                if (pw > 1) Hp[pk(j0 + 1, j0)] = m10;
+                if (pw > 2) { Hp[pk(j0 + 2, j0)] = m20; Hp[pk(j0 + 2, j0 + 1)] = m21; }
+                if (pw > 3) { Hp[pk(j0 + 3, j0)] = m30; Hp[pk(j0 + 3, j0 + 1)] = m31; Hp[pk(j0 + 3, j0 + 2)] = m32; }
+            }
+            if (j1 < NZ) {
+                __syncwarp();
+                const double nrd = -((t == 0) ? rd[0] : (t == 1) ? rd[1] : (t == 2) ? rd[2] : rd[3]);
+                double fa[NB], fb[NB];
+#pragma unroll
+                for (int X = J + h; X < NB; ++X) {
+                    double v = PB[(8 * X + g) * 4 + t];
+                    if (h == 0 && X == J && g < 4) v = 0.0;       // the panel's own rows: nothing to update there
+                    fb[X] = v;
+                    fa[X] = v * nrd;
+                }
+#pragma unroll
+                for (int I = J + h; I < NB; ++I)
+#pragma unroll
+                    for (int J2 = J + h; J2 <= I; ++J2) dmma884(c[I * (I + 1) / 2 + J2], fa[I], fb[J2]);
+            }
         }
-        if (lane < pw) xs[j0 + lane] = (lane == 0) ? x[0] : (lane == 1) ? x[1] : (lane == 2) ? x[2] : x[3];
-        __syncwarp();
     }
+    __syncwarp();
+    if (!ok) return false;
+    ws_backsub<NZ>(Hp, xs);
     return true;
 }
 
@@ -906,7 +1139,8 @@ __global__ void __launch_bounds__(C::WARPS * 32, WsLayout<C>::CTAS)
 wsolve_kernel(const __grid_constant__ DevProb P, int B, double* __restrict__ z_io, const double* __restrict__ U,
               const double* __restrict__ data, double* xprior, nlpf_opts opt,
               double* __restrict__ cost_out, int* __restrict__ iters_out, int* __restrict__ status_out,
-              double* __restrict__ hlin_all, int* __restrict__ counter, WsChain ch) {
+              double* __restrict__ hlin_all, int* __restrict__ counter, const int* __restrict__ order,
+              unsigned long long* __restrict__ prof, WsChain ch) {
     typedef WsLayout<C> L;
     constexpr int K = C::K, N = C::N, M = C::M, E = C::E, NM = C::NM;
     constexpr int NZ = L::NZ;
@@ -914,26 +1148,9 @@ wsolve_kernel(const __grid_constant__ DevProb P, int B, double* __restrict__ z_i
     constexpr int NBD = BND ? C::NB : 1;
     extern __shared__ __align__(16) double smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    double* Dt = smem + L::oDt;
-    for (int i = threadIdx.x; i < K * K; i += C::WARPS * 32) Dt[i] = P.Dt[i];
     uint16_t* ttab = reinterpret_cast<uint16_t*>(smem + L::oTT);
     int* tcnt = reinterpret_cast<int*>(smem + L::oTC);
-    for (int i = threadIdx.x; i < P.tile_cnt[NZ + 1]; i += C::WARPS * 32) ttab[i] = P.tile_tab[i];
-    for (int i = threadIdx.x; i < NZ + 2; i += C::WARPS * 32) tcnt[i] = P.tile_cnt[i];
-    uint16_t* ptab_s = reinterpret_cast<uint16_t*>(smem + L::oPT);
-    for (int i = threadIdx.x; i < E * K; i += C::WARPS * 32) smem[L::oPhi + i] = P.Phi[i];
-    for (int i = threadIdx.x; i < NZ; i += C::WARPS * 32) smem[L::oCW + i] = P.cw[i / N] * P.qinv[i % N];
-    for (int i = threadIdx.x; i < K * (K + 1) / 2; i += C::WARPS * 32) ptab_s[i] = P.ptab[i];
-    WsConst cs;
-    cs.Dt = Dt;
-    cs.Phi = smem + L::oPhi;
-    cs.cwq = smem + L::oCW;
-    cs.ptab = ptab_s;
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-        if (C::MEAS == 0) cs.c[q] = (q < NM) ? P.act[P.rloc[q * NLPF_NIDX]] : -1;
-        else cs.c[q] = P.act[P.run_loc[q]];
-    }
+    const WsConst cs = ws_stage<C>(P, smem);
     __syncthreads();
     double* sm = smem + warp * L::PER_WARP;
     double* Hp = sm + L::oH;
@@ -943,12 +1160,18 @@ wsolve_kernel(const __grid_constant__ DevProb P, int B, double* __restrict__ z_i
     double* dz = sm + L::oDZ;
     double* ds = sm + L::oDS;
     double* dd = sm + L::oDD;
+    // optional per-phase clock counters (nlpf_problem_profile): warp-cycles inside the evaluation and inside the
+    // factorisation + sweep, their call counts, and the warp-cycles spent on windows in total
+    long long pc_eval = 0, pc_ldl = 0, pc_all = 0;
+    unsigned pn_eval = 0, pn_ldl = 0;
 
     while (true) {
         int b = 0;
         if (lane == 0) b = atomicAdd(counter, 1);
         b = __shfl_sync(0xffffffffu, b, 0);
         if (b >= B) break;
+        if (order) b = order[b];                    // longest-first (ws_key_kernel / ws_rank_kernel)
+        const long long pt_win = prof ? clock64() : 0;
         const double* xp = C::PRIOR ? xprior + (size_t)b * N : nullptr;
         for (int i = lane; i < NZ; i += 32) zs[i] = z_io[(size_t)b * NZ + i];
         // receding-horizon chain (autonomous-car.py:232-288): the W windows of run b back to back in this warp --
@@ -1045,7 +1268,9 @@ wsolve_kernel(const __grid_constant__ DevProb P, int B, double* __restrict__ z_i
         while (true) {
             {
                 double Je, me, ne;
+                const long long pt0 = prof ? clock64() : 0;
                 ws_eval<C, true>(P, sm, cs, (ev == EV_TRIAL) ? zt : zs, Ug, dg, xp, hlin, mu, Je, me, ne);
+                if (prof) { pc_eval += clock64() - pt0; ++pn_eval; }
                 if (ev == EV_TRIAL) { Jt = Je; mt = me; nset = ne; }
                 else if (ev == EV_FIRST || ev == EV_STAGE) { J = Je; merit = me; nse0 = ne; }
             }
@@ -1090,7 +1315,11 @@ wsolve_kernel(const __grid_constant__ DevProb P, int B, double* __restrict__ z_i
                         Hp[pk(NZ, i)] = g[i];
                     }
                     h_valid = false;
-                    const bool ok = ws_ldl<NZ, L::LDW>(ttab, tcnt, Hp, dz, sm + L::oF);
+                    bool ok;
+                    const long long pt1 = prof ? clock64() : 0;
+                    if constexpr (C::MMA) ok = ws_ldl_mma<NZ, L::LDW>(Hp, dz, sm + L::oF);
+                    else ok = ws_ldl<NZ, L::LDW>(ttab, tcnt, Hp, dz, sm + L::oF);
+                    if (prof) { pc_ldl += clock64() - pt1; ++pn_ldl; }
                     if (ok) {
                         double a = 1.0, dmx = 0.0, fin = 0.0, pr = 0.0;
                         for (int i = lane; i < NZ; i += 32) {
@@ -1201,7 +1430,15 @@ wsolve_kernel(const __grid_constant__ DevProb P, int B, double* __restrict__ z_i
             iters_out[b] = ch.phiDT ? it_sum : it_last;          // chain: total iterations, windows not converged
             status_out[b] = ch.phiDT ? nbad : st_last;
         }
+        if (prof) pc_all += clock64() - pt_win;
         __syncwarp();
+    }
+    if (prof && lane == 0) {
+        atomicAdd(prof + 0, (unsigned long long)pc_eval);
+        atomicAdd(prof + 1, (unsigned long long)pc_ldl);
+        atomicAdd(prof + 2, (unsigned long long)pn_eval);
+        atomicAdd(prof + 3, (unsigned long long)pn_ldl);
+        atomicAdd(prof + 4, (unsigned long long)pc_all);
     }
 }
 
@@ -1221,8 +1458,25 @@ int ws_launch(nlpf_problem* p, int B, double* z, const double* U, const double* 
     if (nlpf_check_cuda(cudaMemsetAsync(counter, 0, sizeof(int), st), "wsolve counter reset")) return NLPF_E_CUDA;
     int grid = 148 * L::CTAS;
     const int need = (B + C::WARPS - 1) / C::WARPS;
+    // longest-first hand-out: only when some windows have to wait for a free warp (more windows than resident
+    // warps), for plain batches (a chain's length is the same for every run), up to 16384 windows (the counting
+    // rank is quadratic: 2 us at 4096).  NLPF_NO_LPT=1 keeps the index order.
+    static const bool lpt_off = getenv("NLPF_NO_LPT") != nullptr;
+    const int* order = nullptr;
+    if (!lpt_off && ch.W == 1 && !ch.phiDT && B > grid * C::WARPS && B <= 16384 && p->order && p->keys) {
+        auto kkern = ws_key_kernel<C>;
+        static bool kattr = false;
+        if (!kattr) {
+            if (nlpf_check_cuda(cudaFuncSetAttribute(kkern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "ws_key smem attr")) return NLPF_E_CUDA;
+            kattr = true;
+        }
+        kkern<<<grid, C::WARPS * 32, smem, st>>>(p->d, B, z, U, data, xprior, *o, p->keys);
+        ws_rank_kernel<<<(B + 7) / 8, 256, 0, st>>>(B, p->keys, p->order);
+        order = p->order;
+    }
     if (grid > need) grid = need;
-    kern<<<grid, C::WARPS * 32, smem, st>>>(p->d, B, z, U, data, xprior, *o, cost_out, iters_out, status_out, hlin, counter, ch);
+    kern<<<grid, C::WARPS * 32, smem, st>>>(p->d, B, z, U, data, xprior, *o, cost_out, iters_out, status_out, hlin, counter, order,
+                                            p->prof, ch);
     return nlpf_check_cuda(cudaGetLastError(), "wsolve_kernel launch");
 }
 
@@ -1238,10 +1492,18 @@ int ws_launch(nlpf_problem* p, int B, double* z, const double* U, const double* 
 #define WS_CAR_WARPS 2
 #endif
 #ifndef WS_LIN_WARPS
-#define WS_LIN_WARPS 5     // 3 CTAs = 15 windows per SM (measured 5, 6, 7, 8 warps per CTA: 5.29, 5.22, 5.18, 5.12 M windows/s)
+#define WS_LIN_WARPS 4     // register-resident LDL^T: 3 CTAs x 4 warps = 12 windows per SM at 168 registers
+                           // (table version: 3 x 5 = 15 per SM at 128 registers; measured 5, 6, 7, 8 warps per CTA:
+                           // 5.29, 5.22, 5.18, 5.12 M windows/s)
 #endif
-typedef WsCfg<21, 2, 1, 50, 2, NLPF_DYN_VDP, 0, WS_LIN_WARPS> CfgVdp;          // van der Pol MHE (BASELINE configs[1])
-typedef WsCfg<21, 2, 2, 50, 2, NLPF_DYN_AFFINE, 0, WS_LIN_WARPS> CfgExample;   // estimation_example.py
+#ifndef WS_LIN_MMA
+#define WS_LIN_MMA 1
+#endif
+#ifndef WS_LIN_MAXW
+#define WS_LIN_MAXW 12
+#endif
+typedef WsCfg<21, 2, 1, 50, 2, NLPF_DYN_VDP, 0, WS_LIN_WARPS, 0, false, NLPF_LOSS_L2, WS_LIN_MMA != 0, WS_LIN_MAXW> CfgVdp;          // van der Pol MHE (BASELINE configs[1])
+typedef WsCfg<21, 2, 2, 50, 2, NLPF_DYN_AFFINE, 0, WS_LIN_WARPS, 0, false, NLPF_LOSS_L2, WS_LIN_MMA != 0, WS_LIN_MAXW> CfgExample;   // estimation_example.py
 typedef WsCfg<11, 5, 3, 51, 12, NLPF_DYN_AFFINE, 1, WS_GNSS_WARPS> CfgGnss;     // gnss_stationary.py MHE (BASELINE configs[2])
 typedef WsCfg<6, 9, 2, 21, 11, NLPF_DYN_VEHICLE_GNSS, 1, WS_CAR_WARPS, 2, true, NLPF_LOSS_L2> CfgCar;         // autonomous-car.py:184-220
 typedef WsCfg<6, 9, 2, 21, 11, NLPF_DYN_VEHICLE_GNSS, 1, WS_CAR_WARPS, 2, true, NLPF_LOSS_HUBER> CfgCarHuber;  // autonomous-car.py:293-318
