@@ -207,6 +207,14 @@ int nlpf_solve_chain(nlpf_problem* p, int B, int W, double* z, const double* U_a
                      const double* phiDT, const nlpf_opts* opts, double* cost_out, int* iters_sum_out, int* bad_out,
                      double* Z_out, void* stream);
 
+/* Measurement support (no reference counterpart; bench.py's roofline.eval_frac / ldl_frac): per-phase clock
+ * counters of the warp-per-window kernel.  enable != 0 allocates and zeroes five device counters that every
+ * following nlpf_solve / nlpf_solve_chain on this handle adds to; out5 (host, may be NULL) receives what has been
+ * accumulated so far -- [warp-cycles inside the evaluation (kernels 1+2), warp-cycles inside factorisation + sweep
+ * (kernel 3), evaluations, factorisations, warp-cycles spent on windows] -- and synchronises the device;
+ * enable == 0 switches the counters off again.  Problem classes served by the CTA-per-window kernel count nothing. */
+int nlpf_problem_profile(nlpf_problem* p, int enable, unsigned long long* out5);
+
 /* shared memory (bytes) one window of this problem class needs in the whole-solve kernel */
 int nlpf_problem_smem_bytes(const nlpf_problem* p);
 

@@ -37,6 +37,8 @@ extern "C" int nlpf_launch_solve_pr(nlpf_problem*, int, double*, const double*, 
                                     const double*, const nlpf_opts*, double*, int*, int*, double*, cudaStream_t);
 extern "C" int nlpf_launch_sample(nlpf_problem*, int, const double*, int, const double*, double*, cudaStream_t);
 extern "C" int nlpf_ws_variant(int K, int N, int M, int E, int NM, int dyn, int meas, int nb, int prior, int loss);
+extern "C" int nlpf_ws_assemble(int variant, nlpf_problem* p, int B, const double* z, const double* U, const double* data,
+                                const double* xprior, double mu, double* H_out, double* g_out, double* cost_out, cudaStream_t st);
 extern "C" int nlpf_ws_launch(int variant, nlpf_problem* p, int B, double* z, const double* U, const double* data,
                               double* xprior, const nlpf_opts* o, double* cost_out, int* iters_out, int* status_out,
                               double* hlin, int* counter, int W, const double* phiDT, double* Zout, cudaStream_t st);
@@ -547,6 +549,8 @@ extern "C" int nlpf_assemble(nlpf_problem* p, int B, const double* z, const doub
     int rc = check_batch(p, B, z, data);
     if (rc) return rc;
     if (!H_out || !g_out || !cost_out) { nlpf_set_error("null output buffer"); return NLPF_E_ARG; }
+    if (p->ws_variant >= 0 && !wshift && (p->d.m == 0 || U) && (!p->d.has_prior || xprior))      // warp-per-window classes
+        return nlpf_ws_assemble(p->ws_variant, p, B, z, U, data, xprior, mu, H_out, g_out, cost_out, (cudaStream_t)stream);
     auto launch = p->use_big ? (p->use_pr ? nlpf_launch_assemble_prb : nlpf_launch_assemble_genb)
                              : (p->use_pr ? nlpf_launch_assemble_pr : nlpf_launch_assemble_gen);
     return launch(p, B, z, U, data, xprior, wshift, mu, H_out, g_out, cost_out, (cudaStream_t)stream);

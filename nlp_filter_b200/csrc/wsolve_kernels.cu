@@ -177,6 +177,10 @@ template <int K_, int N_, int M_, int E_, int NM_, int DYN_, int MEAS_, int WARP
 struct WsCfg {
     static constexpr bool MMA = MMA_;       // LDL^T with the matrix in registers as FP64 tensor-core tiles (ws_ldl_mma)
     static constexpr int MAXW = MAXW_;      // warps per SM the register budget allows (16: 128 registers, 12: 168)
+    // longest-first hand-out by start cost (ws_key_kernel): measured +16 % on the van der Pol batch (iteration counts
+    // 5..17, predicted by J(z0)), -5 % on the GNSS batch (cold start: J(z0) is the squared start offset and says nothing
+    // about the 7..9 iterations) -- so only for the linear-measurement classes
+    static constexpr bool LPT = (MEAS_ == 0);
     static constexpr int K = K_, N = N_, M = M_, E = E_;
     static constexpr int NM = NM_;          // records per epoch: measured components (MEAS 0) or satellite slots (MEAS 1)
     static constexpr int DYN = DYN_;
@@ -219,7 +223,8 @@ struct WsLayout {
     static constexpr int NQ = (C::MEAS == 0) ? NR : E * 14;      // w*r per residual, or [G_e (10) | q_e (4)] per epoch
     static constexpr int NPB = C::MMA ? 32 * ((NZ + 8) / 8) : 4 * LDW;      // LDL side buffer: panel rows x 4 (ws_ldl_mma) or W^T
     static constexpr int NFQ = (ev(NBLK) + ev(NQ) > NPB) ? ev(NBLK) + ev(NQ) : NPB;   // F | Q, reused by the LDL
-    static constexpr int PER_WARP = oF + NFQ;
+    static constexpr int oCLK = oF + NFQ;              // start clock of the current window (profiling only)
+    static constexpr int PER_WARP = oCLK + 2;
     static_assert(NQ >= NZ, "fb shares the head of Q");
     static constexpr int oDt = C::WARPS * PER_WARP;    // shared by the CTA
     static constexpr int NTILE = ((NZ + 4) / 4) * ((NZ + 4) / 2 + 1);   // bound on the tile table (row quads x column pairs)
@@ -763,6 +768,110 @@ __device__ __forceinline__ void ws_eval(const DevProb& P, double* sm, const WsCo
     __syncwarp();
 }
 
+// constant H of a window with linear measurements: Hc + sum_e (phi_e phi_e^T) (x) diag(w_e), built in the window's
+// shared-memory H and written to hl (NP doubles: an L2-resident cache the evaluation streams from)
+template <class C>
+__device__ __forceinline__ void ws_hlin(const DevProb& P, double* sm, const WsConst& cs, const double* dg, double* hl) {
+    typedef WsLayout<C> L;
+    constexpr int K = C::K, N = C::N, E = C::E, NM = C::NM;
+    const int lane = threadIdx.x & 31;
+    double* Hp = sm + L::oH;
+    for (int p = lane; p < L::NP; p += 32) Hp[p] = P.Hcp[p];
+    double* wts = sm + L::oQ;
+    for (int t = lane; t < L::NR; t += 32) wts[t] = dg[2 * t + 1];
+    // the usual case -- the same weight at every epoch (constant measurement covariance) -- needs no sum
+    // over the epochs: sum_e phi_ej phi_el is a class constant (P.PtP, built on the host)
+    bool same = true;
+    for (int t = lane; t < L::NR; t += 32) same = same && (dg[2 * t + 1] == dg[2 * (t % NM) + 1]);
+    same = __all_sync(0xffffffffu, same);
+    __syncwarp();
+    if (same) {
+        for (int pr = lane; pr < K * (K + 1) / 2; pr += 32) {
+            const int pe = cs.ptab[pr];
+            const int j = pe & 255, l = pe >> 8;
+            const double pp = P.PtP[pr];
+#pragma unroll
+            for (int s = 0; s < NM; ++s) {
+                const int c = cs.c[s < 4 ? s : 3];
+                Hp[pk(j * N + c, l * N + c)] += pp * wts[s];
+            }
+        }
+    } else
+    for (int pr = lane; pr < K * (K + 1) / 2; pr += 32) {
+        const int pe = cs.ptab[pr];
+        const int j = pe & 255, l = pe >> 8;
+        double acc[2][NM];
+#pragma unroll
+        for (int s = 0; s < NM; ++s) acc[0][s] = acc[1][s] = 0.0;
+#pragma unroll 4
+        for (int e = 0; e + 1 < E; e += 2) {
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const double pp = cs.Phi[(e + h) * K + j] * cs.Phi[(e + h) * K + l];
+#pragma unroll
+                for (int s = 0; s < NM; ++s) acc[h][s] = fma(pp, wts[(e + h) * NM + s], acc[h][s]);
+            }
+        }
+        if (E & 1) {
+            const double pp = cs.Phi[(E - 1) * K + j] * cs.Phi[(E - 1) * K + l];
+#pragma unroll
+            for (int s = 0; s < NM; ++s) acc[0][s] = fma(pp, wts[(E - 1) * NM + s], acc[0][s]);
+        }
+#pragma unroll
+        for (int s = 0; s < NM; ++s) {
+            const int c = cs.c[s < 4 ? s : 3];
+            Hp[pk(j * N + c, l * N + c)] += acc[0][s] + acc[1][s];
+        }
+    }
+    __syncwarp();
+    for (int p = lane; p < L::NP; p += 32) hl[p] = Hp[p];
+}
+
+// nlpf_assemble for the classes of this file: kernels (1)+(2) alone -- one evaluation of H (Gauss-Newton part +
+// exact second-order dynamics term), g, J per window, H written to HBM as the full symmetric nz x nz matrix.
+// The same ws_eval the whole-solve kernel iterates on, so the assemble parity tests check it directly.
+template <class C>
+__global__ void __launch_bounds__(C::WARPS * 32, WsLayout<C>::CTAS)
+ws_assemble_kernel(const __grid_constant__ DevProb P, int B, const double* __restrict__ z_in, const double* __restrict__ U,
+                   const double* __restrict__ data, const double* __restrict__ xprior, double mu,
+                   double* __restrict__ H_out, double* __restrict__ g_out, double* __restrict__ cost_out) {
+    typedef WsLayout<C> L;
+    constexpr int K = C::K, N = C::N, M = C::M, NZ = L::NZ;
+    extern __shared__ __align__(16) double smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const WsConst cs = ws_stage<C>(P, smem);
+    __syncthreads();
+    double* sm = smem + warp * L::PER_WARP;
+    double* zs = sm + L::oZ;
+    double* Hp = sm + L::oH;
+    for (int b = blockIdx.x * C::WARPS + warp; b < B; b += gridDim.x * C::WARPS) {
+        for (int i = lane; i < NZ; i += 32) zs[i] = z_in[(size_t)b * NZ + i];
+        const double* dg = data + (size_t)b * P.Ldata;
+        double* Ho = H_out + (size_t)b * NZ * NZ;
+        const double* h0 = P.Hcp;
+        if (C::MEAS == 0) {               // the window's own output block doubles as the constant-H scratch (NP < NZ^2)
+            __syncwarp();
+            ws_hlin<C>(P, sm, cs, dg, Ho);
+            h0 = Ho;
+        }
+        __syncwarp();
+        double J, merit, nse;
+        ws_eval<C, true>(P, sm, cs, zs, U + (size_t)b * K * (M > 0 ? M : 1), dg, C::PRIOR ? xprior + (size_t)b * N : nullptr,
+                         h0, mu, J, merit, nse);
+        __syncwarp();
+        for (int t = lane; t < NZ * NZ; t += 32) {
+            const int r = t / NZ, c = t - r * NZ;
+            Ho[t] = (c <= r) ? Hp[pk(r, c)] : Hp[pk(c, r)];
+        }
+        for (int i = lane; i < NZ; i += 32) g_out[(size_t)b * NZ + i] = sm[L::oG + i];
+        if (lane == 0) {
+            cost_out[2 * b] = J;
+            cost_out[2 * b + 1] = merit;
+        }
+        __syncwarp();
+    }
+}
+
 // ---- longest-first hand-out -----------------------------------------------------------------------------------
 // ncu of round 1 (profiles/r1_vdp_wsolve_kernel_full.json): smsp_cycles_active_avg / sm_cycles_elapsed_max = 0.65.
 // Windows were handed out in index order; 4096 windows are 1.85 rounds of the resident warps, iteration counts run
@@ -1162,8 +1271,8 @@ wsolve_kernel(const __grid_constant__ DevProb P, int B, double* __restrict__ z_i
     double* dd = sm + L::oDD;
     // optional per-phase clock counters (nlpf_problem_profile): warp-cycles inside the evaluation and inside the
     // factorisation + sweep, their call counts, and the warp-cycles spent on windows in total
-    long long pc_eval = 0, pc_ldl = 0, pc_all = 0;
-    unsigned pn_eval = 0, pn_ldl = 0;
+    // (added straight to the global counters by lane 0 when profiling is on: accumulators in registers cost the
+    // van der Pol kernel spills under its 168-register cap)
 
     while (true) {
         int b = 0;
@@ -1171,7 +1280,7 @@ wsolve_kernel(const __grid_constant__ DevProb P, int B, double* __restrict__ z_i
         b = __shfl_sync(0xffffffffu, b, 0);
         if (b >= B) break;
         if (order) b = order[b];                    // longest-first (ws_key_kernel / ws_rank_kernel)
-        const long long pt_win = prof ? clock64() : 0;
+        if (prof && lane == 0) *reinterpret_cast<long long*>(sm + L::oCLK) = clock64();
         const double* xp = C::PRIOR ? xprior + (size_t)b * N : nullptr;
         for (int i = lane; i < NZ; i += 32) zs[i] = z_io[(size_t)b * NZ + i];
         // receding-horizon chain (autonomous-car.py:232-288): the W windows of run b back to back in this warp --
@@ -1188,55 +1297,7 @@ wsolve_kernel(const __grid_constant__ DevProb P, int B, double* __restrict__ z_i
             // constant H of this window: Hc + sum_e (phi_e phi_e^T) (x) diag(w_e), kept in an L2-resident cache
             double* hl = hlin_all + (size_t)b * L::NP;
             hlin = hl;
-            for (int p = lane; p < L::NP; p += 32) Hp[p] = P.Hcp[p];
-            double* wts = sm + L::oQ;
-            for (int t = lane; t < L::NR; t += 32) wts[t] = dg[2 * t + 1];
-            // the usual case -- the same weight at every epoch (constant measurement covariance) -- needs no sum
-            // over the epochs: sum_e phi_ej phi_el is a class constant (P.PtP, built on the host)
-            bool same = true;
-            for (int t = lane; t < L::NR; t += 32) same = same && (dg[2 * t + 1] == dg[2 * (t % NM) + 1]);
-            same = __all_sync(0xffffffffu, same);
-            __syncwarp();
-            if (same) {
-                for (int pr = lane; pr < K * (K + 1) / 2; pr += 32) {
-                    const int pe = cs.ptab[pr];
-                    const int j = pe & 255, l = pe >> 8;
-                    const double pp = P.PtP[pr];
-#pragma unroll
-                    for (int s = 0; s < NM; ++s) {
-                        const int c = cs.c[s < 4 ? s : 3];
-                        Hp[pk(j * N + c, l * N + c)] += pp * wts[s];
-                    }
-                }
-            } else
-            for (int pr = lane; pr < K * (K + 1) / 2; pr += 32) {
-                const int pe = cs.ptab[pr];
-                const int j = pe & 255, l = pe >> 8;
-                double acc[2][NM];
-#pragma unroll
-                for (int s = 0; s < NM; ++s) acc[0][s] = acc[1][s] = 0.0;
-#pragma unroll 4
-                for (int e = 0; e + 1 < E; e += 2) {
-#pragma unroll
-                    for (int h = 0; h < 2; ++h) {
-                        const double pp = cs.Phi[(e + h) * K + j] * cs.Phi[(e + h) * K + l];
-#pragma unroll
-                        for (int s = 0; s < NM; ++s) acc[h][s] = fma(pp, wts[(e + h) * NM + s], acc[h][s]);
-                    }
-                }
-                if (E & 1) {
-                    const double pp = cs.Phi[(E - 1) * K + j] * cs.Phi[(E - 1) * K + l];
-#pragma unroll
-                    for (int s = 0; s < NM; ++s) acc[0][s] = fma(pp, wts[(E - 1) * NM + s], acc[0][s]);
-                }
-#pragma unroll
-                for (int s = 0; s < NM; ++s) {
-                    const int c = cs.c[s < 4 ? s : 3];
-                    Hp[pk(j * N + c, l * N + c)] += acc[0][s] + acc[1][s];
-                }
-            }
-            __syncwarp();
-            for (int p = lane; p < L::NP; p += 32) hl[p] = Hp[p];
+            ws_hlin<C>(P, sm, cs, dg, hl);
         }
         __syncwarp();
         if (BND) {   // start strictly inside the bounds (IPOPT bound_push)
@@ -1270,7 +1331,7 @@ wsolve_kernel(const __grid_constant__ DevProb P, int B, double* __restrict__ z_i
                 double Je, me, ne;
                 const long long pt0 = prof ? clock64() : 0;
                 ws_eval<C, true>(P, sm, cs, (ev == EV_TRIAL) ? zt : zs, Ug, dg, xp, hlin, mu, Je, me, ne);
-                if (prof) { pc_eval += clock64() - pt0; ++pn_eval; }
+                if (prof && lane == 0) { atomicAdd(prof + 0, (unsigned long long)(clock64() - pt0)); atomicAdd(prof + 2, 1ULL); }
                 if (ev == EV_TRIAL) { Jt = Je; mt = me; nset = ne; }
                 else if (ev == EV_FIRST || ev == EV_STAGE) { J = Je; merit = me; nse0 = ne; }
             }
@@ -1319,7 +1380,7 @@ wsolve_kernel(const __grid_constant__ DevProb P, int B, double* __restrict__ z_i
                     const long long pt1 = prof ? clock64() : 0;
                     if constexpr (C::MMA) ok = ws_ldl_mma<NZ, L::LDW>(Hp, dz, sm + L::oF);
                     else ok = ws_ldl<NZ, L::LDW>(ttab, tcnt, Hp, dz, sm + L::oF);
-                    if (prof) { pc_ldl += clock64() - pt1; ++pn_ldl; }
+                    if (prof && lane == 0) { atomicAdd(prof + 1, (unsigned long long)(clock64() - pt1)); atomicAdd(prof + 3, 1ULL); }
                     if (ok) {
                         double a = 1.0, dmx = 0.0, fin = 0.0, pr = 0.0;
                         for (int i = lane; i < NZ; i += 32) {
@@ -1430,15 +1491,8 @@ wsolve_kernel(const __grid_constant__ DevProb P, int B, double* __restrict__ z_i
             iters_out[b] = ch.phiDT ? it_sum : it_last;          // chain: total iterations, windows not converged
             status_out[b] = ch.phiDT ? nbad : st_last;
         }
-        if (prof) pc_all += clock64() - pt_win;
+        if (prof && lane == 0) atomicAdd(prof + 4, (unsigned long long)(clock64() - *reinterpret_cast<long long*>(sm + L::oCLK)));
         __syncwarp();
-    }
-    if (prof && lane == 0) {
-        atomicAdd(prof + 0, (unsigned long long)pc_eval);
-        atomicAdd(prof + 1, (unsigned long long)pc_ldl);
-        atomicAdd(prof + 2, (unsigned long long)pn_eval);
-        atomicAdd(prof + 3, (unsigned long long)pn_ldl);
-        atomicAdd(prof + 4, (unsigned long long)pc_all);
     }
 }
 
@@ -1463,7 +1517,7 @@ int ws_launch(nlpf_problem* p, int B, double* z, const double* U, const double* 
     // rank is quadratic: 2 us at 4096).  NLPF_NO_LPT=1 keeps the index order.
     static const bool lpt_off = getenv("NLPF_NO_LPT") != nullptr;
     const int* order = nullptr;
-    if (!lpt_off && ch.W == 1 && !ch.phiDT && B > grid * C::WARPS && B <= 16384 && p->order && p->keys) {
+    if (C::LPT && !lpt_off && ch.W == 1 && !ch.phiDT && B > grid * C::WARPS && B <= 16384 && p->order && p->keys) {
         auto kkern = ws_key_kernel<C>;
         static bool kattr = false;
         if (!kattr) {
@@ -1478,6 +1532,24 @@ int ws_launch(nlpf_problem* p, int B, double* z, const double* U, const double* 
     kern<<<grid, C::WARPS * 32, smem, st>>>(p->d, B, z, U, data, xprior, *o, cost_out, iters_out, status_out, hlin, counter, order,
                                             p->prof, ch);
     return nlpf_check_cuda(cudaGetLastError(), "wsolve_kernel launch");
+}
+
+template <class C>
+int ws_assemble_launch(nlpf_problem* p, int B, const double* z, const double* U, const double* data, const double* xprior,
+                       double mu, double* H_out, double* g_out, double* cost_out, cudaStream_t st) {
+    typedef WsLayout<C> L;
+    auto kern = ws_assemble_kernel<C>;
+    const size_t smem = sizeof(double) * L::TOTAL;
+    static bool attr = false;
+    if (!attr) {
+        if (nlpf_check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "ws_assemble smem attr")) return NLPF_E_CUDA;
+        attr = true;
+    }
+    int grid = 148 * L::CTAS;
+    const int need = (B + C::WARPS - 1) / C::WARPS;
+    if (grid > need) grid = need;
+    kern<<<grid, C::WARPS * 32, smem, st>>>(p->d, B, z, U, data, xprior, mu, H_out, g_out, cost_out);
+    return nlpf_check_cuda(cudaGetLastError(), "ws_assemble_kernel launch");
 }
 
 // windows (warps) per CTA.  Pseudorange shapes are limited by shared memory (about 21 KB per window):
@@ -1504,9 +1576,21 @@ int ws_launch(nlpf_problem* p, int B, double* z, const double* U, const double* 
 #endif
 typedef WsCfg<21, 2, 1, 50, 2, NLPF_DYN_VDP, 0, WS_LIN_WARPS, 0, false, NLPF_LOSS_L2, WS_LIN_MMA != 0, WS_LIN_MAXW> CfgVdp;          // van der Pol MHE (BASELINE configs[1])
 typedef WsCfg<21, 2, 2, 50, 2, NLPF_DYN_AFFINE, 0, WS_LIN_WARPS, 0, false, NLPF_LOSS_L2, WS_LIN_MMA != 0, WS_LIN_MAXW> CfgExample;   // estimation_example.py
-typedef WsCfg<11, 5, 3, 51, 12, NLPF_DYN_AFFINE, 1, WS_GNSS_WARPS> CfgGnss;     // gnss_stationary.py MHE (BASELINE configs[2])
-typedef WsCfg<6, 9, 2, 21, 11, NLPF_DYN_VEHICLE_GNSS, 1, WS_CAR_WARPS, 2, true, NLPF_LOSS_L2> CfgCar;         // autonomous-car.py:184-220
-typedef WsCfg<6, 9, 2, 21, 11, NLPF_DYN_VEHICLE_GNSS, 1, WS_CAR_WARPS, 2, true, NLPF_LOSS_HUBER> CfgCarHuber;  // autonomous-car.py:293-318
+#ifndef WS_GNSS_MMA
+#define WS_GNSS_MMA 0
+#endif
+#ifndef WS_GNSS_MAXW
+#define WS_GNSS_MAXW 16
+#endif
+#ifndef WS_CAR_MMA
+#define WS_CAR_MMA 1
+#endif
+#ifndef WS_CAR_MAXW
+#define WS_CAR_MAXW 8
+#endif
+typedef WsCfg<11, 5, 3, 51, 12, NLPF_DYN_AFFINE, 1, WS_GNSS_WARPS, 0, false, NLPF_LOSS_L2, WS_GNSS_MMA != 0, WS_GNSS_MAXW> CfgGnss;     // gnss_stationary.py MHE (BASELINE configs[2])
+typedef WsCfg<6, 9, 2, 21, 11, NLPF_DYN_VEHICLE_GNSS, 1, WS_CAR_WARPS, 2, true, NLPF_LOSS_L2, WS_CAR_MMA != 0, WS_CAR_MAXW> CfgCar;         // autonomous-car.py:184-220
+typedef WsCfg<6, 9, 2, 21, 11, NLPF_DYN_VEHICLE_GNSS, 1, WS_CAR_WARPS, 2, true, NLPF_LOSS_HUBER, WS_CAR_MMA != 0, WS_CAR_MAXW> CfgCarHuber;  // autonomous-car.py:293-318
 
 }  // namespace
 
@@ -1520,6 +1604,19 @@ extern "C" int nlpf_ws_variant(int K, int N, int M, int E, int NM, int dyn, int 
     if (meas == 1 && K == 6 && N == 9 && M == 2 && E == 21 && NM == 11 && dyn == NLPF_DYN_VEHICLE_GNSS && nb == 2 && prior)
         return loss == NLPF_LOSS_L2 ? 3 : 4;
     return -1;
+}
+
+extern "C" int nlpf_ws_assemble(int variant, nlpf_problem* p, int B, const double* z, const double* U, const double* data,
+                                const double* xprior, double mu, double* H_out, double* g_out, double* cost_out, cudaStream_t st) {
+    switch (variant) {
+        case 0: return ws_assemble_launch<CfgVdp>(p, B, z, U, data, xprior, mu, H_out, g_out, cost_out, st);
+        case 1: return ws_assemble_launch<CfgExample>(p, B, z, U, data, xprior, mu, H_out, g_out, cost_out, st);
+        case 2: return ws_assemble_launch<CfgGnss>(p, B, z, U, data, xprior, mu, H_out, g_out, cost_out, st);
+        case 3: return ws_assemble_launch<CfgCar>(p, B, z, U, data, xprior, mu, H_out, g_out, cost_out, st);
+        case 4: return ws_assemble_launch<CfgCarHuber>(p, B, z, U, data, xprior, mu, H_out, g_out, cost_out, st);
+    }
+    nlpf_set_error("unknown warp-solve variant %d", variant);
+    return NLPF_E_ARG;
 }
 
 extern "C" int nlpf_ws_launch(int variant, nlpf_problem* p, int B, double* z, const double* U, const double* data,

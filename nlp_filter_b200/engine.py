@@ -142,6 +142,14 @@ class WindowProblem(object):
         if wshift is not None:
             _want("wshift", wshift, (B, d.K, d.n))
 
+    def profile(self, enable=True):
+        """Per-phase clock counters of the warp-per-window kernel (nlpf_problem_profile): returns what has been
+        accumulated so far as a dict, then (re)starts or stops counting."""
+        out = (ctypes.c_ulonglong * 5)()
+        _capi.check(self._lib.nlpf_problem_profile(self._h, 1 if enable else 0, out))
+        return dict(eval_cycles=int(out[0]), ldl_cycles=int(out[1]), evals=int(out[2]), factorisations=int(out[3]),
+                    window_cycles=int(out[4]))
+
     def sample(self, z, PhiT):
         d = self.desc
         z = _f8(z, (-1, d.nz))
