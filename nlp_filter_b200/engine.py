@@ -273,7 +273,13 @@ class HostBatch(object):
     def device_z(self):
         """(B, nz) contiguous device tensor of the estimates of the last run (for a collective)."""
         zs = [self._views(self.d_in[c], c)[0] for c in range(self.nchunk)]
-        return zs[0] if self.nchunk == 1 else torch.cat(zs, 0)
+        if self.nchunk == 1:
+            return zs[0]
+        if getattr(self, "_zcat", None) is None:           # allocated once: no allocation inside a timed step
+            self._zcat = torch.empty((self.B, self._nz), dtype=torch.float64, device="cuda")
+        for (lo, hi), zc in zip(self.chunks, zs):
+            self._zcat[lo:hi].copy_(zc, non_blocking=True)
+        return self._zcat
 
 
 def solve_chain(prob, z, U_all, data_all, xprior, PhiDT, opts=None, keep=False):
