@@ -22,6 +22,12 @@
 #include <math.h>
 #include <stdlib.h>
 
+#ifndef WS_LIN_NEWTON
+#define WS_LIN_NEWTON 1   // Newton steps after the 2^-20 reciprocal seed of the LDL pivots.  2 = full double precision (all
+                          // pseudorange / vehicle classes).  The van der Pol and estimation_example classes (cond(H) ~ 1e4) use 1:
+                          // pivots to 1e-12 relative perturb the STEP by that much, the iteration converges to the same
+                          // point (the gradient decides, not the factorisation); +2.5 % on the van der Pol batch.
+#endif
 #ifndef WS_DMMA
 #define WS_DMMA 1         // measurement Hessian of the pseudorange shapes on the FP64 tensor cores (mma.sync m8n8k4).
                           // Measured on B200: DMMA peak 36.7 TFLOP/s = the vector FMA peak (36.1) -- same pipe -- so the
@@ -57,11 +63,12 @@ __device__ __forceinline__ void cp_async16(double* dst_smem, const double* src) 
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 // reciprocal without the slow path of the IEEE division: MUFU seed (2^-20) + two Newton steps (pivots are
 // checked for d > 0 and finiteness by the caller)
+template <int NEWTON = 2>
 __device__ __forceinline__ double frcp(double d) {
     double r;
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(d));
     r = fma(fma(-d, r, 1.0), r, r);
-    r = fma(fma(-d, r, 1.0), r, r);
+    if (NEWTON >= 2) r = fma(fma(-d, r, 1.0), r, r);
     return r;
 }
 
@@ -961,6 +968,53 @@ __device__ __forceinline__ void ws_backsub(double* Hp, double* xs) {
     }
 }
 
+// Backward sweep with y in REGISTERS (lane i holds y_i and y_(i+32)): the version above goes through shared memory
+// twice per panel (y and x written, re-read after a __syncwarp) -- 11 dependent round trips that were 14.6 % of the
+// van der Pol kernel's samples (profiles/r2a_vdp_wsolve_stalls.txt: backsub, stalls wait + branch + short_sb).
+// Here a panel step is: four y values by shuffle from their owner lanes -> x_B (three dependent FMAs, every lane
+// the same) -> each lane's own y_i -= sum_c l_(j0+c),i x_c.  The l and m loads of every step are independent of the
+// sweep, so with the loop unrolled they are in flight long before they are needed.
+template <int NZ>
+__device__ __forceinline__ void ws_backsub_reg(const double* Hp, double* xs) {
+    static_assert(NZ <= 64, "two y registers per lane");
+    const int lane = threadIdx.x & 31;
+    const double* y = Hp + pk(NZ, 0);
+    double yr0 = (lane < NZ) ? y[lane] : 0.0;
+    double yr1 = (lane + 32 < NZ) ? y[lane + 32] : 0.0;
+#pragma unroll
+    for (int j0 = ((NZ - 1) >> 2) << 2; j0 >= 0; j0 -= 4) {
+        const int pw = (NZ - j0 < 4) ? NZ - j0 : 4;
+        // L11^-1 (strict lower part, stored in place by the factorisation) and the four panel rows of L: no
+        // dependence on the sweep
+        const double m10 = (pw > 1) ? Hp[pk(j0 + 1, j0)] : 0.0;
+        const double2 m2 = (pw > 2) ? *reinterpret_cast<const double2*>(Hp + pk(j0 + 2, j0)) : make_double2(0.0, 0.0);
+        const double2 m3 = (pw > 3) ? *reinterpret_cast<const double2*>(Hp + pk(j0 + 3, j0)) : make_double2(0.0, 0.0);
+        const double m32 = (pw > 3) ? Hp[pk(j0 + 3, j0 + 2)] : 0.0;
+        double la[4] = {0.0, 0.0, 0.0, 0.0}, lb[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            if (c < pw) {
+                if (lane < j0) la[c] = Hp[pk(j0 + c, lane)];
+                if (j0 > 32 && lane + 32 < j0) lb[c] = Hp[pk(j0 + c, lane + 32)];
+            }
+        }
+        double yb[4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            const int i = j0 + c;                      // compile-time after unrolling: register and owner lane are constants
+            yb[c] = (c < pw) ? __shfl_sync(0xffffffffu, (i >= 32) ? yr1 : yr0, i & 31) : 0.0;
+        }
+        const double x3 = yb[3];
+        const double x2 = fma(m32, yb[3], yb[2]);
+        const double x1 = fma(m3.y, yb[3], fma(m2.y, yb[2], yb[1]));
+        const double x0 = fma(m3.x, yb[3], fma(m2.x, yb[2], fma(m10, yb[1], yb[0])));
+        yr0 -= fma(la[0], x0, la[1] * x1) + fma(la[2], x2, la[3] * x3);
+        if (j0 > 32) yr1 -= fma(lb[0], x0, lb[1] * x1) + fma(lb[2], x2, lb[3] * x3);
+        if (lane < pw) xs[j0 + lane] = (lane == 0) ? x0 : (lane == 1) ? x1 : (lane == 2) ? x2 : x3;
+    }
+    __syncwarp();
+}
+
 // LDL^T of the packed matrix with the right-hand side appended as row NZ, then the backward sweep.
 // Right-looking, panels of 4 columns:
 //   1. every lane factors the 4x4 diagonal block redundantly in registers (frcp pivots);
@@ -1115,7 +1169,7 @@ __device__ __forceinline__ void dmma884(double2& c, double a, double b) {
                  : "+d"(c.x), "+d"(c.y) : "d"(a), "d"(b));
 }
 
-template <int NZ, int LDW>
+template <int NZ, int LDW, int RN>
 __device__ __forceinline__ bool ws_ldl_mma(double* Hp, double* xs, double* PB) {
     constexpr int NB = (NZ + 8) / 8;                 // tile rows covering rows 0..NZ
     constexpr int NPANEL = (NZ + 3) / 4;
@@ -1183,7 +1237,7 @@ __device__ __forceinline__ bool ws_ldl_mma(double* Hp, double* xs, double* PB) {
                     a[r][q] = w;
                 }
                 d[q] = a[q][q];
-                rd[q] = frcp(d[q]);
+                rd[q] = frcp<RN>(d[q]);
 #pragma unroll
                 for (int r = q + 1; r < 4; ++r) l[r][q] = a[r][q] * rd[q];
             }
@@ -1239,7 +1293,7 @@ __device__ __forceinline__ bool ws_ldl_mma(double* Hp, double* xs, double* PB) {
     }
     __syncwarp();
     if (!ok) return false;
-    ws_backsub<NZ>(Hp, xs);
+    ws_backsub_reg<NZ>(Hp, xs);
     return true;
 }
 
@@ -1378,7 +1432,7 @@ wsolve_kernel(const __grid_constant__ DevProb P, int B, double* __restrict__ z_i
                     h_valid = false;
                     bool ok;
                     const long long pt1 = prof ? clock64() : 0;
-                    if constexpr (C::MMA) ok = ws_ldl_mma<NZ, L::LDW>(Hp, dz, sm + L::oF);
+                    if constexpr (C::MMA) ok = ws_ldl_mma<NZ, L::LDW, (C::MEAS == 0) ? WS_LIN_NEWTON : 2>(Hp, dz, sm + L::oF);
                     else ok = ws_ldl<NZ, L::LDW>(ttab, tcnt, Hp, dz, sm + L::oF);
                     if (prof && lane == 0) { atomicAdd(prof + 1, (unsigned long long)(clock64() - pt1)); atomicAdd(prof + 3, 1ULL); }
                     if (ok) {

@@ -157,13 +157,42 @@ class Variable(object):
         return "Variable(%s, n=%d)" % (self.name, self.n)
 
 
-class Parameter(object):
-    """A numeric parameter created by addParameter (nlp/nlp.py:38-47); set through setParameter."""
+class ParamPool(object):
+    """One flat float64 array behind every parameter of a problem (the problem-build
+    path).  A parameter is a slice of it, so (a) a whole measurement matrix is uploaded with ONE array assignment
+    (`setMeasurement` on the parameters an `addResidualCost` call returned) and (b) the per-window data block of the
+    kernels is gathered with one fancy-indexing operation from precomputed offsets (`NLP._pack_data`) instead of a
+    Python loop over every scalar residual."""
 
-    def __init__(self, n):
+    def __init__(self):
+        self.buf = np.zeros(256)
+        self.used = 0
+
+    def alloc(self, n):
+        off = self.used
+        self.used += int(n)
+        if self.used > self.buf.shape[0]:
+            nb = np.zeros(max(2 * self.buf.shape[0], self.used))
+            nb[:off] = self.buf[:off]
+            self.buf = nb
+        return off
+
+
+class Parameter(object):
+    """A numeric parameter created by addParameter (nlp/nlp.py:38-47); set through setParameter.  Its value lives in
+    the problem's ParamPool (`value` is a view of the pool); `block` = (first offset, count, size, position) of the
+    addParameter call that created it."""
+
+    def __init__(self, n, pool=None, off=None, block=None):
         self.n = int(n)
-        self.value = np.zeros(self.n)
+        self.pool = pool if pool is not None else ParamPool()
+        self.off = self.pool.alloc(self.n) if off is None else int(off)
+        self.block = block
         self.is_set = False
+
+    @property
+    def value(self):
+        return self.pool.buf[self.off:self.off + self.n]
 
     def set(self, val):
         v = np.asarray(val, dtype=float).reshape(-1)
@@ -171,7 +200,7 @@ class Parameter(object):
             v = np.full(self.n, float(v[0]))
         if v.size != self.n:
             raise ValueError("parameter of size %d cannot take a value of size %d" % (self.n, v.size))
-        self.value = v.copy()
+        self.pool.buf[self.off:self.off + self.n] = v
         self.is_set = True
 
     def __getitem__(self, i):
@@ -189,5 +218,5 @@ class ParamElem(object):
 
     def set(self, val):
         v = np.asarray(val, dtype=float).reshape(-1)
-        self.par.value[self.i] = v[0]
+        self.par.pool.buf[self.par.off + self.i] = v[0]
         self.par.is_set = True
