@@ -207,6 +207,18 @@ int nlpf_solve_chain(nlpf_problem* p, int B, int W, double* z, const double* U_a
                      const double* phiDT, const nlpf_opts* opts, double* cost_out, int* iters_sum_out, int* bad_out,
                      double* Z_out, void* stream);
 
+/* Row A9, multi-segment collocation for long horizons (no reference counterpart: the reference is single-interval,
+ * nlp/nlp.py:189-200, and its monomial Lagrange basis breaks down for N >~ 25, nlp/collocation.py:87-111).  The
+ * horizon is S segments of the ordinary single-segment problem class that share their end nodes; unknowns are the
+ * S*N_s + 1 nodes.  nlpf_assemble on B*S gathered sub-windows gives H_seg, g_seg, J_seg; nlpf_ms_blocks overlap-adds
+ * them into the block-tridiagonal normal equations (bs = N_s*n, S+1 block rows, the last one padded with identity),
+ * adds the arrival cost on node 0 (pinv[n], xprior[B][n]; may be NULL) and the damping lam[B] * diag(H) (NULL: none);
+ * nlpf_blocktri_solve then solves them.  kn = (N_s+1)*n, step = N_s*n. */
+int nlpf_ms_gather(int B, int S, int kn, int step, const double* z, double* zsub, void* stream);
+int nlpf_ms_blocks(int B, int S, int n, int bs, const double* H_seg, const double* g_seg, const double* cost_seg,
+                   const double* pinv, const double* xprior, const double* z, const double* lam, double* Dg, double* Lo,
+                   double* g, double* J, void* stream);
+
 /* Measurement support (no reference counterpart; bench.py's roofline.eval_frac / ldl_frac): per-phase clock
  * counters of the warp-per-window kernel.  enable != 0 allocates and zeroes five device counters that every
  * following nlpf_solve / nlpf_solve_chain on this handle adds to; out5 (host, may be NULL) receives what has been

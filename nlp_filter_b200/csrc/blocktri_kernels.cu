@@ -23,7 +23,8 @@
 
 namespace cg = cooperative_groups;
 
-#define BT_BS_MAX 16
+#define BT_BS_MAX 48          // Riccati: three bs x bs blocks in (dynamic) shared memory = 55 KB at bs = 48
+#define BT_BS_MAX_CR 32       // cyclic reduction: per warp bs x (2 bs + 1) + bs x bs; 4 warps = 98 KB at bs = 32
 #define BT_THREADS 128
 
 // in-place Cholesky of the bs x bs lower triangle of A (row-major, leading dimension bs)
@@ -89,11 +90,12 @@ __global__ void __launch_bounds__(BT_THREADS)
 blocktri_riccati_kernel(int B, int nblk, int bs, const double* __restrict__ Dg, const double* __restrict__ Lo,
                         const double* __restrict__ rhs, double* __restrict__ x_out, int* __restrict__ info,
                         double* __restrict__ work, size_t work_stride) {
-    __shared__ double C[BT_BS_MAX * BT_BS_MAX];                      // chol(S_{i-1})
-    __shared__ double T[BT_BS_MAX * (BT_BS_MAX + 1)];                // S^-1 [L_i^T | y_{i-1}]
-    __shared__ double Li[BT_BS_MAX * BT_BS_MAX];
+    extern __shared__ double bt_sm[];                                // sized by the launcher from bs (multi-segment blocks reach bs = 45)
     cg::thread_block g = cg::this_thread_block();
     const int tid = threadIdx.x, b2 = bs * bs, ld = bs + 1;
+    double* C = bt_sm;                                               // chol(S_{i-1})          bs x bs
+    double* T = C + b2;                                              // S^-1 [L_i^T | y_{i-1}]  bs x (bs + 1)
+    double* Li = T + bs * ld;                                        //                         bs x bs
     for (int b = blockIdx.x; b < B; b += gridDim.x) {
         BtWork w = bt_work(work + (size_t)b * work_stride, nblk, bs);
         const double* Db = Dg + (size_t)b * nblk * b2;
@@ -160,15 +162,14 @@ __global__ void __launch_bounds__(BT_THREADS)
 blocktri_cr_kernel(int B, int nblk, int bs, const double* __restrict__ Dg, const double* __restrict__ Lo,
                    const double* __restrict__ rhs, double* __restrict__ x_out, int* __restrict__ info,
                    double* __restrict__ work, size_t work_stride) {
-    __shared__ double Tsm[BT_THREADS / 32][BT_BS_MAX * (2 * BT_BS_MAX + 1)];
-    __shared__ double Nsm[BT_THREADS / 32][BT_BS_MAX * BT_BS_MAX];
+    extern __shared__ double bt_sm[];
     __shared__ int bad;
     cg::thread_block blk = cg::this_thread_block();
     cg::thread_block_tile<32> wp = cg::tiled_partition<32>(blk);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = BT_THREADS / 32;
     const int b2 = bs * bs, ld = 2 * bs + 1;
-    double* T = Tsm[warp];
-    double* Nw = Nsm[warp];
+    double* T = bt_sm + (size_t)warp * (bs * ld + b2);               // per warp: bs x (2 bs + 1), then bs x bs
+    double* Nw = T + bs * ld;
     for (int b = blockIdx.x; b < B; b += gridDim.x) {
         BtWork w = bt_work(work + (size_t)b * work_stride, nblk, bs);
         if (tid == 0) bad = 0;
@@ -282,7 +283,8 @@ blocktri_cr_kernel(int B, int nblk, int bs, const double* __restrict__ Dg, const
 
 extern "C" int nlpf_blocktri_solve(int B, int nblk, int bs, const double* Dg, const double* Lo, const double* rhs,
                                    double* x_out, int* info_out, int variant, void* stream) {
-    if (B < 1 || nblk < 1 || bs < 1 || bs > BT_BS_MAX) { nlpf_set_error("bad block-tridiagonal sizes B=%d nblk=%d bs=%d (bs <= %d)", B, nblk, bs, BT_BS_MAX); return NLPF_E_ARG; }
+    const int bs_max = (variant == 1) ? BT_BS_MAX_CR : BT_BS_MAX;
+    if (B < 1 || nblk < 1 || bs < 1 || bs > bs_max) { nlpf_set_error("bad block-tridiagonal sizes B=%d nblk=%d bs=%d (bs <= %d for this variant)", B, nblk, bs, bs_max); return NLPF_E_ARG; }
     if (!Dg || !Lo || !rhs || !x_out || !info_out) { nlpf_set_error("null block-tridiagonal buffer"); return NLPF_E_ARG; }
     if (variant != 0 && variant != 1) { nlpf_set_error("variant must be 0 (Riccati) or 1 (cyclic reduction)"); return NLPF_E_ARG; }
     cudaStream_t st = (cudaStream_t)stream;
@@ -290,9 +292,119 @@ extern "C" int nlpf_blocktri_solve(int B, int nblk, int bs, const double* Dg, co
     double* work = nullptr;
     if (nlpf_check_cuda(cudaMallocAsync((void**)&work, sizeof(double) * stride * B, st), "cudaMallocAsync(blocktri workspace)")) return NLPF_E_CUDA;
     const int grid = B < 148 * 8 ? B : 148 * 8;
-    if (variant == 0) blocktri_riccati_kernel<<<grid, BT_THREADS, 0, st>>>(B, nblk, bs, Dg, Lo, rhs, x_out, info_out, work, stride);
-    else blocktri_cr_kernel<<<grid, BT_THREADS, 0, st>>>(B, nblk, bs, Dg, Lo, rhs, x_out, info_out, work, stride);
+    const size_t sm_ric = sizeof(double) * (size_t)(2 * bs * bs + bs * (bs + 1));
+    const size_t sm_cr = sizeof(double) * (size_t)(BT_THREADS / 32) * (bs * (2 * bs + 1) + bs * bs);
+    static bool attr = false;
+    if (!attr) {
+        cudaFuncSetAttribute(blocktri_riccati_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)(sizeof(double) * (2 * BT_BS_MAX * BT_BS_MAX + BT_BS_MAX * (BT_BS_MAX + 1))));
+        cudaFuncSetAttribute(blocktri_cr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)(sizeof(double) * (BT_THREADS / 32) * (BT_BS_MAX_CR * (2 * BT_BS_MAX_CR + 1) + BT_BS_MAX_CR * BT_BS_MAX_CR)));
+        attr = true;
+    }
+    if (variant == 0) blocktri_riccati_kernel<<<grid, BT_THREADS, sm_ric, st>>>(B, nblk, bs, Dg, Lo, rhs, x_out, info_out, work, stride);
+    else blocktri_cr_kernel<<<grid, BT_THREADS, sm_cr, st>>>(B, nblk, bs, Dg, Lo, rhs, x_out, info_out, work, stride);
     int rc = nlpf_check_cuda(cudaGetLastError(), "blocktri kernel launch");
     cudaFreeAsync(work, st);
     return rc;
+}
+
+// ------------------------------------------------------------------------------------------
+// Multi-segment collocation (row A9): a long horizon [0, S T_s] is cut into S segments, each the
+// reference's single-interval Chebyshev collocation (nlp/collocation.py) on its own N_s + 1 nodes;
+// neighbouring segments SHARE their end node (continuity by construction).  Unknowns: S N_s + 1
+// nodes of n states.  Every cost term of nlp/nlp.py:202-277 lives inside one segment, so
+//     J(z) = sum_s J_seg(z_seg(s)) + arrival cost on node 0          z_seg(s) = nodes s N_s .. s N_s + N_s
+// and H, g are the overlap-add of the per-segment dense H_seg, g_seg -- which nlpf_assemble
+// (kernels 1+2) computes for B * S "sub-windows" of the ordinary single-segment problem class.
+// Ordering the unknowns segment by segment (block s = the first N_s nodes of segment s, block S = the
+// last node alone) makes H block-tridiagonal with bs = N_s n: block s couples to block s + 1 only
+// through the first node of block s + 1.
+//
+//   ms_gather_kernel   z[B][(S N_s + 1) n]  ->  zsub[B S][(N_s + 1) n]
+//   ms_blocks_kernel   H_seg, g_seg, J_seg  ->  Dg, Lo [B][S+1][bs][bs], g [B][(S+1) bs], J[B], with the
+//                      Levenberg-Marquardt damping lam_b * diag(H) already added to Dg (so a retry with a larger
+//                      lam only re-reads H_seg) and the padding rows of the last block set to identity.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) ms_gather_kernel(int B, int S, int kn, int step, int nzt, const double* __restrict__ z,
+                                                        double* __restrict__ zsub) {
+    const size_t total = (size_t)B * S * kn;
+    for (size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
+        const int i = t % kn;
+        const int s = (t / kn) % S;
+        const size_t b = t / ((size_t)kn * S);
+        zsub[t] = z[b * nzt + (size_t)s * step + i];
+    }
+}
+
+// one CTA per window; Hs[b][s] is the (kn x kn) row-major segment matrix, kn = bs + n
+__global__ void __launch_bounds__(128) ms_blocks_kernel(int B, int S, int n, int bs, const double* __restrict__ Hs,
+                                                        const double* __restrict__ gs, const double* __restrict__ cs,
+                                                        const double* __restrict__ pinv, const double* __restrict__ xprior,
+                                                        const double* __restrict__ z, const double* __restrict__ lam,
+                                                        double* __restrict__ Dg, double* __restrict__ Lo, double* __restrict__ g,
+                                                        double* __restrict__ J) {
+    const int kn = bs + n, nblk = S + 1, b2 = bs * bs;
+    for (int b = blockIdx.x; b < B; b += gridDim.x) {
+        const double lm = lam ? lam[b] : 0.0;
+        double* Db = Dg + (size_t)b * nblk * b2;
+        double* Lb = Lo + (size_t)b * nblk * b2;
+        double* gb = g + (size_t)b * nblk * bs;
+        const int nzt = S * bs + n;
+        for (int t = threadIdx.x; t < nblk * b2; t += blockDim.x) {
+            const int blk = t / b2, e = t - blk * b2, r = e / bs, c = e - r * bs;
+            double d = 0.0, l = 0.0;
+            if (blk < S) d = Hs[((size_t)b * S + blk) * kn * kn + (size_t)r * kn + c];            // segment blk: its first N_s nodes
+            if (blk > 0 && r < n && c < n)                                                        // last node of segment blk-1 = first node here
+                d += Hs[((size_t)b * S + blk - 1) * kn * kn + (size_t)(bs + r) * kn + bs + c];
+            if (blk == 0 && pinv && r == c && r < n) d += pinv[r];                                // arrival cost (nlp.py:279-286), half-gradient convention
+            if (blk == S && (r >= n || c >= n)) d = (r == c) ? 1.0 : 0.0;                         // padding of the last block
+            // damping lam |H_ii|: H carries the exact second-order dynamics term, so a diagonal entry can be negative far
+            // from the solution; its magnitude keeps the damped matrix positive definite for large enough lam
+            if (r == c && !(blk == S && r >= n)) d += lm * fabs(d);
+            if (blk > 0 && r < n) l = Hs[((size_t)b * S + blk - 1) * kn * kn + (size_t)(bs + r) * kn + c];   // coupling blk <- blk-1
+            Db[t] = d;
+            Lb[t] = l;
+        }
+        for (int t = threadIdx.x; t < nblk * bs; t += blockDim.x) {
+            const int blk = t / bs, r = t - blk * bs;
+            double v = 0.0;
+            if (blk < S) v = gs[((size_t)b * S + blk) * kn + r];
+            if (blk > 0 && r < n) v += gs[((size_t)b * S + blk - 1) * kn + bs + r];
+            if (blk == 0 && pinv && r < n) v += pinv[r] * (z[(size_t)b * nzt + r] - xprior[(size_t)b * n + r]);
+            if (blk == S && r >= n) v = 0.0;
+            gb[t] = v;
+        }
+        if (threadIdx.x < 32) {
+            double s = 0.0;
+            for (int k = threadIdx.x; k < S; k += 32) s += cs[2 * ((size_t)b * S + k)];
+            if (pinv)
+                for (int k = threadIdx.x; k < n; k += 32) {
+                    const double d0 = z[(size_t)b * nzt + k] - xprior[(size_t)b * n + k];
+                    s += pinv[k] * d0 * d0;
+                }
+            for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+            if (threadIdx.x == 0) J[b] = s;
+        }
+    }
+}
+
+extern "C" int nlpf_ms_gather(int B, int S, int kn, int step, const double* z, double* zsub, void* stream) {
+    if (B < 1 || S < 1 || kn < 1 || step < 1 || step >= kn || !z || !zsub) { nlpf_set_error("bad multi-segment gather argument"); return NLPF_E_ARG; }
+    const size_t total = (size_t)B * S * kn;
+    int blocks = (int)((total + 255) / 256);
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    ms_gather_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(B, S, kn, step, S * step + (kn - step), z, zsub);
+    return nlpf_check_cuda(cudaGetLastError(), "ms_gather launch");
+}
+
+extern "C" int nlpf_ms_blocks(int B, int S, int n, int bs, const double* H_seg, const double* g_seg, const double* cost_seg,
+                              const double* pinv, const double* xprior, const double* z, const double* lam, double* Dg,
+                              double* Lo, double* g, double* J, void* stream) {
+    if (B < 1 || S < 1 || n < 1 || bs < n || bs % n != 0 || !H_seg || !g_seg || !cost_seg || !z || !Dg || !Lo || !g || !J || (pinv && !xprior)) {
+        nlpf_set_error("bad multi-segment block-assembly argument");
+        return NLPF_E_ARG;
+    }
+    ms_blocks_kernel<<<B < 148 * 8 ? B : 148 * 8, 128, 0, (cudaStream_t)stream>>>(B, S, n, bs, H_seg, g_seg, cost_seg, pinv, xprior, z, lam, Dg, Lo, g, J);
+    return nlpf_check_cuda(cudaGetLastError(), "ms_blocks launch");
 }

@@ -209,3 +209,22 @@ def generic_model(dyn_id, n, m, K=7, T=3.0, n_epochs=9, extra=()):
             rt.append(t); ep.append(e); ix.append(_idx(*idx))
     d.set_residuals(rt, ep, ix)
     return d.finalize()
+
+
+def vdp_segment(Ns=5, Ts=1.0, n_epochs=5, q=1e-2, r=(0.01, 0.02)):
+    """One segment of a long van der Pol window (multi-segment collocation): K = Ns + 1 nodes on
+    [0, Ts], n_epochs full-state measurement epochs strictly inside the segment (so no epoch belongs to two
+    segments).  40 such segments = a 200-epoch horizon (BASELINE.json configs[3]'s "horizon 200" read as one window)."""
+    t = (np.arange(n_epochs) + 0.5) * (Ts / n_epochs)
+    d = _base(Ns, Ts, 2, 1, t)
+    d.dyn_id = D.DYN_VDP
+    d.qinv = np.array([1.0 / q, 1.0 / q])
+    rt, ep, ix = [], [], []
+    for e in range(n_epochs):
+        for i in range(2):
+            rt.append(D.RT_STATE)
+            ep.append(e)
+            ix.append(_idx(i))
+    d.set_residuals(rt, ep, ix)
+    d.r_inv = 1.0 / np.asarray(r, float)
+    return d.finalize()

@@ -230,3 +230,50 @@ def two_receiver_batch(d, B, seed=5000):
     inv = np.array([0, 1, 2, 3, 4, 5, 6, 8, 9])      # folded columns -> state components
     z0[:] = xprior[:, None, inv]
     return dict(z0=z0.reshape(B, -1), U=U, data=data, xprior=xprior)
+
+
+def vdp_multiseg_batch(seg, S, B, seed=6000):
+    """Long van der Pol windows for the multi-segment path: truth by RK4 (dt 0.005) over [0, S*Ts], noisy full-state
+    measurements at every segment's epochs, controls at every segment's nodes, start point = measurements
+    interpolated to the (shared) nodes.  Returns z0 (B, S*Ns*2 + 2), U (B, S, K, 1), data (B, S, Ldata_seg)."""
+    rng = np.random.default_rng(seed)
+    Ts, K, Ns = seg.T, seg.K, seg.K - 1
+    T = S * Ts
+    x0 = np.stack([rng.normal(0.0, 0.25, B), rng.normal(1.0, 0.25, B)], 1)
+    phase = rng.uniform(0, 2 * np.pi, B)
+    ufun = lambda t: 0.5 * np.sin(t + phase)
+    dt = 0.005
+    nstep = int(round(T / dt))
+    xs = np.zeros((B, 2, nstep + 1))
+    a, b = x0[:, 0].copy(), x0[:, 1].copy()
+    xs[:, 0, 0], xs[:, 1, 0] = a, b
+    for i in range(nstep):
+        t = i * dt
+        k1 = vdp_rhs(a, b, ufun(t))
+        k2 = vdp_rhs(a + 0.5 * dt * k1[0], b + 0.5 * dt * k1[1], ufun(t + 0.5 * dt))
+        k3 = vdp_rhs(a + 0.5 * dt * k2[0], b + 0.5 * dt * k2[1], ufun(t + 0.5 * dt))
+        k4 = vdp_rhs(a + dt * k3[0], b + dt * k3[1], ufun(t + dt))
+        a = a + dt / 6 * (k1[0] + 2 * k2[0] + 2 * k3[0] + k4[0])
+        b = b + dt / 6 * (k1[1] + 2 * k2[1] + 2 * k3[1] + k4[1])
+        xs[:, 0, i + 1], xs[:, 1, i + 1] = a, b
+    tt = np.arange(nstep + 1) * dt
+    t_ep = (np.arange(S)[:, None] * Ts + seg.epochs[None, :]).reshape(-1)              # global epoch times
+    truth = np.stack([_interp_rows(tt, xs[:, 0, :], t_ep), _interp_rows(tt, xs[:, 1, :], t_ep)], 1)   # B, 2, S*E
+    rvar = 1.0 / seg.r_inv
+    y = truth + rng.normal(size=truth.shape) * np.sqrt(rvar)[None, :, None]
+    E = seg.E
+    data = np.zeros((B, S, seg.Ldata))
+    for s in range(S):
+        for e in range(E):
+            for i in range(2):
+                o = seg.roff[e * 2 + i]
+                data[:, s, o] = y[:, i, s * E + e]
+                data[:, s, o + 1] = seg.r_inv[i]
+    tn_loc = seg.cpm.tau2t(seg.cpm.tau)
+    U = np.zeros((B, S, K, 1))
+    for s in range(S):
+        U[:, s, :, 0] = 0.5 * np.sin((s * Ts + tn_loc)[None, :] + phase[:, None])
+    t_nodes = np.concatenate([s * Ts + tn_loc[(0 if s == 0 else 1):] for s in range(S)])     # S*Ns + 1 shared nodes
+    z0 = np.stack([_interp_rows(t_ep, y[:, 0, :], t_nodes), _interp_rows(t_ep, y[:, 1, :], t_nodes)], 2).reshape(B, -1)
+    x_nodes = np.stack([_interp_rows(tt, xs[:, 0, :], t_nodes), _interp_rows(tt, xs[:, 1, :], t_nodes)], 2)
+    return dict(z0=z0, U=U, data=data, truth_nodes=x_nodes, t_nodes=t_nodes, x0=x0)

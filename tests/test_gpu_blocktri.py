@@ -30,9 +30,17 @@ def _dense(Dg, Lo):
 
 
 @pytest.mark.parametrize("variant", [0, 1])
-@pytest.mark.parametrize("nblk,bs", [(1, 4), (2, 3), (5, 6), (8, 10), (13, 16), (21, 10), (200, 10)])
+@pytest.mark.parametrize("nblk,bs", [(1, 4), (2, 3), (5, 6), (8, 10), (13, 16), (21, 10), (200, 10), (9, 30), (41, 32), (7, 45), (201, 45),
+                                     (5, 48)])
 def test_blocktri_matches_lapack(variant, nblk, bs):
+    """Up to 200 segments; block sizes up to 48 through the Riccati recursion (a vehicle segment of 5 nodes x 9 states is
+    45), up to 32 through cyclic reduction (its per-warp workspace)."""
     from nlp_filter_b200 import engine
+    if variant == 1 and bs > 32:
+        from nlp_filter_b200 import _capi
+        with pytest.raises(_capi.NlpfError):
+            engine.blocktri_solve(*_system(2, nblk, bs, seed=1), variant)
+        return
     B = 6
     Dg, Lo, rhs = _system(B, nblk, bs, seed=100 + nblk)
     x, info = engine.blocktri_solve(Dg, Lo, rhs, variant)
