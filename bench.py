@@ -248,7 +248,7 @@ def run_aux(args):
     flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device="cuda")
     peak_fp64 = engine.fp64_peak_tflops()
     if args.workload == "ekf":
-        e = make_ekf_inputs()
+        e = make_ekf_inputs(Bf=256 if args.windows == 4096 else args.windows)      # BASELINE size unless --windows says otherwise
         Bf, steps = e["z"].shape[:2]
         units = Bf * steps
         d = {k: dev(e[k]) for k in ("x0", "S0", "u", "z", "sat", "Q")}
@@ -269,7 +269,7 @@ def run_aux(args):
         d2h = h_out.numel() * 8
         iters_mean = 1.0
     else:
-        l = make_ls_inputs()
+        l = make_ls_inputs(B=16384 if args.windows == 4096 else args.windows)
         units = l["pr"].shape[0]
         d = {k: dev(l[k]) for k in ("sat", "pr")}
         nsat = dev(l["nsat"])
@@ -317,7 +317,9 @@ def run_aux(args):
     line = {"metric": metric, "value": units * args.steps / (ms_dev * 1e-3), "unit": unit, "n_gpus": 1, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": WORKLOAD_DESC[args.workload], "units_per_step": units,
+            "config": {"workload": WORKLOAD_DESC[args.workload] if args.windows == 4096 else
+                       WORKLOAD_DESC[args.workload].replace("256 filters", "%d filters" % args.windows).replace("16384 independent", "%d independent" % args.windows),
+                       "units_per_step": units,
                        "l2": "256 MB buffer written between timed iterations", "mean_iterations": iters_mean},
             "e2e": {"value": units * args.steps / (ms_e2e * 1e-3), "unit": unit, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / args.steps},

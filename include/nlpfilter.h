@@ -159,6 +159,12 @@ int nlpf_ekf_run(int model, int B, int steps, int smax, double* mu_inout, double
                  const double* u, const double* z, const double* sat, const int* nsat,
                  const double* Q, double r, double dt, const double* par,
                  double* mu_traj_out, void* stream);
+/* The same with a FULL process covariance Qfull[n*n] and a full measurement covariance Rfull[smax*smax] (its
+ * leading nsat x nsat block is used at every step), as EKF.predict / EKF.correct accept (utils/ekf.py:43,54); and
+ * correct_only != 0: EKF.correct alone (utils/ekf.py:46-61) -- (mu, S) in are (mu_pred, S_pred), no prediction. */
+int nlpf_ekf_run_general(int model, int B, int steps, int smax, double* mu_inout, double* S_inout, const double* u,
+                         const double* z, const double* sat, const int* nsat, const double* Qfull, const double* Rfull,
+                         double dt, const double* par, double* mu_traj_out, int correct_only, void* stream);
 
 /* Iterative GNSS least squares of B independent epochs (one solve per epoch).
  * replaces: iterativeLeastSquares, utils/leastsquares.py:19-42 (and, with tcol != NULL,

@@ -42,7 +42,7 @@ EXPORTS = ("nlpf_version", "nlpf_last_error", "nlpf_device_count", "nlpf_problem
            "nlpf_problem_destroy", "nlpf_problem_nz", "nlpf_assemble", "nlpf_factor_solve", "nlpf_solve",
            "nlpf_sample", "nlpf_ekf_run", "nlpf_ls_solve", "nlpf_ls_vel", "nlpf_fp64_probe", "nlpf_dmma_probe", "nlpf_blocktri_solve",
            "nlpf_problem_smem_bytes", "nlpf_ecef2enu", "nlpf_enu2lla", "nlpf_solve_chain",
-           "nlpf_problem_has_chain_kernel", "nlpf_problem_profile", "nlpf_ms_gather", "nlpf_ms_blocks")
+           "nlpf_problem_has_chain_kernel", "nlpf_problem_profile", "nlpf_ms_gather", "nlpf_ms_blocks", "nlpf_ekf_run_general")
 
 _lib = None
 
@@ -70,6 +70,8 @@ def lib():
     L.nlpf_sample.argtypes = [vp, ctypes.c_int, vp, ctypes.c_int, vp, vp, vp]
     L.nlpf_ekf_run.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, vp, vp, vp, vp, vp, vp, vp,
                                ctypes.c_double, ctypes.c_double, vp, vp, vp]
+    L.nlpf_ekf_run_general.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, vp, vp, vp, vp, vp, vp, vp, vp,
+                                       ctypes.c_double, vp, vp, ctypes.c_int, vp]
     L.nlpf_ls_solve.argtypes = [ctypes.c_int, ctypes.c_int, vp, vp, vp, vp, vp, ctypes.c_int, ctypes.c_double, vp, vp]
     L.nlpf_ls_vel.argtypes = [ctypes.c_int, ctypes.c_int, vp, vp, vp, vp, vp, vp, vp]
     L.nlpf_blocktri_solve.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int, vp, vp, vp, vp, vp, ctypes.c_int, vp]

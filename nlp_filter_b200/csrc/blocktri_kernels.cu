@@ -296,6 +296,15 @@ extern "C" int nlpf_blocktri_solve(int B, int nblk, int bs, const double* Dg, co
     const size_t sm_cr = sizeof(double) * (size_t)(BT_THREADS / 32) * (bs * (2 * bs + 1) + bs * bs);
     static bool attr = false;
     if (!attr) {
+        // keep the per-call workspace in the stream-ordered pool between calls: with the default release threshold (0)
+        // every synchronisation hands the memory back to the driver and the next call maps it again -- milliseconds
+        // per call, ten times the kernel itself on the 200-epoch workload
+        int devid = 0;
+        cudaMemPool_t pool;
+        if (cudaGetDevice(&devid) == cudaSuccess && cudaDeviceGetDefaultMemPool(&pool, devid) == cudaSuccess) {
+            unsigned long long keep = ~0ULL;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
         cudaFuncSetAttribute(blocktri_riccati_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              (int)(sizeof(double) * (2 * BT_BS_MAX * BT_BS_MAX + BT_BS_MAX * (BT_BS_MAX + 1))));
         cudaFuncSetAttribute(blocktri_cr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,

@@ -13,6 +13,7 @@
 // (G has full column rank whenever >= 4 (5) satellites are in view).
 #include "common.cuh"
 #include <math.h>
+#include <stdlib.h>
 
 #define EKF_NMAX 9
 #define EKF_SMAX 16
@@ -103,15 +104,23 @@ __device__ void ekf_dyn_car9(double* x, const double* u, double dt, const double
 // MODEL is a template parameter: n and m are compile-time (index arithmetic of the small matrix products folds,
 // loops unroll); the number of warps per CTA is the launch's blockDim (small batches: one filter per CTA so that
 // 256 filters spread over all SMs instead of 64 of them).
-template <int MODEL>
+// TILE = lanes per filter: 32 (one filter per warp: small batches, every filter gets a warp scheduler slot of its own)
+// or 16 (two filters per warp: the Cholesky and the substitutions use at most 16 lanes -- EKF_SMAX rows -- so at
+// machine-filling batch sizes half of every warp instruction was idle lanes).  A filter's lanes synchronise with
+// the mask of their own half, so the two filters of a warp may take different numbers of measurements.
+// Qfull / Rfull (may be null): full n x n process covariance and full smax x smax measurement covariance instead of
+// the diagonal Q[n] and r I; correct_only: skip the prediction (S_pred = S, mean untouched) -- EKF.correct, ekf.py:46-61.
+template <int MODEL, int TILE>
 __global__ void __launch_bounds__(EKF_WARPS * 32)
 ekf_kernel(int B, int steps, int smax, double* __restrict__ mu_io, double* __restrict__ S_io,
            const double* __restrict__ u, const double* __restrict__ z, const double* __restrict__ sat,
            const int* __restrict__ nsat, const double* __restrict__ Q, double rvar, double dt,
-           const double* __restrict__ par, double* __restrict__ traj) {
+           const double* __restrict__ par, double* __restrict__ traj, const double* __restrict__ Qfull,
+           const double* __restrict__ Rfull, int correct_only) {
     extern __shared__ double ekf_sm_raw[];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wpc = blockDim.x >> 5;
-    EkfSm& W = reinterpret_cast<EkfSm*>(ekf_sm_raw)[warp];
+    const int lane = threadIdx.x & (TILE - 1), slot = threadIdx.x / TILE, wpc = blockDim.x / TILE;
+    const unsigned tmask = (TILE == 32) ? 0xffffffffu : (0xffffu << (16 * ((threadIdx.x >> 4) & 1)));
+    EkfSm& W = reinterpret_cast<EkfSm*>(ekf_sm_raw)[slot];
     constexpr int model = MODEL;
     constexpr int n = (MODEL == NLPF_EKF_GNSS5) ? 5 : 9;
     constexpr int m = (MODEL == NLPF_EKF_GNSS5) ? 3 : 2;
@@ -121,38 +130,42 @@ ekf_kernel(int B, int steps, int smax, double* __restrict__ mu_io, double* __res
     double cpar[NLPF_NDYNPAR];
     for (int i = 0; i < NLPF_NDYNPAR; ++i) cpar[i] = par ? par[i] : 0.0;
 
-    for (int f = blockIdx.x * wpc + warp; f < B; f += gridDim.x * wpc) {
-        for (int i = lane; i < n; i += 32) W.mu[i] = mu_io[(size_t)f * n + i];
-        for (int i = lane; i < n * n; i += 32) W.S[i] = S_io[(size_t)f * n * n + i];
-        __syncwarp();
+    for (int f = blockIdx.x * wpc + slot; f < B; f += gridDim.x * wpc) {
+        for (int i = lane; i < n; i += TILE) W.mu[i] = mu_io[(size_t)f * n + i];
+        for (int i = lane; i < n * n; i += TILE) W.S[i] = S_io[(size_t)f * n * n + i];
+        __syncwarp(tmask);
         for (int t = 0; t < steps; ++t) {
             const size_t ft = (size_t)f * steps + t;
             // ---- predict (ekf.py:40-44) ----
-            if (lane == 0) {
+            if (lane == 0 && !correct_only) {
                 double uu[3];
                 for (int i = 0; i < m; ++i) uu[i] = u[ft * m + i];
                 if (model == NLPF_EKF_GNSS5) ekf_dyn_gnss5(W.mu, uu, dt, W.G);
                 else ekf_dyn_car9(W.mu, uu, dt, cpar, W.G);
             }
-            __syncwarp();
-            for (int e = lane; e < n * n; e += 32) {      // T = S G^T
+            __syncwarp(tmask);
+            for (int e = lane; e < n * n; e += TILE) {      // T = S G^T
                 const int i = e / n, j = e - i * n;
                 double s = 0.0;
                 for (int k = 0; k < n; ++k) s = fma(W.S[i * n + k], W.G[j * n + k], s);
                 W.T[e] = s;
             }
-            __syncwarp();
-            for (int e = lane; e < n * n; e += 32) {      // S_pred = G T + Q
+            __syncwarp(tmask);
+            for (int e = lane; e < n * n; e += TILE) {      // S_pred = G T + Q
                 const int i = e / n, j = e - i * n;
                 double s = 0.0;
                 for (int k = 0; k < n; ++k) s = fma(W.G[i * n + k], W.T[k * n + j], s);
-                W.Sp[e] = s + ((i == j) ? Q[i] : 0.0);
+                W.Sp[e] = s + (Qfull ? Qfull[e] : ((i == j) ? Q[i] : 0.0));
             }
-            __syncwarp();
+            if (correct_only) {
+                __syncwarp(tmask);
+                for (int e = lane; e < n * n; e += TILE) W.Sp[e] = W.S[e];
+            }
+            __syncwarp(tmask);
             const int ns = min(max(nsat[ft], 0), smax);      // counts come from device memory: never index past the slots
             if (ns > 0) {
                 // ---- correct (ekf.py:46-61) ----
-                for (int s = lane; s < ns; s += 32) {
+                for (int s = lane; s < ns; s += TILE) {
                     const double* sp = sat + (ft * smax + s) * 3;
                     const double d0 = W.mu[ix] - sp[0], d1 = W.mu[iy] - sp[1], d2 = W.mu[iz] - sp[2];
                     const double rho = sqrt(d0 * d0 + d1 * d1 + d2 * d2);
@@ -163,40 +176,40 @@ ekf_kernel(int B, int steps, int smax, double* __restrict__ mu_io, double* __res
                     W.H[s * n + ib] = 1.0;
                     W.v[s] = z[ft * smax + s] - (rho + W.mu[ib]);
                 }
-                __syncwarp();
-                for (int e = lane; e < ns * n; e += 32) {          // HS = H S_pred
+                __syncwarp(tmask);
+                for (int e = lane; e < ns * n; e += TILE) {          // HS = H S_pred
                     const int s = e / n, j = e - s * n;
                     double acc = 0.0;
                     for (int k = 0; k < n; ++k) acc = fma(W.H[s * n + k], W.Sp[k * n + j], acc);
                     W.HS[e] = acc;
                 }
-                __syncwarp();
-                for (int e = lane; e < ns * ns; e += 32) {         // P = (H S_pred) H^T + R  (ekf.py:54)
+                __syncwarp(tmask);
+                for (int e = lane; e < ns * ns; e += TILE) {         // P = (H S_pred) H^T + R  (ekf.py:54)
                     const int s = e / ns, s2 = e - s * ns;
                     double acc = 0.0;
                     for (int k = 0; k < n; ++k) acc = fma(W.HS[s * n + k], W.H[s2 * n + k], acc);
-                    W.P[s * (EKF_SMAX + 1) + s2] = acc + ((s == s2) ? rvar : 0.0);
+                    W.P[s * (EKF_SMAX + 1) + s2] = acc + (Rfull ? Rfull[s * smax + s2] : ((s == s2) ? rvar : 0.0));
                 }
-                __syncwarp();
+                __syncwarp(tmask);
                 // Cholesky P = L L^T in place (lower), lane = row.  (A register-resident variant -- rows in registers, the
                 // eliminated column by shuffles, loops unrolled to EKF_SMAX -- was measured at 0.65x of this one.)
                 for (int j = 0; j < ns; ++j) {
                     double djj = sqrt(W.P[j * (EKF_SMAX + 1) + j]);
-                    __syncwarp();
+                    __syncwarp(tmask);
                     if (lane == j) W.P[j * (EKF_SMAX + 1) + j] = djj;
                     if (lane > j && lane < ns) W.P[lane * (EKF_SMAX + 1) + j] /= djj;
-                    __syncwarp();
+                    __syncwarp(tmask);
                     if (lane > j && lane < ns) {
                         const double lij = W.P[lane * (EKF_SMAX + 1) + j];
                         for (int k = j + 1; k <= lane; ++k)
                             W.P[lane * (EKF_SMAX + 1) + k] = fma(-lij, W.P[k * (EKF_SMAX + 1) + j], W.P[lane * (EKF_SMAX + 1) + k]);
                     }
-                    __syncwarp();
+                    __syncwarp(tmask);
                 }
                 // K^T = P^-1 (H S_pred): one right-hand-side column per lane (K = S_pred H^T P^-1).  (Column-oriented
                 // substitutions with lane = row were measured at 0.74x: the pivot's n divisions then run one after the
                 // other in a single lane instead of side by side in n lanes.)
-                for (int c = lane; c < n; c += 32) {
+                for (int c = lane; c < n; c += TILE) {
                     for (int s = 0; s < ns; ++s) {
                         double acc = W.HS[s * n + c];
                         for (int k = 0; k < s; ++k) acc = fma(-W.P[s * (EKF_SMAX + 1) + k], W.Kt[k * n + c], acc);
@@ -208,58 +221,88 @@ ekf_kernel(int B, int steps, int smax, double* __restrict__ mu_io, double* __res
                         W.Kt[s * n + c] = acc / W.P[s * (EKF_SMAX + 1) + s];
                     }
                 }
-                __syncwarp();
+                __syncwarp(tmask);
                 // Note: K uses HS^T = S_pred^T H^T; the reference forms S_pred H^T.  S_pred is symmetric up
                 // to rounding, so the two differ at the 1e-16 level only.
                 double mucor = 0.0;
                 if (lane < n) {
                     for (int s = 0; s < ns; ++s) mucor = fma(W.Kt[s * n + lane], W.v[s], mucor);
                 }
-                for (int e = lane; e < n * n; e += 32) {           // S = S_pred - K (H S_pred)
+                for (int e = lane; e < n * n; e += TILE) {           // S = S_pred - K (H S_pred)
                     const int i = e / n, j = e - i * n;
                     double acc = 0.0;
                     for (int s = 0; s < ns; ++s) acc = fma(W.Kt[s * n + i], W.HS[s * n + j], acc);
                     W.S[e] = W.Sp[e] - acc;
                 }
-                __syncwarp();
+                __syncwarp(tmask);
                 if (lane < n) W.mu[lane] += mucor;
             } else {
-                for (int e = lane; e < n * n; e += 32) W.S[e] = W.Sp[e];
+                for (int e = lane; e < n * n; e += TILE) W.S[e] = W.Sp[e];
             }
-            __syncwarp();
+            __syncwarp(tmask);
             if (traj)
-                for (int i = lane; i < n; i += 32) traj[ft * n + i] = W.mu[i];
+                for (int i = lane; i < n; i += TILE) traj[ft * n + i] = W.mu[i];
         }
-        for (int i = lane; i < n; i += 32) mu_io[(size_t)f * n + i] = W.mu[i];
-        for (int i = lane; i < n * n; i += 32) S_io[(size_t)f * n * n + i] = W.S[i];
-        __syncwarp();
+        for (int i = lane; i < n; i += TILE) mu_io[(size_t)f * n + i] = W.mu[i];
+        for (int i = lane; i < n * n; i += TILE) S_io[(size_t)f * n * n + i] = W.S[i];
+        __syncwarp(tmask);
     }
+}
+
+static int ekf_launch(int model, int B, int steps, int smax, double* mu_inout, double* S_inout, const double* u,
+                      const double* z, const double* sat, const int* nsat, const double* Q, double r, double dt,
+                      const double* par, double* mu_traj_out, const double* Qfull, const double* Rfull, int correct_only,
+                      void* stream) {
+    if (model != NLPF_EKF_GNSS5 && model != NLPF_EKF_CAR9) { nlpf_set_error("unknown EKF model %d", model); return NLPF_E_ARG; }
+    if (B < 1 || steps < 1 || smax < 1 || smax > EKF_SMAX) { nlpf_set_error("bad EKF sizes B=%d steps=%d smax=%d (smax<=%d)", B, steps, smax, EKF_SMAX); return NLPF_E_ARG; }
+    if (!mu_inout || !S_inout || !u || !z || !sat || !nsat || (!Q && !Qfull)) { nlpf_set_error("null EKF buffer"); return NLPF_E_ARG; }
+    if (model == NLPF_EKF_CAR9 && !par) { nlpf_set_error("vehicle EKF needs the car constants"); return NLPF_E_ARG; }
+    static bool attr_done = false;
+    if (!attr_done) {
+        const int full = (int)(sizeof(EkfSm) * EKF_WARPS * 2);
+        if (nlpf_check_cuda(cudaFuncSetAttribute(ekf_kernel<NLPF_EKF_GNSS5, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, full), "ekf smem attr")) return NLPF_E_CUDA;
+        if (nlpf_check_cuda(cudaFuncSetAttribute(ekf_kernel<NLPF_EKF_CAR9, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, full), "ekf smem attr")) return NLPF_E_CUDA;
+        if (nlpf_check_cuda(cudaFuncSetAttribute(ekf_kernel<NLPF_EKF_GNSS5, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, full), "ekf smem attr")) return NLPF_E_CUDA;
+        if (nlpf_check_cuda(cudaFuncSetAttribute(ekf_kernel<NLPF_EKF_CAR9, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, full), "ekf smem attr")) return NLPF_E_CUDA;
+        attr_done = true;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    static const char* force = getenv("NLPF_EKF_TILE");
+    // two filters per warp once there are more filters than warp slots the machine keeps resident (148 SMs x 16 warps)
+    const bool half = force ? (atoi(force) == 16) : (B > 148 * 16);
+    if (!half) {
+        // filters per CTA: 1 until every SM has a few CTAs, then up to EKF_WARPS
+        int wpc = 1;
+        while (wpc < EKF_WARPS && (B + wpc - 1) / wpc > 148 * 4) wpc *= 2;
+        const size_t smem = sizeof(EkfSm) * wpc;
+        const int blocks = (B + wpc - 1) / wpc;
+        if (model == NLPF_EKF_GNSS5)
+            ekf_kernel<NLPF_EKF_GNSS5, 32><<<blocks, wpc * 32, smem, st>>>(B, steps, smax, mu_inout, S_inout, u, z, sat, nsat, Q, r, dt, par, mu_traj_out, Qfull, Rfull, correct_only);
+        else
+            ekf_kernel<NLPF_EKF_CAR9, 32><<<blocks, wpc * 32, smem, st>>>(B, steps, smax, mu_inout, S_inout, u, z, sat, nsat, Q, r, dt, par, mu_traj_out, Qfull, Rfull, correct_only);
+    } else {
+        const int fpc = EKF_WARPS * 2;                    // filters per CTA
+        const size_t smem = sizeof(EkfSm) * fpc;
+        const int blocks = (B + fpc - 1) / fpc;
+        if (model == NLPF_EKF_GNSS5)
+            ekf_kernel<NLPF_EKF_GNSS5, 16><<<blocks, EKF_WARPS * 32, smem, st>>>(B, steps, smax, mu_inout, S_inout, u, z, sat, nsat, Q, r, dt, par, mu_traj_out, Qfull, Rfull, correct_only);
+        else
+            ekf_kernel<NLPF_EKF_CAR9, 16><<<blocks, EKF_WARPS * 32, smem, st>>>(B, steps, smax, mu_inout, S_inout, u, z, sat, nsat, Q, r, dt, par, mu_traj_out, Qfull, Rfull, correct_only);
+    }
+    return nlpf_check_cuda(cudaGetLastError(), "ekf_kernel launch");
 }
 
 extern "C" int nlpf_ekf_run(int model, int B, int steps, int smax, double* mu_inout, double* S_inout, const double* u,
                             const double* z, const double* sat, const int* nsat, const double* Q, double r, double dt,
                             const double* par, double* mu_traj_out, void* stream) {
-    if (model != NLPF_EKF_GNSS5 && model != NLPF_EKF_CAR9) { nlpf_set_error("unknown EKF model %d", model); return NLPF_E_ARG; }
-    if (B < 1 || steps < 1 || smax < 1 || smax > EKF_SMAX) { nlpf_set_error("bad EKF sizes B=%d steps=%d smax=%d (smax<=%d)", B, steps, smax, EKF_SMAX); return NLPF_E_ARG; }
-    if (!mu_inout || !S_inout || !u || !z || !sat || !nsat || !Q) { nlpf_set_error("null EKF buffer"); return NLPF_E_ARG; }
-    if (model == NLPF_EKF_CAR9 && !par) { nlpf_set_error("vehicle EKF needs the car constants"); return NLPF_E_ARG; }
-    static bool attr_done = false;
-    if (!attr_done) {
-        const int full = (int)(sizeof(EkfSm) * EKF_WARPS);
-        if (nlpf_check_cuda(cudaFuncSetAttribute(ekf_kernel<NLPF_EKF_GNSS5>, cudaFuncAttributeMaxDynamicSharedMemorySize, full), "ekf smem attr")) return NLPF_E_CUDA;
-        if (nlpf_check_cuda(cudaFuncSetAttribute(ekf_kernel<NLPF_EKF_CAR9>, cudaFuncAttributeMaxDynamicSharedMemorySize, full), "ekf smem attr")) return NLPF_E_CUDA;
-        attr_done = true;
-    }
-    // filters per CTA: 1 until every SM has a few CTAs, then up to EKF_WARPS
-    int wpc = 1;
-    while (wpc < EKF_WARPS && (B + wpc - 1) / wpc > 148 * 4) wpc *= 2;
-    const size_t smem = sizeof(EkfSm) * wpc;
-    const int blocks = (B + wpc - 1) / wpc;
-    if (model == NLPF_EKF_GNSS5)
-        ekf_kernel<NLPF_EKF_GNSS5><<<blocks, wpc * 32, smem, (cudaStream_t)stream>>>(B, steps, smax, mu_inout, S_inout, u, z, sat, nsat, Q, r, dt, par, mu_traj_out);
-    else
-        ekf_kernel<NLPF_EKF_CAR9><<<blocks, wpc * 32, smem, (cudaStream_t)stream>>>(B, steps, smax, mu_inout, S_inout, u, z, sat, nsat, Q, r, dt, par, mu_traj_out);
-    return nlpf_check_cuda(cudaGetLastError(), "ekf_kernel launch");
+    return ekf_launch(model, B, steps, smax, mu_inout, S_inout, u, z, sat, nsat, Q, r, dt, par, mu_traj_out, nullptr, nullptr, 0, stream);
+}
+
+extern "C" int nlpf_ekf_run_general(int model, int B, int steps, int smax, double* mu_inout, double* S_inout, const double* u,
+                                    const double* z, const double* sat, const int* nsat, const double* Qfull, const double* Rfull,
+                                    double dt, const double* par, double* mu_traj_out, int correct_only, void* stream) {
+    if (!Qfull || !Rfull) { nlpf_set_error("nlpf_ekf_run_general needs the full Q (n x n) and R (smax x smax)"); return NLPF_E_ARG; }
+    return ekf_launch(model, B, steps, smax, mu_inout, S_inout, u, z, sat, nsat, nullptr, 0.0, dt, par, mu_traj_out, Qfull, Rfull, correct_only, stream);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -352,10 +395,97 @@ ls_kernel(int B, int smax, const double* __restrict__ sat, const double* __restr
     }
 }
 
+// Thread-per-epoch variant for batches that fill the machine.  The warp-per-epoch kernel above spends its time in the
+// 14 x 5 shuffle reductions of every Gauss-Newton iteration (profiles/r1_ls_kernel_full.json: 12 of 32 lanes carry a
+// satellite) and re-reads the epoch's records from L1/L2 each iteration; measured 139 M epochs/s at 16 384 epochs and
+// only 155 M at a million (64 GB/s of HBM).  Here one thread owns an epoch: its <= SMAX satellite records are read ONCE
+// (416 contiguous bytes) into registers, the normal equations are summed in the thread, no shuffles.  Same arithmetic
+// per satellite and the same Cholesky; only the order of the sums over satellites differs (sequential instead of a
+// butterfly), i.e. results agree to rounding.
+template <int NU, int SMAX>
+__global__ void __launch_bounds__(128)
+ls_thread_kernel(int B, int smax, const double* __restrict__ sat, const double* __restrict__ pr, const int* __restrict__ nsat,
+                 const double* __restrict__ tcol, double* __restrict__ x_io, int maxiter, double tol, int* __restrict__ iters_out) {
+    constexpr int NP = NU * (NU + 1) / 2;
+    for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < (size_t)B; e += (size_t)gridDim.x * blockDim.x) {
+        double x[NU];
+#pragma unroll
+        for (int i = 0; i < NU; ++i) x[i] = x_io[e * NU + i];
+        const int ns = min(max(nsat[e], 0), smax);
+        const double* se = sat + e * smax * 3;
+        const double* pe = pr + e * smax;
+        double sx[SMAX], sy[SMAX], sz[SMAX], pv[SMAX], tv[(NU == 5) ? SMAX : 1];
+#pragma unroll
+        for (int s = 0; s < SMAX; ++s) {
+            const bool on = s < ns;
+            sx[s] = on ? se[s * 3 + 0] : 0.0;
+            sy[s] = on ? se[s * 3 + 1] : 0.0;
+            sz[s] = on ? se[s * 3 + 2] : 0.0;
+            pv[s] = on ? pe[s] : 0.0;
+            if (NU == 5) tv[s] = on ? tcol[e * smax + s] : 0.0;
+        }
+        int it = 0;
+        for (; it < maxiter;) {
+            double N[NP], rhs[NU];
+#pragma unroll
+            for (int i = 0; i < NP; ++i) N[i] = 0.0;
+#pragma unroll
+            for (int i = 0; i < NU; ++i) rhs[i] = 0.0;
+#pragma unroll
+            for (int s = 0; s < SMAX; ++s) {
+                if (s < ns) {
+                    const double d0 = x[0] - sx[s], d1 = x[1] - sy[s], d2 = x[2] - sz[s];
+                    const double rho = sqrt(d0 * d0 + d1 * d1 + d2 * d2);
+                    double row[NU];
+                    row[0] = d0 / rho;      // -(sat - x)/|sat - x|, leastsquares.py:6-16
+                    row[1] = d1 / rho;
+                    row[2] = d2 / rho;
+                    row[3] = 1.0;
+                    double pred = rho + x[3];
+                    if (NU == 5) {
+                        row[NU - 1] = tv[s];
+                        pred += x[NU - 1] * tv[s];
+                    }
+                    const double dr = pv[s] - pred;
+                    int q = 0;
+#pragma unroll
+                    for (int i = 0; i < NU; ++i) {
+#pragma unroll
+                        for (int j = 0; j <= i; ++j) N[q++] += row[i] * row[j];
+                        rhs[i] += row[i] * dr;
+                    }
+                }
+            }
+            ++it;
+            if (!chol_solve_small<NU>(N, rhs)) break;        // rank deficient geometry: leave x as is
+            double nrm = 0.0;
+#pragma unroll
+            for (int i = 0; i < NU; ++i) { x[i] += rhs[i]; nrm += rhs[i] * rhs[i]; }
+            if (sqrt(nrm) < tol) break;                      // leastsquares.py:39
+        }
+#pragma unroll
+        for (int i = 0; i < NU; ++i) x_io[e * NU + i] = x[i];
+        if (iters_out) iters_out[e] = it;
+    }
+}
+
 extern "C" int nlpf_ls_solve(int B, int smax, const double* sat, const double* pr, const int* nsat, const double* tcol,
                              double* x_inout, int maxiter, double tol, int* iters_out, void* stream) {
     if (B < 1 || smax < 1 || !sat || !pr || !nsat || !x_inout) { nlpf_set_error("bad LS argument"); return NLPF_E_ARG; }
     const int threads = 128;
+    static const char* force = getenv("NLPF_LS_WARP");
+    if (B >= 2048 && smax <= 16 && !force) {               // enough epochs for a thread each (16 384 epochs = 128 CTAs)
+        const int tb = (B + threads - 1) / threads;
+        cudaStream_t st = (cudaStream_t)stream;
+        if (smax <= 12) {
+            if (tcol) ls_thread_kernel<5, 12><<<tb, threads, 0, st>>>(B, smax, sat, pr, nsat, tcol, x_inout, maxiter, tol, iters_out);
+            else ls_thread_kernel<4, 12><<<tb, threads, 0, st>>>(B, smax, sat, pr, nsat, nullptr, x_inout, maxiter, tol, iters_out);
+        } else {
+            if (tcol) ls_thread_kernel<5, 16><<<tb, threads, 0, st>>>(B, smax, sat, pr, nsat, tcol, x_inout, maxiter, tol, iters_out);
+            else ls_thread_kernel<4, 16><<<tb, threads, 0, st>>>(B, smax, sat, pr, nsat, nullptr, x_inout, maxiter, tol, iters_out);
+        }
+        return nlpf_check_cuda(cudaGetLastError(), "ls_thread_kernel launch");
+    }
     int blocks = (int)(((size_t)B * 32 + threads - 1) / threads);
     if (blocks > 148 * 16) blocks = 148 * 16;
     if (tcol) ls_kernel<5><<<blocks, threads, 0, (cudaStream_t)stream>>>(B, smax, sat, pr, nsat, tcol, x_inout, maxiter, tol, iters_out);

@@ -346,10 +346,11 @@ EKF_GNSS5 = 0
 EKF_CAR9 = 1
 
 
-def ekf_run(model, mu, S, u, z, sat, nsat, Q, r, dt, par=None, want_traj=True):
+def ekf_run(model, mu, S, u, z, sat, nsat, Q, r, dt, par=None, want_traj=True, correct_only=False):
     """`steps` fused predict/update steps of B filters (utils/ekf.py:20-61).
     mu (B,n), S (B,n,n), u (B,steps,m), z (B,steps,smax), sat (B,steps,smax,3), nsat (B,steps) int32,
-    Q (n,) diagonal.  mu and S are updated in place (device tensors); returns the mean trajectory."""
+    Q (n,) diagonal or (n,n) full; r scalar variance or (smax,smax) full covariance.  correct_only: EKF.correct
+    alone.  mu and S are updated in place (device tensors); returns the mean trajectory."""
     _require_cuda()
     L = _capi.lib()
     mu, S = _f8(mu), _f8(S)
@@ -362,13 +363,23 @@ def ekf_run(model, mu, S, u, z, sat, nsat, Q, r, dt, par=None, want_traj=True):
         raise _capi.NlpfError("ekf_run: nsat outside [0, %d]" % smax)
     nsat = torch.as_tensor(nsat).to(device=mu.device, dtype=torch.int32).contiguous()
     for name, t, shape in (("S", S, (B, n, n)), ("z", z, (B, steps, smax)), ("sat", sat, (B, steps, smax, 3)),
-                           ("Q", _f8(Q), (n,))):
+                           ):
         _want(name, t, shape)
     if nsat.numel() != B * steps:
         raise _capi.NlpfError("ekf_run: nsat has %d entries, expected %d" % (nsat.numel(), B * steps))
     Q = _f8(Q)
     par_t = _f8(np.concatenate([np.asarray(par, float), np.zeros(16 - len(par))])) if par is not None else None
     traj = torch.empty((B, steps, n), dtype=torch.float64, device=mu.device) if want_traj else None
+    r_full = np.ndim(r) == 2 if not isinstance(r, torch.Tensor) else r.dim() == 2
+    if Q.dim() == 2 or r_full or correct_only:
+        Qf = Q if Q.dim() == 2 else torch.diag(Q)
+        Rf = _f8(r, (smax, smax)) if r_full else torch.eye(smax, dtype=torch.float64, device=mu.device) * float(r)
+        _want("Q", Qf.contiguous(), (n, n))
+        _capi.check(L.nlpf_ekf_run_general(int(model), B, steps, smax, _ptr(mu), _ptr(S), _ptr(u), _ptr(z), _ptr(sat), _ptr(nsat),
+                                           _ptr(Qf.contiguous()), _ptr(Rf.contiguous()), float(dt), _ptr(par_t), _ptr(traj),
+                                           1 if correct_only else 0, _stream()))
+        return mu, S, traj
+    _want("Q", Q, (n,))
     _capi.check(L.nlpf_ekf_run(int(model), B, steps, smax, _ptr(mu), _ptr(S), _ptr(u), _ptr(z), _ptr(sat), _ptr(nsat),
                                _ptr(Q), float(r), float(dt), _ptr(par_t), _ptr(traj), _stream()))
     return mu, S, traj

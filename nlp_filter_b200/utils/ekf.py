@@ -51,17 +51,17 @@ class EKF(object):
         mu = np.asarray(self.mu, dtype=float).reshape(1, n)
         S = np.asarray(self.S, dtype=float).reshape(1, n, n)
         Qd = np.asarray(Q, dtype=float)
-        if Qd.ndim == 2:
-            if np.any(np.abs(Qd - np.diag(np.diag(Qd))) > 0):
-                raise NotImplementedError("the fused filter step takes a diagonal process covariance Q")
-            Qd = np.diag(Qd)
+        if Qd.ndim == 2 and not np.any(np.abs(Qd - np.diag(np.diag(Qd))) > 0):
+            Qd = np.diag(Qd)                   # diagonal process covariance: the kernel's fast path (a full Q is passed as is)
         if z is not None:
             z = np.asarray(z, dtype=float).reshape(-1)
             ns = z.shape[0]
             Rm = np.asarray(R, dtype=float)
             r = float(Rm[0, 0]) if Rm.ndim == 2 else float(Rm.reshape(-1)[0])
             if Rm.ndim == 2 and np.any(np.abs(Rm - r * np.eye(ns)) > 0):
-                raise NotImplementedError("the fused filter step takes R = r I (one pseudorange variance)")
+                r = Rm.reshape(ns, ns)         # general measurement covariance (ekf.py:54)
+            elif Rm.ndim == 1 and Rm.size == ns and np.any(Rm != r):
+                r = np.diag(Rm)
             sat = np.asarray(meas_func_params["sat_pos"], dtype=float).reshape(1, 1, ns, 3)
             zz = z.reshape(1, 1, ns)
         else:
@@ -94,4 +94,21 @@ class EKF(object):
         return self.mu, S_pred
 
     def correct(self, mu_pred, S_pred, z, R, meas_func, meas_func_params):
-        raise NotImplementedError("correct() alone is not exposed by the fused kernel; call update()")
+        """Measurement update alone (ekf.py:46-61): returns the corrections (mu_cor, S_cor) the reference returns,
+        mu = mu_pred + mu_cor, S = S_pred + S_cor; the filter's own state is not touched."""
+        from .. import engine
+        model = self._model(meas_func)
+        n = 5 if model == EKF_GNSS5 else 9
+        z = np.asarray(z, dtype=float).reshape(-1)
+        ns = z.shape[0]
+        Rm = np.asarray(R, dtype=float)
+        Rf = Rm.reshape(ns, ns) if Rm.ndim == 2 else (np.diag(Rm.reshape(-1)) if Rm.size == ns else float(Rm.reshape(-1)[0]) * np.eye(ns))
+        mu0 = np.asarray(mu_pred, dtype=float).reshape(1, n)
+        S0 = np.asarray(S_pred, dtype=float).reshape(1, n, n)
+        sat = np.asarray(meas_func_params["sat_pos"], dtype=float).reshape(1, 1, ns, 3)
+        par = [1.0] * 6 if model == EKF_CAR9 else None
+        m = 3 if model == EKF_GNSS5 else 2
+        mu_d, S_d, _ = engine.ekf_run(model, mu0.copy(), S0.copy(), np.zeros((1, 1, m)), z.reshape(1, 1, ns), sat,
+                                      np.array([[ns]], dtype=np.int32), np.zeros(n), Rf, 0.0, par=par, want_traj=False,
+                                      correct_only=True)
+        return mu_d.cpu().numpy()[0] - mu0[0], S_d.cpu().numpy()[0] - S0[0]

@@ -94,20 +94,26 @@ def dyn_car9(x, u, dt, par):
 # ------------------------------------------------------------------------------------------
 # EKF (utils/ekf.py:20-61)
 # ------------------------------------------------------------------------------------------
-def ekf_step(model, mu, S, u, z, sat_pos, Qdiag, rvar, dt, par=None):
-    """One EKF.update: predict, then correct when z is not None.  Returns (mu, S)."""
+def ekf_step(model, mu, S, u, z, sat_pos, Qdiag, rvar, dt, par=None, correct_only=False):
+    """One EKF.update: predict, then correct when z is not None.  Returns (mu, S).  Qdiag may also be the full
+    n x n process covariance, rvar the full measurement covariance (ekf.py:43,54 take matrices); correct_only
+    is EKF.correct alone (ekf.py:46-61) applied to (mu, S) = (mu_pred, S_pred)."""
     mu = np.array(mu, dtype=float)
-    if model == 0:
-        mu, G = dyn_gnss5(mu, u, dt)
-        cols = (0, 1, 2, 3)
+    cols = (0, 1, 2, 3) if model == 0 else (0, 1, 8, 6)
+    if correct_only:
+        S_pred = np.array(S, dtype=float)
     else:
-        mu, G = dyn_car9(mu, u, dt, par)
-        cols = (0, 1, 8, 6)
-    S_pred = np.matmul(G, np.matmul(S, G.T)) + np.diag(Qdiag)
+        if model == 0:
+            mu, G = dyn_gnss5(mu, u, dt)
+        else:
+            mu, G = dyn_car9(mu, u, dt, par)
+        Qm = np.asarray(Qdiag, dtype=float)
+        S_pred = np.matmul(G, np.matmul(S, G.T)) + (Qm if Qm.ndim == 2 else np.diag(Qm))
     if z is None or len(z) == 0:
         return mu, S_pred
     z_pred, H = multi_pseudorange(mu, sat_pos, cols)
-    P = np.matmul(H, np.matmul(S_pred, H.T)) + rvar * np.eye(len(z))
+    Rm = np.asarray(rvar, dtype=float)
+    P = np.matmul(H, np.matmul(S_pred, H.T)) + (Rm if Rm.ndim == 2 else float(Rm) * np.eye(len(z)))
     K = np.matmul(S_pred, np.matmul(H.T, np.linalg.inv(P)))
     mu = mu + np.matmul(K, z - z_pred)
     S = S_pred - np.matmul(K, np.matmul(H, S_pred))

@@ -174,3 +174,71 @@ def test_coordinate_kernels_match_values_stored_by_the_reference():
     # the car's satellites too (autonomous-car.py:152-154)
     out = eng.ecef2enu_batch(np.ascontiguousarray(g["sat_ecef"]), p_ref).cpu().numpy()
     assert np.max(np.abs(out - g["sat_enu"])) < 1e-7
+
+
+def _rand_spd(rng, n, scale):
+    M = rng.normal(size=(n, n))
+    return scale * (M @ M.T + n * np.eye(n))
+
+
+def test_ekf_full_covariances_and_correct_alone(G):
+    """utils/ekf.py:43,54 take matrix covariances and :46-61 is callable on its own; the fused kernel takes a full Q
+    (n x n), a full R (ns x ns) and a correction-only mode.  Checked against the restated update (oracle/ekf_ls.py)
+    and through the reference's class interface."""
+    from oracle import ekf_ls
+    import utils.ekf as uekf
+    import utils.gnss as ugnss
+    eng = _eng()
+    rng = np.random.default_rng(17)
+    B, steps, S = 6, 12, 9
+    x0 = G["syn_ekf_x0"][:B].copy()
+    u = rng.normal(size=(B, steps, 3))
+    z = G["syn_ekf_z"][:B, :steps, :S].copy()
+    sat = G["syn_ekf_sat"][:B, :steps, :S].copy()
+    nsat = rng.integers(4, S + 1, (B, steps)).astype(np.int32)
+    Q, R = _rand_spd(rng, 5, 1e-3), _rand_spd(rng, S, 10.0)
+    mu, Sd, traj = eng.ekf_run(eng.EKF_GNSS5, x0, np.tile(np.eye(5), (B, 1, 1)), u, z, sat, nsat, Q, R, 1.0)
+    traj, Sd = traj.cpu().numpy(), Sd.cpu().numpy()
+    for b in range(B):
+        m, Sm = x0[b].copy(), np.eye(5)
+        for t in range(steps):
+            k = nsat[b, t]
+            m, Sm = ekf_ls.ekf_step(0, m, Sm, u[b, t], z[b, t, :k], sat[b, t, :k], Q, R[:k, :k], 1.0)
+            assert _relerr(traj[b, t], m) < 1e-9
+        assert np.max(np.abs(Sd[b] - Sm)) < 1e-9 * (1 + np.max(np.abs(Sm)))
+    # EKF.correct alone, and update() with matrix covariances, through the class interface
+    f = uekf.EKF(ugnss.gnss_pos_and_bias, ugnss.multi_pseudorange, x0[0].copy(), np.eye(5))
+    Rk = R[:7, :7]
+    mu_cor, S_cor = f.correct(x0[0], 2.0 * np.eye(5), z[0, 0, :7], Rk, None, {"sat_pos": sat[0, 0, :7]})
+    m_ref, S_ref = ekf_ls.ekf_step(0, x0[0], 2.0 * np.eye(5), None, z[0, 0, :7], sat[0, 0, :7], None, Rk, 0.0, correct_only=True)
+    assert _relerr(x0[0] + mu_cor, m_ref) < 1e-9 and np.max(np.abs(2.0 * np.eye(5) + S_cor - S_ref)) < 1e-9
+    assert np.array_equal(f.mu, x0[0]) and np.array_equal(f.S, np.eye(5))          # the filter itself is untouched
+    f.update(u[0, 0], z[0, 0, :7], Q, Rk, dyn_func_params={"dt": 1.0}, meas_func_params={"sat_pos": sat[0, 0, :7]})
+    m_ref, S_ref = ekf_ls.ekf_step(0, x0[0], np.eye(5), u[0, 0], z[0, 0, :7], sat[0, 0, :7], Q, Rk, 1.0)
+    assert _relerr(f.mu, m_ref) < 1e-9 and np.max(np.abs(f.S - S_ref)) < 1e-9
+
+
+def test_two_filters_per_warp_equal_one_filter_per_warp():
+    """Above 2368 filters the kernel packs two filters into a warp (16 lanes each, their own synchronisation masks and
+    measurement counts); every output element is still produced by the same sequence of operations, so the results of
+    a large batch equal those of its filters run as a small batch bit for bit."""
+    eng = _eng()
+    rng = np.random.default_rng(23)
+    Bf, steps, S = 3000, 10, 12
+    pos = rng.normal(0, 5.0, (Bf, 3))
+    b0, al = rng.uniform(-1e3, 1e3, Bf), rng.normal(-190, 20, Bf)
+    dirs = rng.normal(size=(Bf, steps, S, 3)); dirs[..., 2] = np.abs(dirs[..., 2]) + 0.3
+    sat = dirs / np.linalg.norm(dirs, axis=3, keepdims=True) * rng.uniform(2.0e7, 2.6e7, (Bf, steps, S, 1))
+    t = np.arange(1, steps + 1)
+    z = np.linalg.norm(pos[:, None, None, :] - sat, axis=3) + b0[:, None, None] + al[:, None, None] * t[None, :, None] + rng.normal(0, 10, (Bf, steps, S))
+    nsat = rng.integers(0, S + 1, (Bf, steps)).astype(np.int32)
+    nsat[nsat < 4] = 0
+    x0 = np.concatenate([pos + rng.normal(0, 3, (Bf, 3)), b0[:, None], al[:, None]], 1)
+    Q = np.array([0.0001, 0.0001, 0.0001, 0.1, 0.001])
+    u = np.zeros((Bf, steps, 3))
+    big = eng.ekf_run(eng.EKF_GNSS5, x0, np.tile(np.eye(5), (Bf, 1, 1)), u, z, sat, nsat, Q, 100.0, 1.0)
+    sel = np.r_[0:60, 1500:1530, 2990:3000]
+    small = eng.ekf_run(eng.EKF_GNSS5, x0[sel], np.tile(np.eye(5), (len(sel), 1, 1)), u[sel], z[sel], sat[sel], nsat[sel], Q, 100.0, 1.0)
+    assert np.array_equal(big[2].cpu().numpy()[sel], small[2].cpu().numpy())
+    assert np.array_equal(big[1].cpu().numpy()[sel], small[1].cpu().numpy())
+    assert np.all(np.isfinite(big[2].cpu().numpy()))
