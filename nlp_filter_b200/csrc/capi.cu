@@ -37,6 +37,7 @@ extern "C" int nlpf_launch_solve_pr(nlpf_problem*, int, double*, const double*, 
                                     const double*, const nlpf_opts*, double*, int*, int*, double*, cudaStream_t);
 extern "C" int nlpf_launch_sample(nlpf_problem*, int, const double*, int, const double*, double*, cudaStream_t);
 extern "C" int nlpf_ws_variant(int K, int N, int M, int E, int NM, int dyn, int meas, int nb, int prior, int loss);
+extern "C" int nlpf_ws_wants_soa(int variant);
 extern "C" int nlpf_ws_assemble(int variant, nlpf_problem* p, int B, const double* z, const double* U, const double* data,
                                 const double* xprior, double mu, double* H_out, double* g_out, double* cost_out, cudaStream_t st);
 extern "C" int nlpf_ws_launch(int variant, nlpf_problem* p, int B, double* z, const double* U, const double* data,
@@ -571,7 +572,8 @@ static int ws_dispatch(nlpf_problem* p, int B, double* z, const double* U, const
                        const nlpf_opts* opts, double* cost_out, int* iters_out, int* status_out, int W,
                        const double* phiDT, double* Zout, cudaStream_t stream) {
     const int nzp = p->d.nz;
-    const size_t need = p->d.lin_meas ? (size_t)B * (2 * ((nzp + 1) >> 1) * ((nzp + 2) >> 1)) : 0;   // padded packed rows
+    size_t need = p->d.lin_meas ? (size_t)B * (2 * ((nzp + 1) >> 1) * ((nzp + 2) >> 1)) : 0;   // padded packed rows
+    if (nlpf_ws_wants_soa(p->ws_variant)) need = (size_t)W * B * p->d.Ldata;                        // structure-of-arrays copy of the records
     if (need > p->scratch_doubles) {
         if (p->scratch) { cudaStreamSynchronize(stream); cudaFree(p->scratch); p->scratch = nullptr; p->scratch_doubles = 0; }
         if (nlpf_check_cuda(cudaMalloc((void**)&p->scratch, need * sizeof(double)), "cudaMalloc(constant-H cache)")) return NLPF_E_CUDA;

@@ -28,6 +28,9 @@
                           // pivots to 1e-12 relative perturb the STEP by that much, the iteration converges to the same
                           // point (the gradient decides, not the factorisation); +2.5 % on the van der Pol batch.
 #endif
+#ifndef WS_SOA
+#define WS_SOA 1
+#endif
 #ifndef WS_DMMA
 #define WS_DMMA 1         // measurement Hessian of the pseudorange shapes on the FP64 tensor cores (mma.sync m8n8k4).
                           // Measured on B200: DMMA peak 36.7 TFLOP/s = the vector FMA peak (36.1) -- same pipe -- so the
@@ -188,6 +191,14 @@ struct WsCfg {
     // 5..17, predicted by J(z0)), -5 % on the GNSS batch (cold start: J(z0) is the squared start offset and says nothing
     // about the 7..9 iterations) -- so only for the linear-measurement classes
     static constexpr bool LPT = (MEAS_ == 0);
+    // pseudorange records as structure-of-arrays [field][slot][epoch] per window (ws_soa_kernel makes the copy once per
+    // call): the evaluation has one lane per epoch, so a warp's loads of one field of one slot are then consecutive
+    // 8-byte words (2 x 128 B per request) instead of 32 words 480 B apart (the caller's record layout [y, w, sat xyz]
+    // per residual, which every evaluation -- about ten per window -- re-read at 32 sectors per request)
+    // Measured (B200, round 2, alternating runs): GNSS batch 3.10 -> 3.12 M windows/s (+0.6 %, copy included) -- the records
+    // were already served from L1 / L2 after the first touch; vehicle chains (21 epochs: 21 of 32 lanes, and a 495 MB
+    // copy per step) 539 k -> 529 k (-2 %).  So: on for classes with at least a warp of epochs, off otherwise.
+    static constexpr bool SOA = (MEAS_ == 1) && (E_ >= 32) && (WS_SOA != 0);
     static constexpr int K = K_, N = N_, M = M_, E = E_;
     static constexpr int NM = NM_;          // records per epoch: measured components (MEAS 0) or satellite slots (MEAS 1)
     static constexpr int DYN = DYN_;
@@ -559,12 +570,21 @@ __device__ __forceinline__ void ws_eval(const DevProb& P, double* sm, const WsCo
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
                     const bool in = s0 + q < NM;
-                    const double* rec = dg + (in ? 5 * (e * NM + s0 + q) : 0);   // uniform layout: [y, w, sat xyz] (host-checked)
-                    ry[q] = rec[0];
-                    rw[q] = in ? rec[1] : 0.0;
-                    rx[q] = rec[2];
-                    rY[q] = rec[3];
-                    rz[q] = rec[4];
+                    if (C::SOA) {                                                // [field][slot][epoch]
+                        const double* rec = dg + (in ? (s0 + q) * E + e : e);
+                        ry[q] = rec[0];
+                        rw[q] = in ? rec[NM * E] : 0.0;
+                        rx[q] = rec[2 * NM * E];
+                        rY[q] = rec[3 * NM * E];
+                        rz[q] = rec[4 * NM * E];
+                    } else {
+                        const double* rec = dg + (in ? 5 * (e * NM + s0 + q) : 0);   // uniform layout: [y, w, sat xyz] (host-checked)
+                        ry[q] = rec[0];
+                        rw[q] = in ? rec[1] : 0.0;
+                        rx[q] = rec[2];
+                        rY[q] = rec[3];
+                        rz[q] = rec[4];
+                    }
                 }
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
@@ -1550,6 +1570,39 @@ wsolve_kernel(const __grid_constant__ DevProb P, int B, double* __restrict__ z_i
     }
 }
 
+// records of one window [e][s][5] -> [5][s][e]: one CTA per window, through shared memory so that both the read and the
+// write are coalesced
+__global__ void __launch_bounds__(256) ws_soa_kernel(size_t nwin, int E, int NM, int Ldata, const double* __restrict__ in,
+                                                     double* __restrict__ out) {
+    extern __shared__ double soa_sm[];
+    const int n = E * NM * 5;
+    for (size_t w = blockIdx.x; w < nwin; w += gridDim.x) {
+        const double* src = in + w * (size_t)Ldata;
+        double* dst = out + w * (size_t)Ldata;
+        for (int i = threadIdx.x; i < n; i += blockDim.x) soa_sm[i] = src[i];
+        __syncthreads();
+        for (int o = threadIdx.x; o < n; o += blockDim.x) {
+            const int e = o % E, s = (o / E) % NM, f = o / (E * NM);
+            dst[o] = soa_sm[(e * NM + s) * 5 + f];
+        }
+        __syncthreads();
+    }
+}
+
+template <class C>
+int ws_make_soa(const nlpf_problem* p, size_t nwin, const double* data, double* soa, cudaStream_t st) {
+    const int n = C::E * C::NM * 5;
+    if (n != p->d.Ldata) { nlpf_set_error("record block of %d doubles does not match the class (%d)", p->d.Ldata, n); return NLPF_E_ARG; }
+    static bool attr = false;
+    if (!attr) {
+        cudaFuncSetAttribute(ws_soa_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+        attr = true;
+    }
+    const size_t grid = nwin < (size_t)148 * 8 ? nwin : (size_t)148 * 8;
+    ws_soa_kernel<<<(unsigned)grid, 256, sizeof(double) * n, st>>>(nwin, C::E, C::NM, p->d.Ldata, data, soa);
+    return nlpf_check_cuda(cudaGetLastError(), "ws_soa_kernel launch");
+}
+
 template <class C>
 int ws_launch(nlpf_problem* p, int B, double* z, const double* U, const double* data, double* xprior,
               const nlpf_opts* o, double* cost_out, int* iters_out, int* status_out, double* hlin, int* counter,
@@ -1564,6 +1617,11 @@ int ws_launch(nlpf_problem* p, int B, double* z, const double* U, const double* 
         attr = true;
     }
     if (nlpf_check_cuda(cudaMemsetAsync(counter, 0, sizeof(int), st), "wsolve counter reset")) return NLPF_E_CUDA;
+    if (C::SOA) {                   // hlin is the caller's scratch of W * B * Ldata doubles for the structure-of-arrays copy
+        int rc = ws_make_soa<C>(p, (size_t)ch.W * B, data, hlin, st);
+        if (rc) return rc;
+        data = hlin;
+    }
     int grid = 148 * L::CTAS;
     const int need = (B + C::WARPS - 1) / C::WARPS;
     // longest-first hand-out: only when some windows have to wait for a free warp (more windows than resident
@@ -1602,6 +1660,17 @@ int ws_assemble_launch(nlpf_problem* p, int B, const double* z, const double* U,
     int grid = 148 * L::CTAS;
     const int need = (B + C::WARPS - 1) / C::WARPS;
     if (grid > need) grid = need;
+    if (C::SOA) {                   // the windows' output blocks (nz^2 > Ldata doubles each? no: use a pooled scratch)
+        double* soa = nullptr;
+        if (nlpf_check_cuda(cudaMallocAsync((void**)&soa, sizeof(double) * (size_t)B * p->d.Ldata, st), "cudaMallocAsync(record copy)")) return NLPF_E_CUDA;
+        int rc = ws_make_soa<C>(p, (size_t)B, data, soa, st);
+        if (!rc) {
+            kern<<<grid, C::WARPS * 32, smem, st>>>(p->d, B, z, U, soa, xprior, mu, H_out, g_out, cost_out);
+            rc = nlpf_check_cuda(cudaGetLastError(), "ws_assemble_kernel launch");
+        }
+        cudaFreeAsync(soa, st);
+        return rc;
+    }
     kern<<<grid, C::WARPS * 32, smem, st>>>(p->d, B, z, U, data, xprior, mu, H_out, g_out, cost_out);
     return nlpf_check_cuda(cudaGetLastError(), "ws_assemble_kernel launch");
 }
@@ -1650,6 +1719,11 @@ typedef WsCfg<6, 9, 2, 21, 11, NLPF_DYN_VEHICLE_GNSS, 1, WS_CAR_WARPS, 2, true, 
 
 // instantiated shapes.  meas: 0 linear state measurements (NM components per epoch), 1 pseudoranges
 // (NM satellite slots per epoch).  Returns the variant index or -1.
+// 1 when the class of this variant wants a W * B * Ldata scratch for the structure-of-arrays record copy
+extern "C" int nlpf_ws_wants_soa(int variant) {
+    return (variant == 2 && CfgGnss::SOA) || (variant == 3 && CfgCar::SOA) || (variant == 4 && CfgCarHuber::SOA) ? 1 : 0;
+}
+
 extern "C" int nlpf_ws_variant(int K, int N, int M, int E, int NM, int dyn, int meas, int nb, int prior, int loss) {
     const bool plain = nb == 0 && !prior && loss == NLPF_LOSS_L2;
     if (plain && meas == 0 && K == 21 && N == 2 && M == 1 && E == 50 && NM == 2 && dyn == NLPF_DYN_VDP) return 0;
