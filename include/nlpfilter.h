@@ -144,6 +144,11 @@ int nlpf_solve(nlpf_problem* p, int B, double* z_inout, const double* U, const d
 int nlpf_sample(nlpf_problem* p, int B, const double* z, int nt, const double* PhiT,
                 double* out, void* stream);
 
+/* Collocation defects W_k = (2/T) sum_j D_kj X_j - f(X_k, U_k) of B problems: W_out[B*K*n].
+ * replaces: the equality rows of fixedTimeOptimalControlNLP.addDynamics, nlp/nlp.py:150-158 (the batched
+ * method-of-multipliers driver of the optimal-control class updates its multipliers with them). */
+int nlpf_defects(nlpf_problem* p, int B, const double* z, const double* U, double* W_out, void* stream);
+
 /* EKF models (utils/gnss.py, autonomous-car.py:18-79) */
 #define NLPF_EKF_GNSS5 0      /* gnss.gnss_pos_and_bias + gnss.multi_pseudorange, n = 5 */
 #define NLPF_EKF_CAR9 1       /* discrete_vehicle_dynamics + vehicle_sensors_model, n = 9 */

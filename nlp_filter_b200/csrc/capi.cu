@@ -36,6 +36,7 @@ extern "C" int nlpf_launch_solve_gen(nlpf_problem*, int, double*, const double*,
 extern "C" int nlpf_launch_solve_pr(nlpf_problem*, int, double*, const double*, const double*, const double*,
                                     const double*, const nlpf_opts*, double*, int*, int*, double*, cudaStream_t);
 extern "C" int nlpf_launch_sample(nlpf_problem*, int, const double*, int, const double*, double*, cudaStream_t);
+extern "C" int nlpf_launch_defects(nlpf_problem*, int, const double*, const double*, double*, cudaStream_t);
 extern "C" int nlpf_ws_variant(int K, int N, int M, int E, int NM, int dyn, int meas, int nb, int prior, int loss);
 extern "C" int nlpf_ws_wants_soa(int variant);
 extern "C" int nlpf_ws_assemble(int variant, nlpf_problem* p, int B, const double* z, const double* U, const double* data,
@@ -649,6 +650,11 @@ extern "C" int nlpf_solve(nlpf_problem* p, int B, double* z, const double* U, co
     auto launch = p->use_big ? (p->use_pr ? nlpf_launch_solve_prb : nlpf_launch_solve_genb)
                              : (p->use_pr ? nlpf_launch_solve_pr : nlpf_launch_solve_gen);
     return launch(p, B, z, U, data, xprior, wshift, opts, cost_out, iters_out, status_out, hlin, (cudaStream_t)stream);
+}
+
+extern "C" int nlpf_defects(nlpf_problem* p, int B, const double* z, const double* U, double* W_out, void* stream) {
+    if (!p || B < 1 || !z || !W_out) { nlpf_set_error("bad argument"); return NLPF_E_ARG; }
+    return nlpf_launch_defects(p, B, z, U, W_out, (cudaStream_t)stream);
 }
 
 extern "C" int nlpf_sample(nlpf_problem* p, int B, const double* z, int nt, const double* PhiT, double* out, void* stream) {

@@ -1515,6 +1515,30 @@ __global__ void sample_kernel(DevProb P, int B, const double* __restrict__ z, in
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// nlpf_defects: W_k = (2/T) sum_j D_kj X_j - f(X_k, U_k) (+ shift), nlp.py:222-235 -- the collocation equalities of the
+// optimal-control class (nlp.py:150-158), whose method-of-multipliers driver needs them for B problems at once
+// ------------------------------------------------------------------------------------------
+__global__ void defects_kernel(DevProb P, int B, const double* __restrict__ z, const double* __restrict__ U,
+                               double* __restrict__ W_out) {
+    const int K = P.K, n = P.n, m = P.m, nv = P.nv;
+    const size_t total = (size_t)B * K;
+    for (size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
+        const int k = t % K;
+        const size_t b = t / K;
+        const double* zb = z + b * P.nz;
+        double x[NLPF_N_MAX], u[NLPF_M_MAX], f[NLPF_N_MAX];
+        for (int i = 0; i < n; ++i) x[i] = zb[k * nv + P.cmap[i]];
+        for (int i = 0; i < m; ++i) u[i] = (P.ucol[i] >= 0) ? zb[k * nv + P.ucol[i]] : (U ? U[(b * K + k) * m + i] : 0.0);
+        dyn_eval(P, x, u, f, false, nullptr);
+        for (int i = 0; i < n; ++i) {
+            double w = -f[i];
+            for (int j = 0; j < K; ++j) w = fma(P.Dt[k * K + j], zb[j * nv + P.cmap[i]], w);
+            W_out[(b * K + k) * n + i] = w;
+        }
+    }
+}
+
 #endif
 
 }  // namespace
@@ -1559,6 +1583,16 @@ extern "C" int nlpf_launch_sample(nlpf_problem* p, int B, const double* z, int n
     return nlpf_check_cuda(cudaGetLastError(), "sample_kernel launch");
 }
 
+#endif
+
+#if !NLPF_PR_RUNS && !NLPF_BIG
+extern "C" int nlpf_launch_defects(nlpf_problem* p, int B, const double* z, const double* U, double* W_out, cudaStream_t st) {
+    const size_t total = (size_t)B * p->d.K;
+    int blocks = (int)((total + 127) / 128);
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    defects_kernel<<<blocks, 128, 0, st>>>(p->d, B, z, U, W_out);
+    return nlpf_check_cuda(cudaGetLastError(), "defects_kernel launch");
+}
 #endif
 
 extern "C" int VN(nlpf_set_smem_attrs)(size_t bytes) {

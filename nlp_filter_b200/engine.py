@@ -142,6 +142,15 @@ class WindowProblem(object):
         if wshift is not None:
             _want("wshift", wshift, (B, d.K, d.n))
 
+    def defects(self, z, U=None):
+        """Collocation defects W (B, K, n) at z (nlp.py:222-235)."""
+        d = self.desc
+        z = _f8(z, (-1, d.nz))
+        B = z.shape[0]
+        W = torch.empty((B, d.K, d.n), dtype=torch.float64, device=z.device)
+        _capi.check(self._lib.nlpf_defects(self._h, B, _ptr(z), _ptr(_f8(U)), _ptr(W), _stream()))
+        return W
+
     def profile(self, enable=True):
         """Per-phase clock counters of the warp-per-window kernel (nlpf_problem_profile): returns what has been
         accumulated so far as a dict, then (re)starts or stops counting."""

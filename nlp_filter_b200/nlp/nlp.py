@@ -369,6 +369,61 @@ class fixedTimeOptimalControlNLP(NLP):
         self.J = info["J"]
         return z, info
 
+    def solve_batch(self, x0_batch, xf_batch=None, opts=None):
+        """Monte-Carlo over the end-point conditions (addition to the reference API; SURVEY.md section 8 row A8:
+        "batching = Monte-Carlo over x0"): B copies of this optimal-control problem that differ only in the value
+        of the FIRST condition added (addInitialCondition, nlp.py:170-174: x0_batch (B, n)) and optionally of the
+        second (addTerminalCondition, nlp.py:176-180: xf_batch (B, n)), solved together -- every whole-solve
+        launch, defect evaluation and multiplier update acts on all B problems.  Same method of multipliers as
+        solve() on one problem.  Returns (X (B, K, n), U (B, K, m), J (B,), status (B,))."""
+        import torch
+        from .. import engine
+        if not self._built:
+            self.build()
+        d = self._desc
+        K, n, m = d.K, d.n, self.m
+        prob = self._problem_handle()
+        x0_batch = np.asarray(x0_batch, dtype=float).reshape(-1, n)
+        B = x0_batch.shape[0]
+        vals = np.tile(np.array(self._cond_vals, dtype=float), (B, 1))
+        vals[:, :n] = x0_batch
+        if xf_batch is not None:
+            vals[:, n:2 * n] = np.asarray(xf_batch, dtype=float).reshape(B, n)
+        dev = lambda a: torch.as_tensor(np.ascontiguousarray(a, dtype=np.float64)).cuda()
+        vals_d = dev(vals)
+        node = torch.as_tensor(np.array([int(np.argmax(d.Phi[d.repoch[r]])) for r in range(d.M)])).cuda()
+        comp = torch.as_tensor(d.ridx[:, 0].astype(np.int64)).cuda()
+        roff = torch.as_tensor(d.roff.astype(np.int64)).cuda()
+        z = dev(np.tile(self._initial_z(), (B, 1)))
+        lamW = torch.zeros((B, K, n), dtype=torch.float64, device="cuda")
+        lamC = torch.zeros((B, d.M), dtype=torch.float64, device="cuda")
+        data = torch.zeros((B, max(d.Ldata, 1)), dtype=torch.float64, device="cuda")
+        if opts is None:
+            opts = D.SolveOpts(max_iter=self.MAX_ITER, max_stage_iter=self.MAX_ITER, tol_step=1e-11)
+        status = torch.full((B,), 2, dtype=torch.int32, device="cuda")
+        done = torch.zeros((B,), dtype=torch.bool, device="cuda")
+        for outer in range(self.MAX_OUTER):
+            data[:, roff] = vals_d - lamC / self.RHO
+            data[:, roff + 1] = self.RHO
+            _, cost, iters, st = prob.solve(z, None, data, None, (lamW / self.RHO).contiguous(), opts)
+            W = prob.defects(z)
+            V = z.view(B, K, d.nv)
+            c = V[:, node, comp] - vals_d
+            viol = torch.maximum(W.abs().amax((1, 2)), c.abs().amax(1) if d.M else torch.zeros_like(cost))
+            failed = (st > 1) & ~done
+            status[failed] = st[failed]
+            upd = ~done & ~failed
+            lamW += self.RHO * W * upd[:, None, None]        # finished problems keep their multipliers (and their solution)
+            lamC += self.RHO * c * upd[:, None]
+            ok = upd & (viol < self.CON_TOL)
+            status[ok] = 0
+            done |= ok | failed
+            if bool(done.all().item()):
+                break
+        V = z.view(B, K, d.nv).cpu().numpy()
+        J = np.sum(d.cq[None, :, None] * d.snode[None, None, :] * V * V, axis=(1, 2))      # the reference's objective
+        return V[:, :, :n].copy(), V[:, :, n:].copy(), J, status.cpu().numpy()
+
     def _unpack(self, z):
         K, n, m = self.N + 1, self.n, self.m
         V = z.reshape(K, n + m)

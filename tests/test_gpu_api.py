@@ -300,3 +300,37 @@ def test_unregistered_models_fail_loudly():
     f = ekf.EKF(lambda *a, **k: None, lambda *a, **k: None, np.zeros(5), np.eye(5))
     with pytest.raises(NlpfError):
         f.update(np.zeros(3), None, np.eye(5), None, dyn_func_params={"dt": 1.0})
+
+
+def test_batched_ocp_monte_carlo_over_x0_equals_single_solves():
+    """Row A8: B copies of van_der_pol.py's optimal-control problem that differ in x0, solved together
+    (solve_batch: one whole-solve launch, one defect evaluation and one multiplier update per outer iteration for
+    all of them) == the reference-API solve of each one."""
+    import nlp.nlp as nlp
+    import nlp.dynamics as dynamics
+    import nlp.cost_functions as cost_functions
+
+    def make(x0):
+        problem = nlp.fixedTimeOptimalControlNLP(20, 10., 2, 1)
+        X = problem.addVariables(21, 2, [-np.inf, -0.25], [np.inf, np.inf], name='x')
+        U = problem.addVariables(21, 1, [-1.0], [1.0], name='u')
+        problem.addDynamics(dynamics.van_der_pol, X, U)
+        problem.addStageCost(cost_functions.van_der_pol, X, U)
+        problem.addInitialCondition(X[0], x0)
+        problem.build()
+        return problem
+    rng = np.random.default_rng(8)
+    x0s = np.array([0.0, 1.0])[None, :] + rng.normal(0, 0.2, (48, 2))
+    x0s[0] = [0.0, 1.0]
+    p = make([0.0, 1.0])
+    Xb, Ub, Jb, st = p.solve_batch(x0s)
+    assert np.all(st == 0), st
+    assert abs(Jb[0] - 2.8784425681) < 1e-6                       # the script's own optimum (SURVEY.md D.5)
+    assert np.max(np.abs(Xb[:, 0, :] - x0s)) < 1e-9               # the end-point condition holds
+    for b in (0, 5, 47):
+        q = make(x0s[b])
+        q.solve()
+        Xs = np.array([q.extractVariableValue('x', k) for k in range(21)])
+        Us = np.array([q.extractVariableValue('u', k) for k in range(21)])
+        assert np.max(np.abs(Xb[b] - Xs)) < 1e-7 and np.max(np.abs(Ub[b] - Us)) < 1e-7
+        assert abs(Jb[b] - q.J) < 1e-8 * max(1.0, q.J)
