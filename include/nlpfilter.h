@@ -35,7 +35,10 @@ extern "C" {
 #define NLPF_DYN_BICYCLE 2       /* dynamics.py:117-136 */
 #define NLPF_DYN_VEHICLE 3       /* dynamics.py:148-164 */
 #define NLPF_DYN_VEHICLE_GNSS 4  /* dynamics.py:166-174 */
-#define NLPF_DYN_QUADCOPTER 5    /* dynamics.py:40-59 */
+#define NLPF_DYN_QUADCOPTER 5     /* dynamics.py:40-59 */
+#define NLPF_DYN_USER 6           /* any callable the reference would hand to casadi.Function (nlp/nlp.py:211-218):
+                                     f and df/d(x,u) are generated as CUDA source and compiled with NVRTC into a copy of
+                                     the window kernels (nlpf_problem_set_user_dynamics) */
 
 /* residual (measurement) types, nlp/measurements.py; per-window record = [y, weight, aux..] */
 #define NLPF_RT_STATE 0       /* full_state component             measurements.py:4       rec 2 */
@@ -105,6 +108,7 @@ typedef struct nlpf_opts {
 
 typedef struct nlpf_problem nlpf_problem;   /* opaque */
 
+#ifndef __CUDACC_RTC__   /* (the window kernels are also compiled at run time with a generated model function: types only there) */
 int nlpf_version(void);
 const char* nlpf_last_error(void);
 int nlpf_device_count(void);
@@ -230,6 +234,18 @@ int nlpf_ms_blocks(int B, int S, int n, int bs, const double* H_seg, const doubl
                    const double* pinv, const double* xprior, const double* z, const double* lam, double* Dg, double* Lo,
                    double* g, double* J, void* stream);
 
+/* Dynamics models outside the kernel library.
+ * replaces: casadi.Function('f', [x, u], [func(x, u, params)]) + CasADi's automatic differentiation, nlp/nlp.py:211-218.
+ * A problem class created with dyn_id = NLPF_DYN_USER (dyn_par[] = the model's numeric constants) gets its model here:
+ * model_src is CUDA source of ONE device function named `nlpf_user_dyn`, returning void, with the parameters
+ *     [const double* par, const double* x, const double* u, double* f, bool jac, const FAcc& F, const int* ucol,
+ *      double* Fk, int nv]
+ * (f = model value; when jac: F.add(i, j, df_i/dx_j), and Fk[i*nv + ucol[j]] += df_i/du_j where ucol[j] >= 0), as
+ * nlp_filter_b200/nlp/_codegen.py generates it from a Python callable.  The window kernels are compiled with it at run
+ * time (NVRTC, sm_100a; csrc_dir / include_dir = where nls_kernels.inl, common.cuh and this header live) and nlpf_solve /
+ * nlpf_assemble use the result.  NLPF_E_ARG with the compiler log in nlpf_last_error() when the source does not compile. */
+int nlpf_problem_set_user_dynamics(nlpf_problem* p, const char* model_src, const char* csrc_dir, const char* include_dir);
+
 /* Measurement support (no reference counterpart; bench.py's roofline.eval_frac / ldl_frac): per-phase clock
  * counters of the warp-per-window kernel.  enable != 0 allocates and zeroes five device counters that every
  * following nlpf_solve / nlpf_solve_chain on this handle adds to; out5 (host, may be NULL) receives what has been
@@ -246,6 +262,7 @@ int nlpf_problem_smem_bytes(const nlpf_problem* p);
 int nlpf_fp64_probe(int iters, double* sink_dev, double* flops_out, void* stream);
 /* same for the FP64 tensor-core path (mma.sync.m8n8k4.f64) */
 int nlpf_dmma_probe(int iters, double* sink_dev, double* flops_out, void* stream);
+#endif /* !__CUDACC_RTC__ */
 
 #ifdef __cplusplus
 }

@@ -31,3 +31,11 @@ def install_reference_names(force=False):
             mod = importlib.import_module("nlp_filter_b200.%s.%s" % (top, n))
             sys.modules["%s.%s" % (top, n)] = mod
             setattr(pkg, n, mod)
+    # user-defined model functions written against the reference do `from casadi import vertcat, sin, ...`
+    # (nlp/dynamics.py:2): when CasADi itself is not installed, publish the stand-in names (NumPy on numbers, traced
+    # expressions under the code generator)
+    if "casadi" not in sys.modules:
+        try:
+            importlib.import_module("casadi")
+        except Exception:
+            sys.modules["casadi"] = importlib.import_module("nlp_filter_b200.nlp._sym")

@@ -42,7 +42,7 @@ EXPORTS = ("nlpf_version", "nlpf_last_error", "nlpf_device_count", "nlpf_problem
            "nlpf_problem_destroy", "nlpf_problem_nz", "nlpf_assemble", "nlpf_factor_solve", "nlpf_solve",
            "nlpf_sample", "nlpf_ekf_run", "nlpf_ls_solve", "nlpf_ls_vel", "nlpf_fp64_probe", "nlpf_dmma_probe", "nlpf_blocktri_solve",
            "nlpf_problem_smem_bytes", "nlpf_ecef2enu", "nlpf_enu2lla", "nlpf_solve_chain",
-           "nlpf_problem_has_chain_kernel", "nlpf_problem_profile", "nlpf_ms_gather", "nlpf_ms_blocks", "nlpf_ekf_run_general", "nlpf_defects")
+           "nlpf_problem_has_chain_kernel", "nlpf_problem_profile", "nlpf_ms_gather", "nlpf_ms_blocks", "nlpf_ekf_run_general", "nlpf_defects", "nlpf_problem_set_user_dynamics")
 
 _lib = None
 
@@ -67,6 +67,7 @@ def lib():
     L.nlpf_assemble.argtypes = [vp, ctypes.c_int, vp, vp, vp, vp, vp, ctypes.c_double, vp, vp, vp, vp]
     L.nlpf_factor_solve.argtypes = [vp, ctypes.c_int, vp, vp, ctypes.c_double, vp, vp, vp]
     L.nlpf_solve.argtypes = [vp, ctypes.c_int, vp, vp, vp, vp, vp, ctypes.POINTER(COpts), vp, vp, vp, vp]
+    L.nlpf_problem_set_user_dynamics.argtypes = [vp, ctypes.c_char_p, ctypes.c_char_p, ctypes.c_char_p]
     L.nlpf_defects.argtypes = [vp, ctypes.c_int, vp, vp, vp, vp]
     L.nlpf_sample.argtypes = [vp, ctypes.c_int, vp, ctypes.c_int, vp, vp, vp]
     L.nlpf_ekf_run.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, vp, vp, vp, vp, vp, vp, vp,

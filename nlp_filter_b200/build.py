@@ -7,7 +7,7 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 INCLUDE = os.path.join(os.path.dirname(HERE), "include")
-SOURCES = ("capi.cu", "nls_kernels_gen.cu", "nls_kernels_pr.cu", "nls_kernels_gen_big.cu", "nls_kernels_pr_big.cu", "ekf_ls_kernels.cu", "blocktri_kernels.cu", "wsolve_kernels.cu")
+SOURCES = ("capi.cu", "nls_kernels_gen.cu", "nls_kernels_pr.cu", "nls_kernels_gen_big.cu", "nls_kernels_pr_big.cu", "ekf_ls_kernels.cu", "blocktri_kernels.cu", "wsolve_kernels.cu", "user_model.cu")
 LIB = os.path.join(HERE, "libnlpfilter.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
@@ -45,7 +45,7 @@ def build(force=False, verbose=False):
         for l in logs:
             sys.stderr.write(l)
     if force or jobs or _stale(LIB, objs):
-        run([NVCC, "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a"])
+        run([NVCC, "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-ldl"])
     return LIB
 
 

@@ -37,6 +37,11 @@ extern "C" int nlpf_launch_solve_pr(nlpf_problem*, int, double*, const double*, 
                                     const double*, const nlpf_opts*, double*, int*, int*, double*, cudaStream_t);
 extern "C" int nlpf_launch_sample(nlpf_problem*, int, const double*, int, const double*, double*, cudaStream_t);
 extern "C" int nlpf_launch_defects(nlpf_problem*, int, const double*, const double*, double*, cudaStream_t);
+extern "C" void nlpf_user_release(nlpf_problem* p);
+extern "C" int nlpf_user_launch_solve(nlpf_problem*, int, double*, const double*, const double*, const double*, const double*,
+                                      const nlpf_opts*, double*, int*, int*, double*, cudaStream_t);
+extern "C" int nlpf_user_launch_assemble(nlpf_problem*, int, const double*, const double*, const double*, const double*,
+                                         const double*, double, double*, double*, double*, cudaStream_t);
 extern "C" int nlpf_ws_variant(int K, int N, int M, int E, int NM, int dyn, int meas, int nb, int prior, int loss);
 extern "C" int nlpf_ws_wants_soa(int variant);
 extern "C" int nlpf_ws_assemble(int variant, nlpf_problem* p, int B, const double* z, const double* U, const double* data,
@@ -131,10 +136,10 @@ extern "C" int nlpf_problem_create(const nlpf_desc* D, nlpf_problem** out) {
                        K, n, m, nv, ng, nz, NLPF_K_MAX, NLPF_N_MAX, NLPF_M_MAX, NLPF_NV_MAX, NLPF_NG_MAX, NLPF_NZ_MAX);
         return NLPF_E_ARG;
     }
-    if (D->dyn_id < 0 || D->dyn_id > NLPF_DYN_QUADCOPTER) { nlpf_set_error("unknown dynamics id %d", D->dyn_id); return NLPF_E_ARG; }
-    static const int dyn_n[] = {0, 2, 6, 6, 9, 12};
-    static const int dyn_m[] = {0, 1, 2, 2, 2, 4};
-    if (D->dyn_id != NLPF_DYN_AFFINE && (n != dyn_n[D->dyn_id] || m != dyn_m[D->dyn_id])) {
+    if (D->dyn_id < 0 || D->dyn_id > NLPF_DYN_USER) { nlpf_set_error("unknown dynamics id %d", D->dyn_id); return NLPF_E_ARG; }
+    static const int dyn_n[] = {0, 2, 6, 6, 9, 12, 0};
+    static const int dyn_m[] = {0, 1, 2, 2, 2, 4, 0};
+    if (D->dyn_id != NLPF_DYN_AFFINE && D->dyn_id != NLPF_DYN_USER && (n != dyn_n[D->dyn_id] || m != dyn_m[D->dyn_id])) {
         nlpf_set_error("dynamics id %d needs n=%d m=%d, got n=%d m=%d", D->dyn_id, dyn_n[D->dyn_id], dyn_m[D->dyn_id], n, m);
         return NLPF_E_ARG;
     }
@@ -529,6 +534,7 @@ extern "C" int nlpf_problem_destroy(nlpf_problem* p) {
     if (p->counter) cudaFree(p->counter);
     if (p->order) cudaFree(p->order);
     if (p->prof) cudaFree(p->prof);
+    nlpf_user_release(p);
     if (p->keys) cudaFree(p->keys);
     delete p;
     return NLPF_OK;
@@ -551,6 +557,8 @@ extern "C" int nlpf_assemble(nlpf_problem* p, int B, const double* z, const doub
     int rc = check_batch(p, B, z, data);
     if (rc) return rc;
     if (!H_out || !g_out || !cost_out) { nlpf_set_error("null output buffer"); return NLPF_E_ARG; }
+    if (p->d.dyn_id == NLPF_DYN_USER)
+        return nlpf_user_launch_assemble(p, B, z, U, data, xprior, wshift, mu, H_out, g_out, cost_out, (cudaStream_t)stream);
     if (p->ws_variant >= 0 && !wshift && (p->d.m == 0 || U) && (!p->d.has_prior || xprior))      // warp-per-window classes
         return nlpf_ws_assemble(p->ws_variant, p, B, z, U, data, xprior, mu, H_out, g_out, cost_out, (cudaStream_t)stream);
     auto launch = p->use_big ? (p->use_pr ? nlpf_launch_assemble_prb : nlpf_launch_assemble_genb)
@@ -647,6 +655,8 @@ extern "C" int nlpf_solve(nlpf_problem* p, int B, double* z, const double* U, co
         }
         hlin = p->scratch;
     }
+    if (p->d.dyn_id == NLPF_DYN_USER)
+        return nlpf_user_launch_solve(p, B, z, U, data, xprior, wshift, opts, cost_out, iters_out, status_out, hlin, (cudaStream_t)stream);
     auto launch = p->use_big ? (p->use_pr ? nlpf_launch_solve_prb : nlpf_launch_solve_genb)
                              : (p->use_pr ? nlpf_launch_solve_pr : nlpf_launch_solve_gen);
     return launch(p, B, z, U, data, xprior, wshift, opts, cost_out, iters_out, status_out, hlin, (cudaStream_t)stream);

@@ -1,7 +1,18 @@
 // common.cuh -- shared declarations of libnlpfilter.so (sm_100a, fp64 throughout).
 #pragma once
+#ifdef __CUDACC_RTC__
+// run-time compilation of the window kernels with a generated model function (user_model.cu): no host headers
+typedef unsigned char uint8_t;
+typedef unsigned short uint16_t;
+typedef unsigned int uint32_t;
+typedef unsigned long long size_t_rtc_unused;
+#ifndef INFINITY
+#define INFINITY __longlong_as_double(0x7ff0000000000000LL)
+#endif
+#else
 #include <cuda_runtime.h>
 #include <stdint.h>
+#endif
 #include "nlpfilter.h"
 
 #define NLPF_NT 128            // threads per window CTA (4 warps: one per SM sub-partition)
@@ -78,6 +89,7 @@ struct DevProb {
     int o_Ve, o_G, o_q, o_Phi, o_Dt, o_red, smem_doubles;
 };
 
+#ifndef __CUDACC_RTC__
 struct nlpf_problem {
     DevProb d;
     void* blob;          // one device allocation holding every table
@@ -92,9 +104,11 @@ struct nlpf_problem {
     int* order;          // longest-first hand-out of the warp-per-window kernel: window indices by descending start cost
     double* keys;        // ... and the start costs
     size_t order_cap;
+    void *user_module, *user_solve, *user_assemble;   // NVRTC-compiled window kernels of a user-defined model (user_model.cu)
     unsigned long long* prof;   // nlpf_problem_profile: [eval cycles, LDL cycles, evaluations, factorisations, window cycles] or null
     int device;
 };
 
 void nlpf_set_error(const char* fmt, ...);
 int nlpf_check_cuda(cudaError_t e, const char* what);
+#endif  // !__CUDACC_RTC__

@@ -14,7 +14,9 @@
 // (lower triangle, row-major) in shared memory with the right-hand side appended as one more
 // row, so the forward substitution happens inside the factorisation.
 #include "common.cuh"
+#ifndef __CUDACC_RTC__
 #include <math.h>
+#endif
 
 // This file is compiled four times (nls_kernels_{gen,pr}.cu and their _big twins): NLPF_PR_RUNS = 1 adds the
 // lane-group / register-accumulation path for pseudorange runs.  Keeping it out of the other
@@ -140,6 +142,14 @@ struct FAcc {
         Fk[row * nv + cmap[statecomp]] += v;
     }
 };
+
+#ifdef NLPF_USER_DYN
+// generated at run time from a user's Python callable (nlp_filter_b200/nlp/_codegen.py) and compiled with NVRTC
+// together with this file (csrc/user_model.cu):
+//   __device__ void nlpf_user_dyn(const double* par, const double* x, const double* u, double* f, bool jac,
+//                                 const FAcc& F, const int* ucol, double* Fk, int nv);
+#include "nlpf_user_dyn.inc"
+#endif
 
 __device__ void vehicle6(const double* par, const double* x, const double* u, double* f, bool jac,
                          const FAcc& F) {
@@ -296,6 +306,11 @@ __device__ void dyn_eval(const DevProb& P, const double* x, const double* u, dou
         case NLPF_DYN_QUADCOPTER:
             quadcopter12(P.dyn_par, x, u, f, jac, F);
             return;
+#ifdef NLPF_USER_DYN
+        case NLPF_DYN_USER:
+            nlpf_user_dyn(P.dyn_par, x, u, f, jac, F, P.ucol, Fk, nv);
+            return;
+#endif
     }
 }
 
@@ -1544,6 +1559,7 @@ __global__ void defects_kernel(DevProb P, int B, const double* __restrict__ z, c
 }  // namespace
 using namespace VN(nlpf_ns);
 
+#ifndef __CUDACC_RTC__
 // ------------------------------------------------------------------------------------------
 // launchers (called from capi.cu)
 // ------------------------------------------------------------------------------------------
@@ -1609,3 +1625,4 @@ extern "C" int VN(nlpf_set_smem_attrs)(size_t bytes) {
     if (e != cudaSuccess) return nlpf_check_cuda(e, "smem carveout solve");
     return 0;
 }
+#endif  // !__CUDACC_RTC__

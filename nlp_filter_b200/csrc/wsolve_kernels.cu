@@ -31,6 +31,14 @@
 #ifndef WS_SOA
 #define WS_SOA 1
 #endif
+#ifndef WS_UNROLL_ROUNDS
+#define WS_UNROLL_ROUNDS 1
+#endif
+#if WS_UNROLL_ROUNDS
+#define WS_ROUND_PRAGMA _Pragma("unroll")
+#else
+#define WS_ROUND_PRAGMA _Pragma("unroll 1")
+#endif
 #ifndef WS_DMMA
 #define WS_DMMA 1         // measurement Hessian of the pseudorange shapes on the FP64 tensor cores (mma.sync m8n8k4).
                           // Measured on B200: DMMA peak 36.7 TFLOP/s = the vector FMA peak (36.1) -- same pipe -- so the
@@ -351,7 +359,10 @@ __device__ __forceinline__ void ws_eval(const DevProb& P, double* sm, const WsCo
     }
     __syncwarp();
     // defects W_ki = sum_j Dt_kj x_ji - f_ki, weights
-    for (int t = lane; t < NZ; t += 32) {
+    WS_ROUND_PRAGMA
+    for (int t_r = 0; t_r < (NZ + 31) / 32; ++t_r) {      // rounds unrolled: their dependent chains interleave (WS_UNROLL_ROUNDS)
+        const int t = lane + 32 * t_r;
+        if (t >= NZ) continue;
         const int k = t / N, i = t - k * N;
         const double fki = fb[t];
         // (sums over nodes / epochs below are split over 2-4 accumulators: with 4 warps per scheduler the
@@ -380,7 +391,10 @@ __device__ __forceinline__ void ws_eval(const DevProb& P, double* sm, const WsCo
     __syncwarp();
     if (FULL) {
         // gradient of the dynamics cost: g_(j,a) = sum_k Dt_kj lw_ka - sum_i F_j[i][a] lw_ji
-        for (int t = lane; t < NZ; t += 32) {
+        WS_ROUND_PRAGMA
+        for (int t_r = 0; t_r < (NZ + 31) / 32; ++t_r) {      // rounds unrolled: their dependent chains interleave (WS_UNROLL_ROUNDS)
+            const int t = lane + 32 * t_r;
+            if (t >= NZ) continue;
             const int j = t / N, a = t - j * N;
             double s = 0.0, s2 = 0.0;
 #pragma unroll
@@ -503,7 +517,10 @@ __device__ __forceinline__ void ws_eval(const DevProb& P, double* sm, const WsCo
     }
     if (C::MEAS == 0) {
         // linear measurements: residual t = e*NM + s measures one state component at epoch e (record [y, w])
-        for (int t = lane; t < L::NR; t += 32) {
+        WS_ROUND_PRAGMA
+        for (int t_r = 0; t_r < (L::NR + 31) / 32; ++t_r) {      // rounds unrolled: their dependent chains interleave (WS_UNROLL_ROUNDS)
+            const int t = lane + 32 * t_r;
+            if (t >= L::NR) continue;
             const int e = t / NM;
             const int sl = t - e * NM;
             const int c = (sl == 0) ? cs.c[0] : (sl == 1) ? cs.c[1] : (sl == 2) ? cs.c[2] : cs.c[3];
@@ -525,7 +542,10 @@ __device__ __forceinline__ void ws_eval(const DevProb& P, double* sm, const WsCo
         }
         if (FULL) {
             __syncwarp();
-            for (int t = lane; t < NZ; t += 32) {
+            WS_ROUND_PRAGMA
+            for (int t_r = 0; t_r < (NZ + 31) / 32; ++t_r) {      // rounds unrolled: their dependent chains interleave (WS_UNROLL_ROUNDS)
+                const int t = lane + 32 * t_r;
+                if (t >= NZ) continue;
                 const int j = t / N, a = t - j * N;
                 int s = -1;                                // slot of component a in an epoch's record set, or -1
 #pragma unroll

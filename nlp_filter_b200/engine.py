@@ -71,6 +71,13 @@ class WindowProblem(object):
         h = ctypes.c_void_p()
         _capi.check(self._lib.nlpf_problem_create(ctypes.byref(cdesc), ctypes.byref(h)))
         self._h = h
+        if desc.dyn_id == 6:                 # DYN_USER: compile the window kernels with the generated model (NVRTC)
+            if not getattr(desc, "user_src", None):
+                raise _capi.NlpfError("problem class with a user-defined model carries no generated source (desc.user_src)")
+            here = os.path.dirname(os.path.abspath(__file__))
+            _capi.check(self._lib.nlpf_problem_set_user_dynamics(h, desc.user_src.encode("utf-8"),
+                                                                 os.path.join(here, "csrc").encode("utf-8"),
+                                                                 os.path.join(os.path.dirname(here), "include").encode("utf-8")))
         self.nz = desc.nz
         self.smem_bytes = int(self._lib.nlpf_problem_smem_bytes(h))
 

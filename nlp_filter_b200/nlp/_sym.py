@@ -17,7 +17,23 @@ def _num(x):
     return x.value if isinstance(x, Parameter) else x
 
 
+def _symbolic(*args):
+    """True when an argument is (or contains) a traced expression of the code generator (_codegen.Sym)."""
+    from . import _codegen
+    for a in args:
+        if isinstance(a, (_codegen.Sym, _codegen.SymVec)):
+            return True
+        if isinstance(a, (list, tuple)) and any(isinstance(v, (_codegen.Sym, _codegen.SymVec)) for v in a):
+            return True
+        if isinstance(a, np.ndarray) and a.dtype == object:
+            return True
+    return False
+
+
 def vertcat(*args):
+    if _symbolic(*args):
+        from . import _codegen
+        return _codegen.flatten(list(args))
     parts = [np.atleast_1d(np.asarray(_num(a))).reshape(-1) for a in args]
     return np.concatenate(parts) if parts else np.zeros(0)
 
@@ -38,15 +54,32 @@ def sqrt(x):
     return np.sqrt(_num(x))
 
 
+def exp(x):
+    return np.exp(_num(x))
+
+
+def log(x):
+    return np.log(_num(x))
+
+
 def atan2(y, x):
     return np.arctan2(_num(y), _num(x))
 
 
 def dot(a, b):
+    if _symbolic(a, b):
+        from . import _codegen
+        fa, fb = _codegen.flatten(a), _codegen.flatten(b)
+        acc = 0.0
+        for u, v in zip(fa, fb):
+            acc = acc + u * v
+        return acc
     return np.dot(np.asarray(_num(a)).reshape(-1), np.asarray(_num(b)).reshape(-1))
 
 
 def norm_2(a):
+    if _symbolic(a):
+        return sqrt(dot(a, a))
     return np.linalg.norm(np.asarray(_num(a)).reshape(-1))
 
 

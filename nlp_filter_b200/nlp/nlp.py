@@ -806,13 +806,23 @@ class fixedTimeOptimalEstimationNLP(NLP):
 # =============================================================================================
 # helpers of the lowering
 # =============================================================================================
-def _call_dyn(func, x, u, m, params):
-    if m == 0:
-        return np.asarray(func(x, params), dtype=float).reshape(-1)
+def _call_dyn_raw(func, x, u, m, params):
+    """The model callable with the reference's calling convention -- func(x, u, params), func(x, params) without
+    controls (nlp/nlp.py:211-218) -- tolerating callables that take no params argument.  Returns whatever the callable
+    returns (numbers, arrays, or traced expressions under the code generator)."""
+    import inspect
     try:
-        return np.asarray(func(x, u, params), dtype=float).reshape(-1)
-    except TypeError:
-        return np.asarray(func(x, u), dtype=float).reshape(-1)
+        npar = len([q for q in inspect.signature(func).parameters.values()
+                    if q.kind in (q.POSITIONAL_ONLY, q.POSITIONAL_OR_KEYWORD)])
+    except (TypeError, ValueError):
+        npar = 3
+    if m == 0:
+        return func(x, params) if npar >= 2 else func(x)
+    return func(x, u, params) if npar >= 3 else func(x, u)
+
+
+def _call_dyn(func, x, u, m, params):
+    return np.asarray(_call_dyn_raw(func, x, u, m, params), dtype=float).reshape(-1)
 
 
 def _lower_dynamics(d, func, n, m, params):
@@ -852,8 +862,18 @@ def _lower_dynamics(d, func, n, m, params):
             if np.max(np.abs(f - (c0 + A @ x + B[:, :m] @ u[:m]))) > 1e-9 * (1 + np.max(np.abs(f))):
                 raise ValueError
     except Exception:
-        raise NotImplementedError("dynamics %r is neither a registered model (nlp/dynamics.py) nor affine in (x, u); "
-                                  "there is no CPU fallback for arbitrary callables" % (func,))
+        # neither registered nor affine: generate the CUDA model (value + symbolic Jacobian) from the callable itself;
+        # csrc/user_model.cu compiles it into the window kernels with NVRTC when the problem is created on the device
+        from . import _codegen
+        try:
+            src, info = _codegen.generate(func, n, m, params, _call_dyn_raw)
+        except Exception as e:
+            raise NotImplementedError("dynamics %r is neither a registered model (nlp/dynamics.py), nor affine in (x, u), nor "
+                                      "traceable for code generation (%s); there is no CPU fallback" % (func, e))
+        d.dyn_id = D.DYN_USER
+        d.user_src = src
+        d.user_func = (func, params, m)
+        return
     d.dyn_id = D.DYN_AFFINE
     d.A, d.Bm, d.c0 = A, B, c0
 

@@ -119,6 +119,34 @@ def dynamics(desc, x, u):
     did = desc.dyn_id
     dt = np.result_type(x.dtype, u.dtype if m > 0 else x.dtype)
     Fu = np.zeros((n, max(m, 1)), dtype=dt)
+    if did == getattr(D, "DYN_USER", 6):
+        # a user's own callable (not in nlp/dynamics.py): the ORACLE evaluates the callable itself and differentiates
+        # it numerically (central differences, step 1e-6 (1 + |v|): Jacobian good to ~1e-9) -- independent of the
+        # symbolic differentiation and generated CUDA source the product path uses
+        func, params, mm = desc.user_func
+
+        def call(xx, uu):
+            try:
+                out = func(xx, uu, params) if mm > 0 else func(xx, params)
+            except TypeError:
+                out = func(xx, uu) if mm > 0 else func(xx)
+            return np.asarray(out, dtype=float).reshape(-1)
+        xr, ur = np.asarray(x, dtype=float), np.asarray(u, dtype=float)[:max(m, 1)]
+        f = call(xr, ur[:m])
+        F = np.zeros((n, n))
+        for j in range(n):
+            h = 1e-6 * (1.0 + abs(xr[j]))
+            xp, xm = xr.copy(), xr.copy()
+            xp[j] += h
+            xm[j] -= h
+            F[:, j] = (call(xp, ur[:m]) - call(xm, ur[:m])) / (2 * h)
+        for j in range(m):
+            h = 1e-6 * (1.0 + abs(ur[j]))
+            up, um = ur.copy(), ur.copy()
+            up[j] += h
+            um[j] -= h
+            Fu[:, j] = (call(xr, up[:m]) - call(xr, um[:m])) / (2 * h)
+        return f, F, Fu
     if did == D.DYN_AFFINE:
         f = desc.A @ x + desc.c0
         if m > 0:

@@ -116,12 +116,18 @@ def test_ocp_lowering_and_affine_probe():
     q.build()
     assert q._desc.dyn_id == D.DYN_AFFINE and np.array_equal(q._desc.A, [[0, 1], [-3, 0]])
     assert np.array_equal(q._desc.Bm[:, 0], [2, 0]) and np.array_equal(q._desc.c0, [0, 0.5])
-    # ... a non-affine unregistered one is refused (no CPU fallback for arbitrary callables)
+    # ... a non-affine unregistered one is lowered by code generation (CUDA source for NVRTC; round 2) ...
     r = nlp.fixedTimeOptimalEstimationNLP(5, 1.0, 2, 1)
     Xr = r.addVariables(6, 2, name='x')
     r.addDynamics(lambda x, u, params=None: np.array([np.sin(x[0]), u[0]]), Xr, None, None)
+    r.build()
+    assert r._desc.dyn_id == D.DYN_USER and "sin(x[0])" in r._desc.user_src and "cos(x[0])" in r._desc.user_src
+    # ... and one that cannot be traced (data-dependent branch) is refused: no CPU fallback for arbitrary callables
+    r2 = nlp.fixedTimeOptimalEstimationNLP(5, 1.0, 2, 1)
+    Xr2 = r2.addVariables(6, 2, name='x')
+    r2.addDynamics(lambda x, u, params=None: np.array([x[1] if x[0] > 0 else -x[1], u[0] * x[0]]), Xr2, None, None)
     with pytest.raises(NotImplementedError):
-        r.build()
+        r2.build()
 
 
 def test_model_callables_are_dual_use_numeric():
