@@ -15,6 +15,8 @@
 #include <nvrtc.h>
 #include <stdio.h>
 #include <string.h>
+#include <map>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -60,6 +62,11 @@ Rtc& rtc() {
     r.ok = all;
     return r;
 }
+// compiled models of this process: (kernel variant + generated source) -> module.  A batch in chunks creates one
+// problem handle per chunk (engine.HostBatch): they share one compilation.  Modules stay loaded for the process.
+struct UserMod { CUmodule mod; CUfunction fs, fa; };
+std::map<std::string, UserMod>& mod_cache() { static std::map<std::string, UserMod> c; return c; }
+std::mutex& mod_mutex() { static std::mutex m; return m; }
 }  // namespace
 
 extern "C" int nlpf_problem_set_user_dynamics(nlpf_problem* p, const char* model_src, const char* csrc_dir, const char* include_dir) {
@@ -71,6 +78,17 @@ extern "C" int nlpf_problem_set_user_dynamics(nlpf_problem* p, const char* model
     char head[256];
     snprintf(head, sizeof(head), "#define NLPF_USER_DYN 1\n#define NLPF_PR_RUNS %d\n#define NLPF_BIG %d\n#include \"nls_kernels.inl\"\n",
              p->use_pr ? 1 : 0, p->use_big ? 1 : 0);
+    const std::string key = std::string(head) + model_src;
+    {
+        std::lock_guard<std::mutex> lk(mod_mutex());
+        auto it = mod_cache().find(key);
+        if (it != mod_cache().end()) {
+            p->user_module = nullptr;              // owned by the cache
+            p->user_solve = it->second.fs;
+            p->user_assemble = it->second.fa;
+            return NLPF_OK;
+        }
+    }
     const char* suffix = p->use_big ? (p->use_pr ? "prb" : "genb") : (p->use_pr ? "pr" : "gen");
     const std::string n_solve = std::string("nlpf_ns_") + suffix + "::solve_kernel_" + suffix;
     const std::string n_asm = std::string("nlpf_ns_") + suffix + "::assemble_kernel_" + suffix;
@@ -115,8 +133,11 @@ extern "C" int nlpf_problem_set_user_dynamics(nlpf_problem* p, const char* model
         if (mod) R.ModuleUnload(mod);
         return NLPF_E_CUDA;
     }
-    if (p->user_module) R.ModuleUnload((CUmodule)p->user_module);
-    p->user_module = mod;
+    {
+        std::lock_guard<std::mutex> lk(mod_mutex());
+        mod_cache()[key] = UserMod{mod, fs, fa};
+    }
+    p->user_module = nullptr;                      // owned by the cache
     p->user_solve = fs;
     p->user_assemble = fa;
     return NLPF_OK;
