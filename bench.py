@@ -549,47 +549,17 @@ def run_ours(args):
     flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device="cuda")     # 256 MB > 126 MB L2
     peak_fp64 = engine.fp64_peak_tflops()
 
-    # Multi-GPU: the gather of step s (NCCL's own stream) overlaps the solve of step s+1 -- two estimate / gather
-    # buffers alternate, a buffer is reused only after its gather has completed, and the timed region ends only
+    # Multi-GPU: the gather of step s (NCCL's own stream) overlaps the solve of step s+1 -- sharding.GatherPipe: two
+    # gather buffers alternate, a buffer is reused only after its gather has completed, and the timed region ends only
     # after the last gather has (pipe.finish()).  The end-to-end leg also brings every gathered batch to the host.
-    class GatherPipe(object):
-        def __init__(self, to_host):
-            self.k = 0
-            self.pending = [None, None]
-            self.zb = [z, torch.empty_like(z0)] if world > 1 else [z]
-            self.gb = [torch.empty((world * B, desc.nz), dtype=torch.float64, device="cuda") for _ in range(2)] if world > 1 else [None]
-            self.hb = [torch.empty((world * B, desc.nz), dtype=torch.float64).pin_memory() for _ in range(2)] if (world > 1 and to_host) else None
-            self.copy_stream = torch.cuda.Stream() if self.hb is not None else None
-
-        def _complete(self, i):
-            if self.pending[i] is None:
-                return
-            self.pending[i].wait()                 # the current stream waits for the collective
-            if self.hb is not None:                # gathered estimates -> pinned host memory
-                self.hb[i].copy_(self.gb[i], non_blocking=True)
-            self.pending[i] = None
-
-        def slot(self):
-            i = self.k & 1 if world > 1 else 0
-            self.k += 1
-            if world > 1:
-                self._complete(i)
-            return i
-
-        def gather(self, i, src):
-            if world > 1:
-                self.pending[i] = dist.all_gather_into_tensor(self.gb[i], src, async_op=True)
-
-        def finish(self):
-            for i in range(2 if world > 1 else 0):
-                self._complete(i)
-
-    pipes = {"dev": GatherPipe(False), "e2e": GatherPipe(True)}
+    from nlp_filter_b200 import sharding
+    pipes = {"dev": sharding.GatherPipe(B, (desc.nz,)), "e2e": sharding.GatherPipe(B, (desc.nz,), to_host=True)}
+    zbuf = [z, torch.empty_like(z0)] if world > 1 else [z]
 
     def step_device():
         pipe = pipes["dev"]
         i = pipe.slot()
-        zi = pipe.zb[i]
+        zi = zbuf[i]
         zi.copy_(z0)
         prob.solve(zi, U, data, xprior, None, None, out=(cost, iters, status))
         pipe.gather(i, zi)

@@ -35,6 +35,17 @@ def _worker(rank, world, port, B, out_path):
     full = sharding.gather_estimates(torch.as_tensor(local), B)
     if rank == 0:
         np.save(out_path, full.numpy())
+    if B % world == 0:
+        # the pipelined form bench.py uses: three "steps" whose gathers overlap the next step; every gathered batch
+        # (device buffer and host copy) must equal the plain gather of that step's estimates
+        pipe = sharding.GatherPipe(hi - lo, (d.nz,), device="cpu", to_host=True)
+        for step in range(3):
+            i = pipe.slot()
+            pipe.gather(i, torch.as_tensor(local) + float(step))
+        pipe.finish()
+        for step, i in ((1, 1), (2, 0)):               # slots alternate 0, 1, 0: slot 0 now holds step 2, slot 1 step 1
+            dev_buf, host_buf = pipe.last(i)
+            assert torch.equal(dev_buf, full + float(step)) and torch.equal(host_buf, full + float(step))
     dist.barrier()
     dist.destroy_process_group()
 
