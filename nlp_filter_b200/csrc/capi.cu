@@ -127,6 +127,19 @@ extern "C" int nlpf_problem_create(const nlpf_desc* D, nlpf_problem** out) {
         nlpf_set_error("no CUDA device visible: libnlpfilter has no CPU fallback");
         return NLPF_E_NOGPU;
     }
+    {   // per-call workspaces come from the stream-ordered pool (cudaMallocAsync): keep them cached between calls -- with the
+        // default release threshold every synchronisation returns them to the driver and the next call maps them again
+        static bool pool_done = false;
+        if (!pool_done) {
+            int devid = 0;
+            cudaMemPool_t pool;
+            if (cudaGetDevice(&devid) == cudaSuccess && cudaDeviceGetDefaultMemPool(&pool, devid) == cudaSuccess) {
+                unsigned long long keep = ~0ULL;
+                cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+            }
+            pool_done = true;
+        }
+    }
     const int K = D->K, n = D->n, m = D->m, nv = D->nv, ng = D->ng;
     const int mm = m > 0 ? m : 1;
     const int nz = K * nv + ng;

@@ -31,11 +31,14 @@
 #ifndef WS_SOA
 #define WS_SOA 1
 #endif
+#ifndef WS_BACKSUB_REG_MAXNZ
+#define WS_BACKSUB_REG_MAXNZ 48   // vehicle class (nz = 54): rolled sweep, +2 % (instruction fetch)
+#endif
 #ifndef WS_UNROLL_ROUNDS
 #define WS_UNROLL_ROUNDS 1
 #endif
 #if WS_UNROLL_ROUNDS
-#define WS_ROUND_PRAGMA _Pragma("unroll")
+#define WS_ROUND_PRAGMA _Pragma("unroll (C::RU)")
 #else
 #define WS_ROUND_PRAGMA _Pragma("unroll 1")
 #endif
@@ -191,7 +194,7 @@ static_assert(fpat_check_vehicle(), "F^T Lambda F pair list does not match the J
 
 // compile-time description of one problem class
 template <int K_, int N_, int M_, int E_, int NM_, int DYN_, int MEAS_, int WARPS_, int NB_ = 0, bool PRIOR_ = false,
-          int LOSS_ = NLPF_LOSS_L2, bool MMA_ = false, int MAXW_ = 16>
+          int LOSS_ = NLPF_LOSS_L2, bool MMA_ = false, int MAXW_ = 16, bool AOS_ = false>
 struct WsCfg {
     static constexpr bool MMA = MMA_;       // LDL^T with the matrix in registers as FP64 tensor-core tiles (ws_ldl_mma)
     static constexpr int MAXW = MAXW_;      // warps per SM the register budget allows (16: 128 registers, 12: 168)
@@ -199,6 +202,9 @@ struct WsCfg {
     // 5..17, predicted by J(z0)), -5 % on the GNSS batch (cold start: J(z0) is the squared start offset and says nothing
     // about the 7..9 iterations) -- so only for the linear-measurement classes
     static constexpr bool LPT = (MEAS_ == 0);
+    // rounds of 32 lanes of the evaluation loops unrolled (their dependent chains interleave): GNSS +1.8 %, van der Pol
+    // neutral; not for the vehicle class, whose kernel is bound by instruction fetch (160 KB of SASS)
+    static constexpr int RU = (DYN_ == NLPF_DYN_VEHICLE_GNSS) ? 1 : 4;
     // pseudorange records as structure-of-arrays [field][slot][epoch] per window (ws_soa_kernel makes the copy once per
     // call): the evaluation has one lane per epoch, so a warp's loads of one field of one slot are then consecutive
     // 8-byte words (2 x 128 B per request) instead of 32 words 480 B apart (the caller's record layout [y, w, sat xyz]
@@ -206,7 +212,7 @@ struct WsCfg {
     // Measured (B200, round 2, alternating runs): GNSS batch 3.10 -> 3.12 M windows/s (+0.6 %, copy included) -- the records
     // were already served from L1 / L2 after the first touch; vehicle chains (21 epochs: 21 of 32 lanes, and a 495 MB
     // copy per step) 539 k -> 529 k (-2 %).  So: on for classes with at least a warp of epochs, off otherwise.
-    static constexpr bool SOA = (MEAS_ == 1) && (E_ >= 32) && (WS_SOA != 0);
+    static constexpr bool SOA = (MEAS_ == 1) && (E_ >= 32) && (WS_SOA != 0) && !AOS_;      // AOS_: single-evaluation kernels (assemble)
     static constexpr int K = K_, N = N_, M = M_, E = E_;
     static constexpr int NM = NM_;          // records per epoch: measured components (MEAS 0) or satellite slots (MEAS 1)
     static constexpr int DYN = DYN_;
@@ -1333,7 +1339,10 @@ __device__ __forceinline__ bool ws_ldl_mma(double* Hp, double* xs, double* PB) {
     }
     __syncwarp();
     if (!ok) return false;
-    ws_backsub_reg<NZ>(Hp, xs);
+    // (fully unrolled register sweep only where its code is small: the vehicle kernel is bound by instruction fetch --
+    // ncu stall no_instruction 20-40 % in every phase at 160 KB of SASS -- so it keeps the rolled shared-memory sweep)
+    if constexpr (NZ <= WS_BACKSUB_REG_MAXNZ) ws_backsub_reg<NZ>(Hp, xs);
+    else ws_backsub<NZ>(Hp, xs);
     return true;
 }
 
@@ -1732,6 +1741,8 @@ typedef WsCfg<21, 2, 2, 50, 2, NLPF_DYN_AFFINE, 0, WS_LIN_WARPS, 0, false, NLPF_
 #define WS_CAR_MAXW 8
 #endif
 typedef WsCfg<11, 5, 3, 51, 12, NLPF_DYN_AFFINE, 1, WS_GNSS_WARPS, 0, false, NLPF_LOSS_L2, WS_GNSS_MMA != 0, WS_GNSS_MAXW> CfgGnss;     // gnss_stationary.py MHE (BASELINE configs[2])
+// nlpf_assemble evaluates once per window: the structure-of-arrays copy would cost more than it saves (measured 0.18 vs 0.14 ms)
+typedef WsCfg<11, 5, 3, 51, 12, NLPF_DYN_AFFINE, 1, WS_GNSS_WARPS, 0, false, NLPF_LOSS_L2, WS_GNSS_MMA != 0, WS_GNSS_MAXW, true> CfgGnssAsm;
 typedef WsCfg<6, 9, 2, 21, 11, NLPF_DYN_VEHICLE_GNSS, 1, WS_CAR_WARPS, 2, true, NLPF_LOSS_L2, WS_CAR_MMA != 0, WS_CAR_MAXW> CfgCar;         // autonomous-car.py:184-220
 typedef WsCfg<6, 9, 2, 21, 11, NLPF_DYN_VEHICLE_GNSS, 1, WS_CAR_WARPS, 2, true, NLPF_LOSS_HUBER, WS_CAR_MMA != 0, WS_CAR_MAXW> CfgCarHuber;  // autonomous-car.py:293-318
 
@@ -1759,7 +1770,7 @@ extern "C" int nlpf_ws_assemble(int variant, nlpf_problem* p, int B, const doubl
     switch (variant) {
         case 0: return ws_assemble_launch<CfgVdp>(p, B, z, U, data, xprior, mu, H_out, g_out, cost_out, st);
         case 1: return ws_assemble_launch<CfgExample>(p, B, z, U, data, xprior, mu, H_out, g_out, cost_out, st);
-        case 2: return ws_assemble_launch<CfgGnss>(p, B, z, U, data, xprior, mu, H_out, g_out, cost_out, st);
+        case 2: return ws_assemble_launch<CfgGnssAsm>(p, B, z, U, data, xprior, mu, H_out, g_out, cost_out, st);
         case 3: return ws_assemble_launch<CfgCar>(p, B, z, U, data, xprior, mu, H_out, g_out, cost_out, st);
         case 4: return ws_assemble_launch<CfgCarHuber>(p, B, z, U, data, xprior, mu, H_out, g_out, cost_out, st);
     }

@@ -294,7 +294,9 @@ def test_unregistered_models_fail_loudly():
     from nlp_filter_b200._capi import NlpfError
     problem = nlp.fixedTimeOptimalEstimationNLP(5, 1.0, 2, 1)
     X = problem.addVariables(6, 2, name='x')
-    problem.addDynamics(lambda x, u, params=None: np.array([np.sin(x[0]) + u[0], x[1] ** 2]), X, None, None)
+    # (a smooth unregistered model is now lowered by code generation -- tests/test_gpu_codegen.py; one that cannot be
+    # traced still fails loudly instead of falling back to the CPU)
+    problem.addDynamics(lambda x, u, params=None: np.array([np.sin(x[0]) + u[0], x[1] ** 2 if x[1] > 0 else 0.0]), X, None, None)
     with pytest.raises(NotImplementedError):
         problem.build()
     f = ekf.EKF(lambda *a, **k: None, lambda *a, **k: None, np.zeros(5), np.eye(5))
