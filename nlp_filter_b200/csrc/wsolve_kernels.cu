@@ -31,9 +31,6 @@
 #ifndef WS_SOA
 #define WS_SOA 1
 #endif
-#ifndef WS_TILEH
-#define WS_TILEH 1
-#endif
 #ifndef WS_LINQ
 #define WS_LINQ 1         // linear measurements with constant weights as a quadratic form (see ws_eval)
 #endif
@@ -211,13 +208,6 @@ struct WsCfg {
     // rounds of 32 lanes of the evaluation loops unrolled (their dependent chains interleave): GNSS +1.8 %, van der Pol
     // neutral; not for the vehicle class, whose kernel is bound by instruction fetch (160 KB of SASS)
     static constexpr int RU = (DYN_ == NLPF_DYN_VEHICLE_GNSS) ? 1 : 4;
-    // H is never assembled in shared memory: the evaluation leaves per-node blocks (G~F, F^T Lambda F + second-order
-    // term) and the diagonals, and the factorisation builds its register tiles from them, the window's constant part
-    // (global, L2) and D~ (ws_tile_value).  Replaces the read-modify-write scatter of the dynamics Hessian into the packed
-    // matrix (11 % of the samples, a third of its shared-memory wavefronts conflict replays), the cp.async reload of the
-    // constant part every evaluation and the tile load.  Van der Pol class (n = 2: a column pair of a tile is one node).
-    static constexpr bool TILEH = MMA_ && (DYN_ == NLPF_DYN_VDP) && (MEAS_ == 0) && (NB_ == 0) && !PRIOR_ &&
-                                  (LOSS_ == NLPF_LOSS_L2) && (N_ == 2) && (WS_TILEH != 0);
     // pseudorange records as structure-of-arrays [field][slot][epoch] per window (ws_soa_kernel makes the copy once per
     // call): the evaluation has one lane per epoch, so a warp's loads of one field of one slot are then consecutive
     // 8-byte words (2 x 128 B per request) instead of 32 words 480 B apart (the caller's record layout [y, w, sat xyz]
@@ -272,13 +262,7 @@ struct WsLayout {
     // linear measurements with constant weights (WS_LINQ): b = Phi^T W y per unknown, [sum w y^2, flag], per window
     static constexpr int oBM = oCLK + 2;
     static constexpr int oC0 = oBM + ev(C::MEAS == 0 ? NZ : 0);
-    // TILEH: per-node blocks GFt_j[a][b] = w_jb F_j[b][a], FFS_j = F_j^T Lambda_j F_j + second-order term, diagonal of the
-    // window's constant H, damped diagonal handed to the factorisation
-    static constexpr int oGF = oC0 + (C::MEAS == 0 ? 2 : 0);
-    static constexpr int oFFS = oGF + (C::TILEH ? ev(K * N * N) : 0);
-    static constexpr int oHD = oFFS + (C::TILEH ? ev(K * N * N) : 0);
-    static constexpr int oDL = oHD + (C::TILEH ? ev(NZ) : 0);
-    static constexpr int PER_WARP = oDL + (C::TILEH ? ev(NZ) : 0);
+    static constexpr int PER_WARP = oC0 + (C::MEAS == 0 ? 2 : 0);
     static_assert(NQ >= NZ, "fb shares the head of Q");
     static constexpr int oDt = C::WARPS * PER_WARP;    // shared by the CTA
     static constexpr int NTILE = ((NZ + 4) / 4) * ((NZ + 4) / 2 + 1);   // bound on the tile table (row quads x column pairs)
@@ -378,7 +362,7 @@ __device__ __forceinline__ void ws_eval(const DevProb& P, double* sm, const WsCo
     auto phi = [&](int e, int j) -> double { return cs.Phi[e * K + j]; };
     auto phiT = [&](int j, int e) -> double { return cs.Phi[e * K + j]; };
 
-    if (FULL && !C::TILEH) {       // constant part (+ linear measurements), asynchronously; waited for before the first use of Hp
+    if (FULL) {       // constant part (+ linear measurements), asynchronously; waited for before the first use of Hp
         for (int p = 2 * lane; p < L::NP; p += 64) cp_async16<C::MEAS == 0>(Hp + p, h0 + p);
     }
     // node dynamics
@@ -451,41 +435,8 @@ __device__ __forceinline__ void ws_eval(const DevProb& P, double* sm, const WsCo
             }
             g[t] = s;
         }
-        if (!C::TILEH) cp_async_wait_all();
+        cp_async_wait_all();
         __syncwarp();
-        if constexpr (C::TILEH) {
-            // per-node blocks for ws_tile_value, the Gauss-Newton diagonal dd and the full diagonal ds
-            double* GFt = sm + L::oGF;
-            double* FFS = sm + L::oFFS;
-            for (int t = lane; t < K * N * N; t += 32) {
-                const int k = t / (N * N), rem = t - k * N * N, a = rem / N, b = rem - a * N;
-                const double* Fk = Fm + k * N * N;
-                GFt[t] = cs.cwq[k * N + b] * Fk[b * N + a];
-                double ff = 0.0;
-#pragma unroll
-                for (int i = 0; i < N; ++i) ff = fma(Fk[i * N + a] * cs.cwq[k * N + i], Fk[i * N + b], ff);
-                FFS[t] = ff;
-            }
-            __syncwarp();
-            double* dd_ = sm + L::oDD;
-            double* ds_ = sm + L::oDS;
-            const double* hd = sm + L::oHD;
-            for (int r = lane; r < NZ; r += 32) {
-                const int j = r / N, a = r - j * N;
-                const double gn = hd[r] - 2.0 * Dt[j * K + j] * GFt[(j * N + a) * N + a] + FFS[(j * N + a) * N + a];
-                dd_[r] = gn;
-                double so = 0.0;                            // exact second-order term: hess f0 = [[0, -2 x1], [-2 x1, -2 x0]]
-                if (a == 1) so = lw[j * N] * 2.0 * zc[j * N];
-                ds_[r] = gn + so;
-            }
-            __syncwarp();
-            for (int k = lane; k < K; k += 32) {            // second-order term into FFS (entries (1,0), (0,1), (1,1))
-                const double x0 = zc[k * N], x1 = zc[k * N + 1], l0 = lw[k * N];
-                FFS[(k * N + 1) * N + 0] += l0 * 2.0 * x1;
-                FFS[(k * N + 0) * N + 1] += l0 * 2.0 * x1;
-                FFS[(k * N + 1) * N + 1] += l0 * 2.0 * x0;
-            }
-        } else
         if (!C::HCONST) {
             // H_(j,a),(l,b) += -Dt_jl w_jb F_j[b][a] - Dt_lj w_la F_l[a][b]  (+ Huber: sum_k Dt_kj Dt_kl w_ka on a == b)
             for (int pr = lane; pr < K * (K + 1) / 2; pr += 32) {
@@ -897,7 +848,7 @@ __device__ __forceinline__ void ws_eval(const DevProb& P, double* sm, const WsCo
             }
         }
     }
-    if (FULL && !C::TILEH) {
+    if (FULL) {
         __syncwarp();
         // Gauss-Newton diagonal for the damping, then the exact second-order dynamics term
         double* dd = sm + L::oDD;
@@ -919,48 +870,6 @@ __device__ __forceinline__ void ws_eval(const DevProb& P, double* sm, const WsCo
     merit_out = merit;
     noise_out = 2.220446049250313e-16 * (0.5 * wsum(nse) + fabs(merit));
     __syncwarp();
-}
-
-// One accumulator-tile register pair of the matrix the factorisation works on, computed instead of loaded (WsCfg::TILEH):
-// entries (r, c), (r, c+1) with r = 8 I + lane/4, c = 8 J + 2 (lane%4), lower triangle, n = 2 (c even: one node l = c/2).
-//   H_(j,a),(l,b) = hlin + [ -D~_jl w_jb F_j[b][a] - D~_lj w_la F_l[a][b] ] + (j == l) (F^T Lambda F + second order)_j[a][b]
-// the diagonal replaced by `diag` (damped, or the plain diagonal for nlpf_assemble), row nz = the right-hand side,
-// rows beyond: unit pivots.
-struct WsTileSrc {
-    const double* h0;      // window's constant H, row-padded packed (global)
-    const double* Dt;      // K x K (shared)
-    const double* GFt;     // [j][a][b] = w_jb F_j[b][a]
-    const double* FFS;     // [j][a][b]
-    const double* diag;    // nz
-    const double* rhs;     // nz (gradient)
-};
-template <int NZ, int K, int N>
-__device__ __forceinline__ double2 ws_tile_value(const WsTileSrc& T, int r, int c) {
-    static_assert(N == 2, "a column pair of a tile is one node");
-    double2 v = make_double2(0.0, 0.0);
-    if (r < NZ && c <= r) {
-        const double2 hl = *reinterpret_cast<const double2*>(T.h0 + po(r) + c);
-        const int j = r / N, a = r - j * N, l = c / N;
-        const double djl = T.Dt[j * K + l], dlj = T.Dt[l * K + j];
-        const double2 gj = *reinterpret_cast<const double2*>(T.GFt + (j * N + a) * N);     // w_jb F_j[b][a], b = 0, 1
-        const double gl0 = T.GFt[(l * N + 0) * N + a], gl1 = T.GFt[(l * N + 1) * N + a];     // w_la F_l[a][b], b = 0, 1
-        v.x = fma(-dlj, gl0, fma(-djl, gj.x, hl.x));
-        v.y = fma(-dlj, gl1, fma(-djl, gj.y, hl.y));
-        if (j == l) {
-            const double2 ff = *reinterpret_cast<const double2*>(T.FFS + (j * N + a) * N);
-            v.x += ff.x;
-            v.y += ff.y;
-        }
-        if (c == r) { v.x = T.diag[r]; v.y = 0.0; }             // (c, c+1) = (diagonal, upper triangle)
-        else if (c + 1 == r) v.y = T.diag[r];
-    } else if (r == NZ && c < NZ) {
-        v = *reinterpret_cast<const double2*>(T.rhs + c);      // NZ even: c + 1 < NZ as well
-    }
-    if (r >= NZ) {                                             // unit pivots for the appended row and the padding rows
-        if (c == r) v.x = 1.0;
-        if (c + 1 == r) v.y = 1.0;
-    }
-    return v;
 }
 
 // constant H of a window with linear measurements: Hc + sum_e (phi_e phi_e^T) (x) diag(w_e), built in the window's
@@ -1042,9 +951,6 @@ __device__ __forceinline__ void ws_hlin(const DevProb& P, double* sm, const WsCo
     }
     __syncwarp();
     for (int p = lane; p < L::NP; p += 32) hl[p] = Hp[p];
-    if constexpr (C::TILEH) {                          // diagonal of the constant part, for the evaluation's dd / ds
-        for (int i = lane; i < K * N; i += 32) sm[L::oHD + i] = Hp[pk(i, i)];
-    }
 }
 
 // nlpf_assemble for the classes of this file: kernels (1)+(2) alone -- one evaluation of H (Gauss-Newton part +
@@ -1079,29 +985,6 @@ ws_assemble_kernel(const __grid_constant__ DevProb P, int B, const double* __res
         ws_eval<C, true>(P, sm, cs, zs, U + (size_t)b * K * (M > 0 ? M : 1), dg, C::PRIOR ? xprior + (size_t)b * N : nullptr,
                          h0, mu, J, merit, nse);
         __syncwarp();
-        if constexpr (C::TILEH) {
-            // H is not in shared memory for this class: the same tile values the factorisation starts from (plain
-            // diagonal), all into registers first -- the constant part is read from this very output block -- then out
-            constexpr int NB8 = (NZ + 7) / 8;
-            WsTileSrc ts;
-            ts.h0 = h0; ts.Dt = cs.Dt; ts.GFt = sm + L::oGF; ts.FFS = sm + L::oFFS; ts.diag = sm + L::oDS; ts.rhs = sm + L::oG;
-            double2 tv[NB8 * (NB8 + 1) / 2];
-            const int gq = lane >> 2, tq = lane & 3;
-#pragma unroll
-            for (int I = 0; I < NB8; ++I)
-#pragma unroll
-                for (int J = 0; J <= I; ++J) tv[I * (I + 1) / 2 + J] = ws_tile_value<NZ, K, N>(ts, 8 * I + gq, 8 * J + 2 * tq);
-            __syncwarp();
-#pragma unroll
-            for (int I = 0; I < NB8; ++I)
-#pragma unroll
-                for (int J = 0; J <= I; ++J) {
-                    const int r = 8 * I + gq, c = 8 * J + 2 * tq;
-                    const double2 v = tv[I * (I + 1) / 2 + J];
-                    if (r < NZ && c <= r) { Ho[r * NZ + c] = v.x; Ho[c * NZ + r] = v.x; }
-                    if (r < NZ && c + 1 <= r) { Ho[r * NZ + c + 1] = v.y; Ho[(c + 1) * NZ + r] = v.y; }
-                }
-        } else
         for (int t = lane; t < NZ * NZ; t += 32) {
             const int r = t / NZ, c = t - r * NZ;
             Ho[t] = (c <= r) ? Hp[pk(r, c)] : Hp[pk(c, r)];
@@ -1406,8 +1289,8 @@ __device__ __forceinline__ void dmma884(double2& c, double a, double b) {
                  : "+d"(c.x), "+d"(c.y) : "d"(a), "d"(b));
 }
 
-template <int NZ, int LDW, int RN, int K = 0, int N = 0>
-__device__ __forceinline__ bool ws_ldl_mma(double* Hp, double* xs, double* PB, const WsTileSrc* tsrc = nullptr) {
+template <int NZ, int LDW, int RN>
+__device__ __forceinline__ bool ws_ldl_mma(double* Hp, double* xs, double* PB) {
     constexpr int NB = (NZ + 8) / 8;                 // tile rows covering rows 0..NZ
     constexpr int NPANEL = (NZ + 3) / 4;
     // PB: 32 * NB doubles (WsLayout::NPB)
@@ -1419,10 +1302,6 @@ __device__ __forceinline__ bool ws_ldl_mma(double* Hp, double* xs, double* PB, c
         for (int J = 0; J <= I; ++J) {
             const int r = 8 * I + g, cc = 8 * J + 2 * t;
             double2 v = make_double2(0.0, 0.0);
-            if constexpr (K > 0) {                   // tiles computed from the per-node blocks (WsCfg::TILEH)
-                c[I * (I + 1) / 2 + J] = ws_tile_value<NZ, K, N>(*tsrc, r, cc);
-                continue;
-            }
             if (r <= NZ && cc <= r) {                // (always true off the diagonal tiles for r <= NZ)
                 v = *reinterpret_cast<const double2*>(Hp + po(r) + cc);
                 if (cc == r) v.y = 0.0;              // upper triangle / row padding
@@ -1649,7 +1528,7 @@ wsolve_kernel(const __grid_constant__ DevProb P, int B, double* __restrict__ z_i
                     dm = 0.0;
                     for (int i = lane; i < NZ; i += 32) {
                         gm = fmax(gm, fabs(g[i]));
-                        if (!C::TILEH) ds[i] = Hp[pk(i, i)];       // (TILEH: the evaluation wrote ds itself)
+                        ds[i] = Hp[pk(i, i)];
                         dm = fmax(dm, dd[i]);
                     }
                     dm = wmax(dm);
@@ -1669,23 +1548,13 @@ wsolve_kernel(const __grid_constant__ DevProb P, int B, double* __restrict__ z_i
                     if (!h_valid) { h_valid = true; ev = EV_RESTORE; need_eval = true; continue; }
                     pc = PC_SOLVE;
                 } else if (pc == PC_SOLVE) {
-                    if constexpr (C::TILEH) {
-                        for (int i = lane; i < NZ; i += 32) sm[L::oDL + i] = ds[i] + lam * (dd[i] + 1e-14 * dm);
-                        __syncwarp();
-                    } else {
-                        for (int i = lane; i < NZ; i += 32) {
-                            Hp[pk(i, i)] = ds[i] + lam * (dd[i] + 1e-14 * dm);
-                            Hp[pk(NZ, i)] = g[i];
-                        }
+                    for (int i = lane; i < NZ; i += 32) {
+                        Hp[pk(i, i)] = ds[i] + lam * (dd[i] + 1e-14 * dm);
+                        Hp[pk(NZ, i)] = g[i];
                     }
                     h_valid = false;
                     bool ok;
                     const long long pt1 = prof ? clock64() : 0;
-                    if constexpr (C::TILEH) {
-                        WsTileSrc ts;
-                        ts.h0 = hlin; ts.Dt = cs.Dt; ts.GFt = sm + L::oGF; ts.FFS = sm + L::oFFS; ts.diag = sm + L::oDL; ts.rhs = g;
-                        ok = ws_ldl_mma<NZ, L::LDW, WS_LIN_NEWTON, K, N>(Hp, dz, sm + L::oF, &ts);
-                    } else
                     if constexpr (C::MMA) ok = ws_ldl_mma<NZ, L::LDW, (C::MEAS == 0) ? WS_LIN_NEWTON : 2>(Hp, dz, sm + L::oF);
                     else ok = ws_ldl<NZ, L::LDW>(ttab, tcnt, Hp, dz, sm + L::oF);
                     if (prof && lane == 0) { atomicAdd(prof + 1, (unsigned long long)(clock64() - pt1)); atomicAdd(prof + 3, 1ULL); }
