@@ -29,34 +29,40 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 # algorithmic flop per Gauss-Newton iteration and compulsory bytes per window
-FLOP_PER_ITER = {"vdp": 146480.0, "gnss": 297342.0, "2rx": 1338750.0, "car": 172272.0, "ekf": 9178.0, "ls": 806.0}
+FLOP_PER_ITER = {"vdp": 146480.0, "gnss": 297342.0, "2rx": 1338750.0, "car": 172272.0, "ekf": 9178.0, "ls": 806.0,
+                 "rc": 1517808.0, "mrx": 2052636.0}
 # of which factorisation + the two triangular solves (kernel 3); the rest is kernels 1+2
-FLOP_CHOL_PER_ITER = {"vdp": 28224.0, "gnss": 61508.0, "2rx": 467866.0, "car": 58320.0}
+FLOP_CHOL_PER_ITER = {"vdp": 28224.0, "gnss": 61508.0, "2rx": 467866.0, "car": 58320.0, "rc": 698544.0, "mrx": 731818.0}
 NZ = {"vdp": 42, "gnss": 55, "car": 54, "2rx": 99}
-BYTES_PER_WINDOW = {"vdp": 2104.0 + 360.0, "gnss": 25184.0 + 464.0, "2rx": 7920.0 + 904.0, "car": 9840.0 + 456.0, "ekf": 448.0, "ls": 416.0}
+BYTES_PER_WINDOW = {"rc": 21024.0 + 1032.0, "mrx": 62512.0 + 1048.0, "vdp": 2104.0 + 360.0, "gnss": 25184.0 + 464.0, "2rx": 7920.0 + 904.0, "car": 9840.0 + 456.0, "ekf": 448.0, "ls": 416.0}
 WORKLOAD_DESC = {
     "vdp": "van_der_pol MHE windows (K=21 nodes, n=2, m=1, 50 full-state epochs, Q=1e-2 I, nz=42)",
     "gnss": "stationary-receiver GNSS MHE windows (K=11, n=5, m=3, 51 epochs x 12 pseudoranges, nz=55)",
     "2rx": "two-receiver GNSS MHE scenarios (gnss-multi-receiver.py shape: K=11, n=10, m=6, 120 pseudorange slots + 51 range + "
            "51 heading residuals, arrival cost, zA == zB folded, nz=99), 1024 scenarios in total sharded over the GPUs",
+    "rc": "RC-car MHE windows (rc-car.py shape: K=21, n=6, m=2, 41 epochs x 12 pseudoranges, nz=126), start near the truth",
+    "mrx": "multi-receiver MHE windows (multi-receiver.py shape: K=16, n=8, m=0, 3 global unknowns, 64 epochs x (11 pseudoranges + 11 "
+           "pseudorange rates + 1 range), nz=131): flat valley, most windows run to the 300-iteration limit (DESIGN section 3)",
     "car": "vehicle MHE chains (autonomous-car.py shape: K=6, n=9, m=2, 21 epochs x 11 pseudoranges, arrival cost, bounds, nz=54), "
            "receding-horizon windows DT = 1 s, warm-started",
     "ekf": "5-state GNSS EKF (utils/ekf.py + utils/gnss.py), 256 filters x 64 predict/update steps, 12 satellites",
     "ls": "iterative GNSS least squares (utils/leastsquares.py:19-42), 16384 independent epochs x 12 satellites, ECEF",
 }
-METRIC = {"vdp": ("solved_windows_per_sec", "windows/s"), "gnss": ("solved_windows_per_sec", "windows/s"),
+METRIC = {"rc": ("solved_windows_per_sec", "windows/s"), "mrx": ("solved_windows_per_sec", "windows/s"),
+          "vdp": ("solved_windows_per_sec", "windows/s"), "gnss": ("solved_windows_per_sec", "windows/s"),
           "car": ("solved_windows_per_sec", "windows/s"), "2rx": ("solved_windows_per_sec", "windows/s"),
           "ekf": ("ekf_steps_per_sec", "filter-steps/s"), "ls": ("ls_epochs_per_sec", "epochs/s")}
 
 
 def make_problem(workload):
     from nlp_filter_b200 import shapes
-    return {"vdp": shapes.vdp_mhe, "gnss": shapes.gnss, "2rx": shapes.two_receiver}[workload]()
+    return {"vdp": shapes.vdp_mhe, "gnss": shapes.gnss, "2rx": shapes.two_receiver, "rc": shapes.rc, "mrx": shapes.multi_receiver}[workload]()
 
 
 def make_batch(desc, workload, B, seed):
     from nlp_filter_b200 import synth
-    return {"vdp": synth.vdp_mhe_batch, "gnss": synth.gnss_batch, "2rx": synth.two_receiver_batch}[workload](desc, B, seed=seed)
+    return {"vdp": synth.vdp_mhe_batch, "gnss": synth.gnss_batch, "2rx": synth.two_receiver_batch, "rc": synth.rc_batch,
+            "mrx": synth.multi_receiver_batch}[workload](desc, B, seed=seed)
 
 
 # ---------------------------------------------------------------------------------------------
@@ -75,7 +81,8 @@ def _cpu_init(workload, B, seed):
 def _cpu_solve(i):
     from oracle import nls
     d, bt = _CPU["d"], _CPU["bt"]
-    win = nls.Window(d, U=bt["U"][i], data=bt["data"][i], xprior=None if bt.get("xprior") is None else bt["xprior"][i])
+    win = nls.Window(d, U=None if bt.get("U") is None else bt["U"][i], data=bt["data"][i],
+                     xprior=None if bt.get("xprior") is None else bt["xprior"][i])
     z, info = nls.solve(d, win, bt["z0"][i])
     return info["iters"]
 
@@ -467,7 +474,7 @@ def run_reference(args):
         return 0
     world = int(os.environ.get("WORLD_SIZE", "1"))
     cores = os.cpu_count() or 1
-    n = args.cpu_windows or {"vdp": 256, "gnss": 64, "2rx": 48, "ekf": 64, "ls": 2048, "car": 0}.get(args.workload, 0)
+    n = args.cpu_windows or {"vdp": 256, "gnss": 64, "2rx": 48, "ekf": 64, "ls": 2048, "car": 0, "rc": 32, "mrx": 16}.get(args.workload, 0)
     vals = []
     for s in range(args.warmup + args.steps):
         t0 = time.perf_counter()
@@ -481,7 +488,7 @@ def run_reference(args):
         if s >= args.warmup:
             vals.append((v, time.perf_counter() - t0, it))
     value = float(np.mean([v[0] for v in vals]))
-    if args.workload in ("vdp", "gnss", "2rx"):
+    if args.workload in ("vdp", "gnss", "2rx", "rc", "mrx"):
         _, config = shared_config(args, world)
     elif args.workload == "car":
         config = {"workload": WORKLOAD_DESC["car"], "runs": 2048, "chained_windows_per_run": args.chain, "windows_per_step": 2048 * args.chain}
@@ -506,6 +513,8 @@ def shared_config(args, world):
     """The `config` dict both arms print (the CPU arm's bounded sample is described in its cpu_baseline)."""
     strong = args.workload == "2rx"
     B = (1024 // world if args.windows == 4096 else args.windows) if strong else args.windows
+    if args.windows == 4096 and args.workload in ("rc", "mrx"):
+        B = {"rc": 1024, "mrx": 256}[args.workload]          # windows of these classes are 10-100x the work of the headline ones
     return B, {"workload": WORKLOAD_DESC[args.workload], "windows_per_gpu": B, "global_windows": world * B,
                "parallelism": "windows sharded over %d GPU(s), all-gather of estimates at the end" % world
                               + (" of every step, overlapped with the next step's solve (two buffers)" if world > 1 else ""),
@@ -519,7 +528,7 @@ def run_ours(args):
     cpu_base = None
     if world == 1 and rank == 0 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
-        n = args.cpu_windows or {"vdp": 512, "gnss": 128, "2rx": 64}[args.workload]
+        n = args.cpu_windows or {"vdp": 512, "gnss": 128, "2rx": 64, "rc": 32, "mrx": 16}[args.workload]
         v, it = cpu_path_windows_per_sec(args.workload, n, cores)        # before CUDA is initialised (fork)
         cpu_base = {"value": v, "unit": "windows/s", "cores": cores, "kind": "port",
                     "sample": "the first %d windows of the same synthetic batch (seed 2000), NumPy restatement "
@@ -540,7 +549,8 @@ def run_ours(args):
     prob = engine.WindowProblem(desc)
     bt = make_batch(desc, args.workload, B, seed=2000 + rank)
     dev = lambda a: torch.as_tensor(np.ascontiguousarray(a)).cuda()
-    z0, U, data = dev(bt["z0"]), dev(bt["U"]), dev(bt["data"])
+    z0, data = dev(bt["z0"]), dev(bt["data"])
+    U = dev(bt["U"]) if bt.get("U") is not None else None
     xprior = dev(bt["xprior"]) if bt.get("xprior") is not None else None
     z = torch.empty_like(z0)
     cost = torch.empty((B,), dtype=torch.float64, device="cuda")
@@ -701,7 +711,7 @@ def run_ours(args):
                              + (" -> all-gather -> D2H of the gathered estimates" if world > 1 else "")
                              + "; the NumPy -> pinned staging (HostBatch.load, once) and the NumPy views of the results are outside"},
             "gpu_launches": args.steps * (3 if (args.workload == "vdp" and B > 1776) else 1),
-            "roofline": {"bound": "fp64", "bound_note": "compute-bound on the FP64 FMA pipe; the contract's vocabulary is hbm|tensor: B200 has no FP64 tcgen05 kind and its FP64 mma.sync peak (nlpf_dmma_probe: 36.7 TFLOP/s) equals the vector peak used here", "kernel": {"vdp": "wsolve_kernel<CfgVdp>", "gnss": "wsolve_kernel<CfgGnss>", "2rx": "solve_kernel_prb"}[args.workload], "achieved": achieved, "peak": peak_fp64,
+            "roofline": {"bound": "fp64", "bound_note": "compute-bound on the FP64 FMA pipe; the contract's vocabulary is hbm|tensor: B200 has no FP64 tcgen05 kind and its FP64 mma.sync peak (nlpf_dmma_probe: 36.7 TFLOP/s) equals the vector peak used here", "kernel": {"vdp": "wsolve_kernel<CfgVdp>", "gnss": "wsolve_kernel<CfgGnss>", "2rx": "solve_kernel_prb", "rc": "solve_kernel_prb", "mrx": "solve_kernel_prb"}[args.workload], "achieved": achieved, "peak": peak_fp64,
                          "unit": "TFLOP/s", "frac": achieved / peak_fp64 if peak_fp64 > 0 else None,
                          "traffic": traffic, "kernel_ms": ms_kernel,
                          "peak_source": "FP64 FMA probe (nlpf_fp64_probe) measured in this run; MEASURED_PEAKS.json "
@@ -913,7 +923,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="vdp", choices=["vdp", "gnss", "2rx", "car", "ekf", "ls",
-                                                          "assemble-vdp", "assemble-gnss", "assemble-car", "vdp-long"])
+                                                          "assemble-vdp", "assemble-gnss", "assemble-car", "vdp-long", "rc", "mrx"])
     ap.add_argument("--chain", type=int, default=200, help="chained windows per run (car workload; BASELINE configs[3]: horizon 200)")
     ap.add_argument("--windows", type=int, default=4096, help="windows per GPU per step")
     ap.add_argument("--cpu-windows", type=int, default=0, help="size of the CPU-path sample")

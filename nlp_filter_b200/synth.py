@@ -277,3 +277,98 @@ def vdp_multiseg_batch(seg, S, B, seed=6000):
     z0 = np.stack([_interp_rows(t_ep, y[:, 0, :], t_nodes), _interp_rows(t_ep, y[:, 1, :], t_nodes)], 2).reshape(B, -1)
     x_nodes = np.stack([_interp_rows(tt, xs[:, 0, :], t_nodes), _interp_rows(tt, xs[:, 1, :], t_nodes)], 2)
     return dict(z0=z0, U=U, data=data, truth_nodes=x_nodes, t_nodes=t_nodes, x0=x0)
+
+
+def rc_batch(d, B, seed=7000, n_sat=12, r_pr=1.0):
+    """RC-car windows (rc-car.py:85-114 shape: K=21, n=6, m=2, 41 epochs x 12 pseudoranges on state components
+    [0, 1, 2, 3]): truth by RK4 of the model the estimator uses (nlp/dynamics.py:117-136, quirks included), smooth
+    throttle / steering, start point = truth + noise (the script's zero start needs 100+ iterations)."""
+    rng = np.random.default_rng(seed)
+    T, E, K = d.T, d.E, d.K
+    epochs = d.epochs
+    ph = rng.uniform(0, 2 * np.pi, (B, 2))
+
+    def ctrl(t):
+        return np.stack([0.35 + 0.1 * np.sin(0.2 * t + ph[:, 0]), 0.3 * np.sin(0.15 * t + ph[:, 1])], 1)
+
+    def rhs(x, u):
+        v = 8.72649116358 * u[:, 0] - 0.856053299155
+        dl = np.deg2rad(28) * u[:, 1]
+        f = np.zeros_like(x)
+        f[:, 0] = v * np.cos(x[:, 2])
+        f[:, 1] = v * np.sin(x[:, 2])
+        f[:, 3] = x[:, 4]
+        f[:, 5] = (v / 0.28) * np.tan(dl)
+        return f
+
+    x = np.zeros((B, 6))
+    x[:, 2] = rng.uniform(-1.0, 1.0, B)
+    x[:, 3] = rng.uniform(-100, 100, B)
+    x[:, 4] = rng.normal(0.0, 1.0, B)
+    dt = 0.02
+    nstep = int(round(T / dt))
+    xs = np.zeros((nstep + 1, B, 6))
+    xs[0] = x
+    for i in range(nstep):
+        t = i * dt
+        k1 = rhs(x, ctrl(t))
+        k2 = rhs(x + 0.5 * dt * k1, ctrl(t + 0.5 * dt))
+        k3 = rhs(x + 0.5 * dt * k2, ctrl(t + 0.5 * dt))
+        k4 = rhs(x + dt * k3, ctrl(t + dt))
+        x = x + dt / 6 * (k1 + 2 * k2 + 2 * k3 + k4)
+        xs[i + 1] = x
+    el = np.arcsin(rng.uniform(np.sin(np.deg2rad(15)), 1.0, (B, n_sat)))
+    az = rng.uniform(0, 2 * np.pi, (B, n_sat))
+    rad = rng.uniform(2.0e7, 2.6e7, (B, n_sat))
+    sat = np.stack([rad * np.cos(el) * np.sin(az), rad * np.cos(el) * np.cos(az), rad * np.sin(el)], 2)
+    data = np.zeros((B, d.Ldata))
+    off = d.roff.reshape(E, n_sat)
+    for e in range(E):
+        xe = xs[int(round(epochs[e] / dt))]
+        rho = np.sqrt(np.sum((xe[:, None, :3] - sat) ** 2, 2))
+        pr = rho + xe[:, 3:4] + rng.normal(0.0, np.sqrt(r_pr), rho.shape)
+        for j in range(n_sat):
+            o = off[e, j]
+            data[:, o] = pr[:, j]
+            data[:, o + 1] = 1.0 / r_pr
+            data[:, o + 2:o + 5] = sat[:, j]
+    tn = d.cpm.tau2t(d.cpm.tau)
+    U = np.stack([ctrl(t) for t in tn], 1)
+    idx = np.clip(np.round(tn / dt).astype(int), 0, nstep)
+    z0 = xs[idx].transpose(1, 0, 2) + rng.normal(0, 0.3, (B, K, 6)) * np.array([1, 1, 0.05, 1, 0.05, 0.05])
+    return dict(z0=z0.reshape(B, -1), U=np.ascontiguousarray(U), data=data, xprior=None, truth=xs[idx].transpose(1, 0, 2))
+
+
+def multi_receiver_batch(d, B, seed=8000):
+    """multi-receiver.py:62-99 shape (K=16, n=8, m=0, three global unknowns XA; per epoch pseudorange + pseudorange rate
+    per satellite and one planar range to XA): a receiver moving at constant velocity, start point = the truth's
+    neighbourhood (the script's zero start is multi-modal)."""
+    rng = np.random.default_rng(seed)
+    n_sat = (d.M // d.E - 1) // 2
+    pos = np.array([-545.0, -53.0, 75.0]) + rng.normal(0, 1, (B, 3))
+    vel = rng.normal(0, 0.3, (B, 3))
+    xa = pos[:, :2] + np.array([1.7, 1.7])
+    el = np.arcsin(rng.uniform(np.sin(np.deg2rad(15)), 1.0, (B, n_sat)))
+    az = rng.uniform(0, 2 * np.pi, (B, n_sat))
+    rad = rng.uniform(2.0e7, 2.6e7, (B, n_sat))
+    sat = np.stack([rad * np.cos(el) * np.sin(az), rad * np.cos(el) * np.cos(az), rad * np.sin(el)], 2)
+    sv = rng.normal(0, 2e3, (B, n_sat, 3))
+    data = np.zeros((B, d.Ldata))
+    r = 0
+    for e in range(d.E):
+        t = d.epochs[e]
+        p = pos + vel * t
+        for j in range(n_sat):
+            s = sat[:, j] + sv[:, j] * t
+            los = s - p
+            rho = np.linalg.norm(los, axis=1)
+            o = d.roff[r]; data[:, o] = rho + 13.5 + 0.7 * t + rng.normal(0, 3, B); data[:, o + 1] = 0.01; data[:, o + 2:o + 5] = s; r += 1
+            o = d.roff[r]; data[:, o] = np.sum((sv[:, j] - vel) * los / rho[:, None], 1) + 0.7 + rng.normal(0, 0.1, B)
+            data[:, o + 1] = 10.0; data[:, o + 2:o + 5] = s; data[:, o + 5:o + 8] = sv[:, j]; r += 1
+        o = d.roff[r]; data[:, o] = 2.4384; data[:, o + 1] = 100.0; r += 1
+    assert r == d.M
+    z0 = np.zeros((B, d.K, 8))
+    z0[:, :, :3] = pos[:, None, :]
+    z0[:, :, 3] = 13.5
+    z0 = np.concatenate([z0.reshape(B, -1), xa, np.zeros((B, 1))], 1)
+    return dict(z0=z0, U=None, data=data, xprior=None)
