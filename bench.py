@@ -327,7 +327,8 @@ def run_aux(args):
             "config": {"workload": WORKLOAD_DESC[args.workload] if args.windows == 4096 else
                        WORKLOAD_DESC[args.workload].replace("256 filters", "%d filters" % args.windows).replace("16384 independent", "%d independent" % args.windows),
                        "units_per_step": units,
-                       "l2": "256 MB buffer written between timed iterations", "mean_iterations": iters_mean},
+                       "l2": "256 MB buffer written between timed iterations"},
+            "stats": {"mean_iterations": iters_mean},
             "e2e": {"value": units * args.steps / (ms_e2e * 1e-3), "unit": unit, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": args.steps,
@@ -448,7 +449,8 @@ def run_car(args):
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": WORKLOAD_DESC["car"], "runs": B, "chained_windows_per_run": W, "windows_per_step": units,
                        "l2": "256 MB buffer written between timed iterations; chain inputs (%d MB) exceed L2" % (data_all.numel() * 8 // 2 ** 20),
-                       "mean_iterations_per_window": it_mean, "windows_not_converged": nbad},
+                       },
+            "stats": {"mean_iterations_per_window": it_mean, "windows_not_converged": nbad},
             "e2e": {"value": units * args.steps / (ms_e2e * 1e-3), "unit": "windows/s",
                     "h2d_bytes_per_step": int(hU.numel() * 8 + hdata.numel() * 8), "d2h_bytes_per_step": int(h_out.numel() * 8),
                     "ms_per_step": ms_e2e / args.steps},
@@ -694,14 +696,15 @@ def run_ours(args):
                 traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
             except Exception:
                 traffic = None
-        config["mean_iterations_per_window"] = it_mean_all
-        config["converged_fraction"] = float(np.mean(st <= 1))
+        # run-dependent numbers live in "stats", not in "config": both arms print the SAME config dict
+        stats = {"mean_iterations_per_window": it_mean_all, "converged_fraction": float(np.mean(st <= 1))}
         gather_d2h = world * B * desc.nz * 8 if world > 1 else 0
         line = {
             "metric": "solved_windows_per_sec", "value": value, "unit": "windows/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev / args.steps,
             "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": config,
+            "stats": stats,
             "timing": {"method": "one CUDA-event pair around all timed steps (L2 flushes inside), max over ranks; the flushes "
                                  "alone, timed the same way, are subtracted",
                        "region_ms": ms_dev_region, "flush_ms": ms_flush, "e2e_region_ms": ms_e2e_region},
@@ -900,8 +903,9 @@ def run_long(args):
             "config": {"workload": "van der Pol MHE over a 200-epoch horizon: ONE window = 40 collocation segments (N_s = 5, 5 epochs each) "
                                    "sharing their end nodes, 402 unknowns, block-tridiagonal normal equations (41 blocks of 10) solved by "
                                    + ("block cyclic reduction" if variant == multiseg.CYCLIC else "the Riccati recursion"),
-                       "windows_per_step": B, "epochs_per_step": B * S * E, "mean_iterations_per_window": it_mean, "converged_fraction": conv,
+                       "windows_per_step": B, "epochs_per_step": B * S * E,
                        "l2": "per-iteration working set (%d MB of segment matrices and blocks) is re-written every iteration" % ((B * S * (K * n) ** 2 * 8 * 2 + B * (S + 1) * bs * bs * 16) >> 20)},
+            "stats": {"mean_iterations_per_window": it_mean, "converged_fraction": conv},
             "e2e": {"value": B * args.steps / (ms_e2e * 1e-3), "unit": "windows/s", "h2d_bytes_per_step": int(sum(t.numel() * 8 for t in h_in)),
                     "d2h_bytes_per_step": int(h_out.numel() * 8), "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": int(args.steps * (1 + it_mean * 1.3) * 4),
