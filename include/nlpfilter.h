@@ -65,6 +65,11 @@ extern "C" {
                                  factorisation failed or every step was non-finite): a failure, where
                                  opti.solve() of the reference would raise (nlp/nlp.py:82) */
 #define NLPF_STALL_GTOL 1e-6
+/* defaults of the damping schedule (nlpf_opts.lam0, lam_jump, lam_jump_indef, lam_dec_first <= 0 select them) */
+#define NLPF_LAM0 1e-12
+#define NLPF_LAM_JUMP 1e-4
+#define NLPF_LAM_JUMP_INDEF 0.1
+#define NLPF_LAM_DEC_FIRST 1000.0
 
 /* Problem class = everything the reference fixes when a script has finished calling
  * addVariables/addDynamics/addDynamicsCost/addResidualCost/addInitialCost/addVarBounds/
@@ -100,10 +105,15 @@ typedef struct nlpf_opts {
     int max_iter;                 /* total accepted steps per window */
     int max_stage_iter;           /* accepted steps per barrier stage */
     double tol_step;              /* stop when |step|_inf < tol_step (1 + |z|_inf) */
-    double lam0;                  /* initial damping */
+    double lam0;                  /* damping lam (H + lam D, D = diagonal of the Gauss-Newton part) of the first try: with the
+                                     default 1e-12 a Newton step */
     double mu0, mu_min;           /* barrier schedule (only with bounds) */
     double bound_push;            /* initial distance from a bound */
     double tau_ftb;               /* fraction to the boundary */
+    /* how the damping moves (cf. IPOPT's inertia correction: first perturbation 1e-4, growing on failure, shrinking after success) */
+    double lam_jump;              /* a step that did not decrease the merit:           lam <- max(10 lam, lam_jump) */
+    double lam_jump_indef;        /* a pivot that is not positive / a non-finite step: lam <- max(10 lam, lam_jump_indef) */
+    double lam_dec_first;         /* accepted at the first value tried: lam <- max(lam / lam_dec_first, 1e-12); after rejections lam / 10 */
 } nlpf_opts;
 
 typedef struct nlpf_problem nlpf_problem;   /* opaque */

@@ -585,6 +585,17 @@ extern "C" int nlpf_factor_solve(nlpf_problem* p, int B, const double* H, const 
     return nlpf_launch_factor_solve(p, B, H, g, lam, dz_out, info_out, (cudaStream_t)stream);
 }
 
+// damping-schedule fields <= 0 -> defaults (include/nlpfilter.h, NLPF_LAM_*; oracle/nls.py: damping_schedule)
+static nlpf_opts resolve_opts(const nlpf_problem* p, const nlpf_opts* opts) {
+    (void)p;
+    nlpf_opts o = *opts;
+    if (!(o.lam0 > 0.0)) o.lam0 = NLPF_LAM0;
+    if (!(o.lam_jump > 0.0)) o.lam_jump = NLPF_LAM_JUMP;
+    if (!(o.lam_jump_indef > 0.0)) o.lam_jump_indef = NLPF_LAM_JUMP_INDEF;
+    if (!(o.lam_dec_first > 0.0)) o.lam_dec_first = NLPF_LAM_DEC_FIRST;
+    return o;
+}
+
 // warp-per-window kernel (its own constant-H cache and work counter); W > 1 / phiDT: fused receding-horizon chains
 static bool ws_eligible(const nlpf_problem* p, const double* U, const double* xprior, const double* wshift) {
     return p->ws_variant >= 0 && !wshift && (p->d.m == 0 || U) && (!p->d.has_prior || xprior);
@@ -646,7 +657,8 @@ extern "C" int nlpf_solve_chain(nlpf_problem* p, int B, int W, double* z, const 
         nlpf_set_error("no fused chain kernel for this problem class (loop nlpf_solve + nlpf_sample instead)");
         return NLPF_E_ARG;
     }
-    return ws_dispatch(p, B, z, U_all, data_all, xprior, opts, cost_out, iters_sum_out, bad_out, W, phiDT, Z_out, (cudaStream_t)stream);
+    const nlpf_opts ro = resolve_opts(p, opts);
+    return ws_dispatch(p, B, z, U_all, data_all, xprior, &ro, cost_out, iters_sum_out, bad_out, W, phiDT, Z_out, (cudaStream_t)stream);
 }
 
 extern "C" int nlpf_solve(nlpf_problem* p, int B, double* z, const double* U, const double* data, const double* xprior,
@@ -655,6 +667,8 @@ extern "C" int nlpf_solve(nlpf_problem* p, int B, double* z, const double* U, co
     int rc = check_batch(p, B, z, data);
     if (rc) return rc;
     if (!opts || !cost_out || !iters_out || !status_out) { nlpf_set_error("null opts/output buffer"); return NLPF_E_ARG; }
+    const nlpf_opts ro = resolve_opts(p, opts);
+    opts = &ro;
     if (ws_eligible(p, U, xprior, wshift))
         return ws_dispatch(p, B, z, U, data, const_cast<double*>(xprior), opts, cost_out, iters_out, status_out, 1, nullptr, nullptr,
                            (cudaStream_t)stream);

@@ -1385,7 +1385,9 @@ VN(solve_kernel)(const __grid_constant__ DevProb P, int B, double* __restrict__ 
                     bool accepted = false, at_floor = false;
                     bool h_valid = true;      // Hp still holds H(z)
                     double alpha = 1.0, Jt = J, mt = merit, dzmax = 0.0, nset = 0.0;
+                    const double lam_it0 = lam;
                     while (lam <= 1e18) {
+                        bool tried = false;   // a trial point was evaluated (else: pivot not positive / step not finite)
                         if (!h_valid) {       // the factorisation overwrote H: rebuild it at z
                             double Jd, md, nd;
                             eval_window_cold(P, sm, zs, wp, mu, Jd, md, nd, hmode);
@@ -1430,6 +1432,7 @@ VN(solve_kernel)(const __grid_constant__ DevProb P, int B, double* __restrict__ 
                                 // FULL evaluation at the trial point: an accepted step (the usual case) needs H and g
                                 // there anyway; a rejected one rebuilds H at z below, as it had to before
                                 eval_window<true>(P, sm, zt, wp, mu, Jt, mt, nset, hmode);
+                                tried = true;
                                 if (isfinite(mt) && mt < merit) {
                                     accepted = true;
                                     alpha = a;
@@ -1448,7 +1451,7 @@ VN(solve_kernel)(const __grid_constant__ DevProb P, int B, double* __restrict__ 
                                 }
                             }
                         }
-                        lam *= 10.0;
+                        lam = fmax(10.0 * lam, tried ? opt.lam_jump : opt.lam_jump_indef);
                     }
                     if (!accepted) {
                         status = NLPF_ST_STALLED;
@@ -1482,7 +1485,7 @@ VN(solve_kernel)(const __grid_constant__ DevProb P, int B, double* __restrict__ 
                         zm = fmax(zm, fabs(zt[i]));
                     }
                     zm = block_max(zm, red);
-                    lam = fmax(lam / 10.0, 1e-12);
+                    lam = fmax(lam / ((lam <= lam_it0) ? opt.lam_dec_first : 10.0), 1e-12);
                     ++iters;
                     ++stage_steps;
                     J = Jt;               // H, g, dd already belong to the accepted point

@@ -1499,7 +1499,7 @@ wsolve_kernel(const __grid_constant__ DevProb P, int B, double* __restrict__ z_i
         enum { PC_STAGE_INIT, PC_ITER_TOP, PC_LAM_TOP, PC_SOLVE, PC_AFTER_TRIAL, PC_STALL_CHECK, PC_STAGE_END };
         double mu = BND ? opt.mu0 : 0.0;
         int iters = 0, status = NLPF_ST_MAXITER, stage_steps = 0, floor_steps = 0;
-        double lam = opt.lam0, J = 0.0, merit = 0.0, nse0 = 0.0;
+        double lam = opt.lam0, lam_it0 = opt.lam0, J = 0.0, merit = 0.0, nse0 = 0.0;
         double Jt = 0.0, mt = 0.0, nset = 0.0, dzmax = 0.0, alpha = 1.0, pred = 0.0, dm = 0.0;
         bool h_valid = true;
         int ev = EV_FIRST;
@@ -1537,6 +1537,7 @@ wsolve_kernel(const __grid_constant__ DevProb P, int B, double* __restrict__ z_i
                         if (mu > opt.mu_min && stage_steps >= 1 && gm < 10.0 * mu) { status = NLPF_ST_CONVERGED; pc = PC_STAGE_END; continue; }
                     }
                     h_valid = true;
+                    lam_it0 = lam;
                     pc = PC_LAM_TOP;
                 } else if (pc == PC_LAM_TOP) {
                     if (!(lam <= 1e18)) {   // no acceptable step
@@ -1591,7 +1592,7 @@ wsolve_kernel(const __grid_constant__ DevProb P, int B, double* __restrict__ z_i
                             continue;
                         }
                     }
-                    lam *= 10.0;
+                    lam = fmax(10.0 * lam, opt.lam_jump_indef);     // pivot not positive or step not finite
                     pc = PC_LAM_TOP;
                 } else if (pc == PC_AFTER_TRIAL) {
                     bool accepted = false, at_floor = false;
@@ -1600,7 +1601,7 @@ wsolve_kernel(const __grid_constant__ DevProb P, int B, double* __restrict__ z_i
                         const double nb = nse0 + nset;
                         if (isfinite(mt) && (mt - merit) <= nb && pred <= 4.0 * nb) { accepted = true; at_floor = true; }
                     }
-                    if (!accepted) { lam *= 10.0; pc = PC_LAM_TOP; continue; }
+                    if (!accepted) { lam = fmax(10.0 * lam, opt.lam_jump); pc = PC_LAM_TOP; continue; }
                     const double step = alpha * dzmax;
                     double zm = 0.0;
                     for (int i = lane; i < NZ; i += 32) {
@@ -1608,7 +1609,7 @@ wsolve_kernel(const __grid_constant__ DevProb P, int B, double* __restrict__ z_i
                         zm = fmax(zm, fabs(zt[i]));
                     }
                     zm = wmax(zm);
-                    lam = fmax(lam / 10.0, 1e-12);
+                    lam = fmax(lam / ((lam <= lam_it0) ? opt.lam_dec_first : 10.0), 1e-12);
                     ++iters;
                     ++stage_steps;
                     J = Jt;             // H, g, dd already belong to the accepted point

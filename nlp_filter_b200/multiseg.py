@@ -104,7 +104,7 @@ class MultiSegmentProblem(object):
         data = self._sub(data, B, max(d.Ldata, 1))
         xp = None if xprior is None else engine._f8(xprior, (B, self.n))
         cur, tri = self._buffers(B), self._buffers(B)
-        lam = torch.full((B,), o.lam0, dtype=torch.float64, device="cuda")
+        lam = torch.full((B,), o.lam0 if o.lam0 > 0.0 else 1e-3, dtype=torch.float64, device="cuda")   # exact-Hessian class (nlpf_opts.lam0)
         iters = torch.zeros((B,), dtype=torch.int32, device="cuda")
         status = torch.full((B,), 2, dtype=torch.int32, device="cuda")
         active = torch.ones((B,), dtype=torch.bool, device="cuda")
@@ -141,7 +141,7 @@ class MultiSegmentProblem(object):
             # their first-order noise bound; nlpf_assemble does not report that bound, 1e-10 |J| stands in for it)
             floor = ok & ~acc & small & ((tri["J"] - cur["J"]) <= 1e-10 * cur["J"].abs())
             conv = (acc & small) | floor
-            lam.copy_(torch.where(acc, torch.clamp(lam / 10.0, min=1e-12), torch.where(rej, lam * 10.0, lam)))
+            lam.copy_(torch.where(acc, torch.clamp(lam / 10.0, min=1e-12), torch.where(rej, torch.clamp(lam * 10.0, min=1e-4), lam)))
             iters += acc.to(torch.int32)
             stalled = rej & ~floor & (lam > 1e18)
             status[conv] = 0

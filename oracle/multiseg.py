@@ -33,7 +33,7 @@ def evaluate(seg, S, z, U, data, pinv=None, xprior=None):
 
 def solve(seg, S, z0, U, data, pinv=None, xprior=None, tol_step=1e-9, lam0=1e-3, max_iter=300):
     """Damped Gauss-Newton on the dense system (the decisions of oracle/nls.py: accept on decrease, lam / 10, else
-    lam * 10; stop on the step)."""
+    max(10 lam, 1e-4); stop on the step)."""
     z = np.array(z0, dtype=float)
     lam, iters = lam0, 0
     J, g, H = evaluate(seg, S, z, U, data, pinv, xprior)
@@ -45,14 +45,14 @@ def solve(seg, S, z0, U, data, pinv=None, xprior=None, tol_step=1e-9, lam0=1e-3,
                 L = np.linalg.cholesky(A)
                 dz = np.linalg.solve(L.T, np.linalg.solve(L, g))
             except np.linalg.LinAlgError:
-                lam *= 10.0
+                lam = max(10.0 * lam, 1e-4)
                 continue
             zt = z - dz
             Jt, gt, Ht = evaluate(seg, S, zt, U, data, pinv, xprior)
             if np.isfinite(Jt) and Jt < J:
                 accepted = True
                 break
-            lam *= 10.0
+            lam = max(10.0 * lam, 1e-4)
         if not accepted:
             return z, dict(J=J, iters=iters, status=4)
         step = float(np.max(np.abs(dz)))

@@ -36,6 +36,20 @@ ST_STALLED = 1          # no damping value produced a decrease (rounding-level s
 ST_MAXITER = 2
 ST_NUMERIC = 3          # non-finite cost at the starting point
 ST_NOSTEP = 4           # no damping value produced a decrease at a NON-stationary point (failure)
+# defaults of the damping schedule (include/nlpfilter.h, NLPF_LAM_*; nlpf_opts fields <= 0 select them)
+LAM0 = 1e-12
+LAM_JUMP = 1e-4         # a step that did not decrease the merit: lam <- max(10 lam, lam_jump)
+LAM_JUMP_INDEF = 0.1    # a pivot that is not positive or a non-finite step: lam <- max(10 lam, lam_jump_indef)
+LAM_DEC_FIRST = 1000.0  # accepted at the first damping value tried: lam / lam_dec_first (floor 1e-12); after rejections: lam / 10
+
+
+def damping_schedule(opts):
+    """(lam0, lam_jump, lam_jump_indef, lam_dec_first) with the defaults filled in."""
+    pick = lambda v, dflt: v if v > 0.0 else dflt
+    return (pick(opts.lam0, LAM0), pick(opts.lam_jump, LAM_JUMP), pick(opts.lam_jump_indef, LAM_JUMP_INDEF),
+            pick(opts.lam_dec_first, LAM_DEC_FIRST))
+
+
 STALL_GTOL = 1e-6       # stalled counts as stationary when max |g_i| / H_ii < STALL_GTOL (1 + |z|_inf)
 
 
@@ -355,12 +369,13 @@ def solve(desc, win, z0, opts=None):
     mu = opts.mu0 if bounded else 0.0
     iters = 0
     status = ST_MAXITER
-    lam = opts.lam0
+    lam0, lam_jump, lam_jump_indef, lam_dec_first = damping_schedule(opts)
+    lam = lam0
     J, merit, g, H, nz0 = evaluate(desc, win, z, mu, with_noise=True)
     if not np.isfinite(merit):
         return z, dict(J=J, iters=0, status=ST_NUMERIC, lam=lam, mu=mu)
     while True:
-        lam = opts.lam0
+        lam = lam0
         stage_steps = 0
         floor_steps = 0
         status = ST_MAXITER
@@ -370,6 +385,7 @@ def solve(desc, win, z0, opts=None):
                 break
             accepted = False
             floor = False
+            lam_it0 = lam
             dg = np.diag(H).copy()                 # damping uses the (positive) Gauss-Newton diagonal
             dg = dg + 1e-14 * np.max(dg)
             Hn = H + second_order(desc, win, z)    # exact Hessian where the model provides it
@@ -395,7 +411,7 @@ def solve(desc, win, z0, opts=None):
                         floor = True      # accept: the Gauss-Newton step is still accurate (g is)
                         accepted = True
                         break
-                lam *= 10.0
+                lam = max(10.0 * lam, lam_jump if ok else lam_jump_indef)
             if not accepted:
                 status = ST_STALLED
                 with np.errstate(all="ignore"):
@@ -405,7 +421,7 @@ def solve(desc, win, z0, opts=None):
                 break
             step = a * float(np.max(np.abs(dz)))
             z = zt
-            lam = max(lam / 10.0, 1e-12)
+            lam = max(lam / (lam_dec_first if lam <= lam_it0 else 10.0), 1e-12)
             iters += 1
             stage_steps += 1
             J, merit, g, H, nz0 = evaluate(desc, win, z, mu, with_noise=True)

