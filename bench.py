@@ -354,16 +354,30 @@ def _cpu_car_chain(b):
     xp = ch["xhat0"][b].copy()
     it = 0
     for w in range(ch["data"].shape[0]):
-        z, info = nls.solve(d, nls.Window(d, U=ch["U"][w, b], data=ch["data"][w, b], xprior=xp), z)
+        z, info = nls.solve(d, nls.Window(d, U=ch["U"][w, b], data=ch["data"][w, b], xprior=xp), z, _CPU["opts"].for_window(w))
         xp = (ch["PhiDT"] @ z.reshape(d.K, d.nv))[0]
         it += info["iters"]
     return it
 
 
-def cpu_car_windows_per_sec(runs, windows, cores):
+def car_opts(args):
+    from nlp_filter_b200.desc import SolveOpts
+    return SolveOpts(mu0_warm=args.mu0_warm)
+
+
+def car_config(args, B, W):
+    from nlp_filter_b200 import shapes
+    d = shapes.car()
+    return {"workload": WORKLOAD_DESC["car"], "runs": B, "chained_windows_per_run": W, "windows_per_step": B * W,
+            "solver": "log barrier from mu0 = 0.1 in the first window of a run, from mu0_warm = %g in the warm-started windows after it "
+                      "(nlpf_opts.mu0_warm; 0 = 0.1 everywhere, as IPOPT's default mu_init)" % args.mu0_warm,
+            "l2": "256 MB buffer written between timed iterations; chain inputs (%d MB) exceed L2" % (W * B * d.Ldata * 8 // 2 ** 20)}
+
+
+def cpu_car_windows_per_sec(runs, windows, cores, opts):
     from nlp_filter_b200 import shapes, synth
     d = shapes.car()
-    _CPU["d"], _CPU["ch"] = d, synth.car_chain_batch(d, runs, windows, seed=4000)
+    _CPU["d"], _CPU["ch"], _CPU["opts"] = d, synth.car_chain_batch(d, runs, windows, seed=4000), opts
     ctx = mp.get_context("fork")
     with ctx.Pool(cores) as pool:
         t0 = time.perf_counter()
@@ -386,7 +400,7 @@ def run_car(args):
     cpu_base = None
     if not args.no_cpu_baseline:
         runs, wins = (args.cpu_windows or 2 * cores), 3
-        v, it = cpu_car_windows_per_sec(runs, wins, cores)
+        v, it = cpu_car_windows_per_sec(runs, wins, cores, car_opts(args))
         cpu_base = {"value": v, "unit": "windows/s", "cores": cores, "kind": "port",
                     "sample": "%d runs x %d chained windows of the same synthetic workload, NumPy restatement oracle/nls.py, "
                               "%d-process pool, mean %.1f iterations/window" % (runs, wins, cores, it)}
@@ -408,11 +422,12 @@ def run_car(args):
     flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device="cuda")
     peak_fp64 = engine.fp64_peak_tflops()
     stats = {}
+    opts = car_opts(args)
 
     def step_device():
         z.zero_()
         xp.copy_(xh0)
-        stats["it"], stats["bad"] = engine.solve_chain(prob, z, U_all, data_all, xp, ch["PhiDT"])
+        stats["it"], stats["bad"] = engine.solve_chain(prob, z, U_all, data_all, xp, ch["PhiDT"], opts=opts)
 
     def step_e2e():
         U_all.copy_(hU, non_blocking=True)
@@ -447,9 +462,7 @@ def run_car(args):
     line = {"metric": "solved_windows_per_sec", "value": units * args.steps / (ms_dev * 1e-3), "unit": "windows/s", "n_gpus": 1,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": WORKLOAD_DESC["car"], "runs": B, "chained_windows_per_run": W, "windows_per_step": units,
-                       "l2": "256 MB buffer written between timed iterations; chain inputs (%d MB) exceed L2" % (data_all.numel() * 8 // 2 ** 20),
-                       },
+            "config": car_config(args, B, W),
             "stats": {"mean_iterations_per_window": it_mean, "windows_not_converged": nbad},
             "e2e": {"value": units * args.steps / (ms_e2e * 1e-3), "unit": "windows/s",
                     "h2d_bytes_per_step": int(hU.numel() * 8 + hdata.numel() * 8), "d2h_bytes_per_step": int(h_out.numel() * 8),
@@ -481,7 +494,7 @@ def run_reference(args):
     for s in range(args.warmup + args.steps):
         t0 = time.perf_counter()
         if args.workload == "car":
-            v, it = cpu_car_windows_per_sec(2 * cores, 3, cores)
+            v, it = cpu_car_windows_per_sec(2 * cores, 3, cores, car_opts(args))
             n = 2 * cores * 3
         elif args.workload in ("ekf", "ls"):
             v, it = cpu_aux_per_sec(args.workload, n, cores), 0.0
@@ -493,7 +506,7 @@ def run_reference(args):
     if args.workload in ("vdp", "gnss", "2rx", "rc", "mrx"):
         _, config = shared_config(args, world)
     elif args.workload == "car":
-        config = {"workload": WORKLOAD_DESC["car"], "runs": 2048, "chained_windows_per_run": args.chain, "windows_per_step": 2048 * args.chain}
+        config = car_config(args, args.windows if args.windows != 4096 else 2048, args.chain)
     else:
         config = {"workload": WORKLOAD_DESC[args.workload]}
     line = {
@@ -928,6 +941,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="vdp", choices=["vdp", "gnss", "2rx", "car", "ekf", "ls",
                                                           "assemble-vdp", "assemble-gnss", "assemble-car", "vdp-long", "rc", "mrx"])
+    ap.add_argument("--mu0-warm", type=float, default=1e-6, help="car workload: barrier parameter at which the warm-started windows 2.. of a run start (0: mu0)")
     ap.add_argument("--chain", type=int, default=200, help="chained windows per run (car workload; BASELINE configs[3]: horizon 200)")
     ap.add_argument("--windows", type=int, default=4096, help="windows per GPU per step")
     ap.add_argument("--cpu-windows", type=int, default=0, help="size of the CPU-path sample")

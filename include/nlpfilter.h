@@ -114,6 +114,8 @@ typedef struct nlpf_opts {
     double lam_jump;              /* a step that did not decrease the merit:           lam <- max(10 lam, lam_jump) */
     double lam_jump_indef;        /* a pivot that is not positive / a non-finite step: lam <- max(10 lam, lam_jump_indef) */
     double lam_dec_first;         /* accepted at the first value tried: lam <- max(lam / lam_dec_first, 1e-12); after rejections lam / 10 */
+    double mu0_warm;              /* nlpf_solve_chain: barrier parameter at which windows 2.. of a run start (they are warm-started from
+                                     the previous window; cf. IPOPT warm_start_init_point + mu_init); <= 0: mu0 for every window */
 } nlpf_opts;
 
 typedef struct nlpf_problem nlpf_problem;   /* opaque */

@@ -36,7 +36,8 @@ class COpts(ctypes.Structure):
     _fields_ = [("max_iter", ctypes.c_int), ("max_stage_iter", ctypes.c_int), ("tol_step", ctypes.c_double),
                 ("lam0", ctypes.c_double), ("mu0", ctypes.c_double), ("mu_min", ctypes.c_double),
                 ("bound_push", ctypes.c_double), ("tau_ftb", ctypes.c_double),
-                ("lam_jump", ctypes.c_double), ("lam_jump_indef", ctypes.c_double), ("lam_dec_first", ctypes.c_double)]
+                ("lam_jump", ctypes.c_double), ("lam_jump_indef", ctypes.c_double), ("lam_dec_first", ctypes.c_double),
+                ("mu0_warm", ctypes.c_double)]
 
 
 EXPORTS = ("nlpf_version", "nlpf_last_error", "nlpf_device_count", "nlpf_problem_create",
@@ -146,4 +147,5 @@ def make_copts(o):
     c.tol_step, c.lam0, c.mu0, c.mu_min = o.tol_step, o.lam0, o.mu0, o.mu_min
     c.bound_push, c.tau_ftb = o.bound_push, o.tau_ftb
     c.lam_jump, c.lam_jump_indef, c.lam_dec_first = o.lam_jump, o.lam_jump_indef, o.lam_dec_first
+    c.mu0_warm = o.mu0_warm
     return c

@@ -1497,7 +1497,7 @@ wsolve_kernel(const __grid_constant__ DevProb P, int B, double* __restrict__ z_i
         //                                                       rejected step (the factorisation overwrote H)
         enum { EV_FIRST, EV_STAGE, EV_TRIAL, EV_RESTORE, EV_STALL };
         enum { PC_STAGE_INIT, PC_ITER_TOP, PC_LAM_TOP, PC_SOLVE, PC_AFTER_TRIAL, PC_STALL_CHECK, PC_STAGE_END };
-        double mu = BND ? opt.mu0 : 0.0;
+        double mu = BND ? ((w > 0 && opt.mu0_warm > 0.0) ? opt.mu0_warm : opt.mu0) : 0.0;   // windows 2.. of a chain are warm-started
         int iters = 0, status = NLPF_ST_MAXITER, stage_steps = 0, floor_steps = 0;
         double lam = opt.lam0, lam_it0 = opt.lam0, J = 0.0, merit = 0.0, nse0 = 0.0;
         double Jt = 0.0, mt = 0.0, nset = 0.0, dzmax = 0.0, alpha = 1.0, pred = 0.0, dm = 0.0;

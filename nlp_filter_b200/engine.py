@@ -335,7 +335,7 @@ def solve_chain(prob, z, U_all, data_all, xprior, PhiDT, opts=None, keep=False):
         it_sum, bad = it32.to(torch.int64), bad32.to(torch.int64)
         return (it_sum, bad, Z) if keep else (it_sum, bad)
     for w in range(W):
-        prob.solve(z, None if U_all is None else U_all[w], data_all[w], xprior, None, opts, out=(cost, iters, status))
+        prob.solve(z, None if U_all is None else U_all[w], data_all[w], xprior, None, (opts or SolveOpts()).for_window(w), out=(cost, iters, status))
         xprior.copy_(prob.sample(z, PhiDT)[:, 0, :])
         it_sum += iters
         bad += (status > 1)

@@ -104,22 +104,27 @@ def test_256_filters_64_steps_against_oracle_subset():
         assert np.max(np.abs(S_.cpu().numpy()[b] - Sref)) < 1e-9
 
 
-def test_vehicle_chains_against_oracle_and_truth():
+@pytest.mark.parametrize("mu0_warm", [0.0, 1e-6])
+def test_vehicle_chains_against_oracle_and_truth(mu0_warm):
     """Synthetic receding-horizon vehicle chains (autonomous-car.py:232-288 pattern): device-side chain
-    driver vs the oracle run through the same chain, and estimates close to the simulated truth."""
+    driver vs the oracle run through the same chain, and estimates close to the simulated truth.  mu0_warm: the
+    warm-started windows 2.. start the barrier there (nlpf_opts.mu0_warm; 0 = at mu0 like the first window)."""
     import torch
     from nlp_filter_b200 import engine
     from oracle import nls
     d = shapes.car()
+    opts = D.SolveOpts(mu0_warm=mu0_warm)
     B, W = 64, 5
     ch = synth.car_chain_batch(d, B, W, seed=11)
     prob = engine.WindowProblem(d)
     dev = lambda a: torch.as_tensor(np.ascontiguousarray(a)).cuda()
     z = torch.zeros((B, d.nz), dtype=torch.float64, device="cuda")
     xp = dev(ch["xhat0"])
-    it_sum, bad, Z = engine.solve_chain(prob, z, dev(ch["U"]), dev(ch["data"]), xp, ch["PhiDT"], keep=True)
+    it_sum, bad, Z = engine.solve_chain(prob, z, dev(ch["U"]), dev(ch["data"]), xp, ch["PhiDT"], opts=opts, keep=True)
     torch.cuda.synchronize()
     assert int(bad.sum()) == 0
+    if mu0_warm > 0.0:
+        assert float(it_sum.sum()) / (B * W) < 12.0          # (the full barrier schedule per window: 14-15)
     Z = Z.cpu().numpy()
     V = Z[-1].reshape(B, d.K, d.nv)
     assert np.median(np.linalg.norm(V[:, 0, :2] - ch["truth"][-1][:, :2], axis=1)) < 1.5      # metres, GNSS noise level
@@ -127,7 +132,7 @@ def test_vehicle_chains_against_oracle_and_truth():
         zo = np.zeros(d.nz)
         xpo = ch["xhat0"][b].copy()
         for w in range(W):
-            zo, info = nls.solve(d, nls.Window(d, U=ch["U"][w, b], data=ch["data"][w, b], xprior=xpo), zo)
+            zo, info = nls.solve(d, nls.Window(d, U=ch["U"][w, b], data=ch["data"][w, b], xprior=xpo), zo, opts.for_window(w))
             xpo = (ch["PhiDT"] @ zo.reshape(d.K, d.nv))[0]
             Vg, Vo = Z[w, b].reshape(d.K, d.nv), zo.reshape(d.K, d.nv)
             assert np.max(np.abs(Vg[:, [0, 1, 8]] - Vo[:, [0, 1, 8]])) < 1e-3                  # positions within 1 mm
@@ -135,7 +140,8 @@ def test_vehicle_chains_against_oracle_and_truth():
     prob.close()
 
 
-def test_fused_chain_kernel_equals_the_per_window_loop(monkeypatch):
+@pytest.mark.parametrize("mu0_warm", [0.0, 1e-6])
+def test_fused_chain_kernel_equals_the_per_window_loop(monkeypatch, mu0_warm):
     """nlpf_solve_chain (every run's windows back to back in one warp) against the host loop of
     nlpf_solve + nlpf_sample launches it replaces: same kernel code per window, so identical results."""
     import os
@@ -158,7 +164,8 @@ def test_fused_chain_kernel_equals_the_per_window_loop(monkeypatch):
                 monkeypatch.delenv("NLPF_CHAIN_LOOP", raising=False)
             z = torch.zeros((B, d.nz), dtype=torch.float64, device="cuda")
             xp = dev(ch["xhat0"])
-            it_sum, bad, Z = engine.solve_chain(prob, z, dev(ch["U"]), dev(ch["data"]), xp, ch["PhiDT"], keep=True)
+            it_sum, bad, Z = engine.solve_chain(prob, z, dev(ch["U"]), dev(ch["data"]), xp, ch["PhiDT"],
+                                                opts=D.SolveOpts(mu0_warm=mu0_warm), keep=True)
             torch.cuda.synchronize()
             out.append((it_sum.cpu().numpy(), bad.cpu().numpy(), Z.cpu().numpy(), z.cpu().numpy(), xp.cpu().numpy()))
         f, l = out
@@ -219,7 +226,8 @@ def test_2048_vehicle_runs_of_200_windows():
     z = torch.zeros((B, d.nz), dtype=torch.float64, device="cuda")
     xp = dev(ch["xhat0"])
     U_d, data_d = dev(ch["U"]), dev(ch["data"])
-    it_sum, bad, Z = engine.solve_chain(prob, z, U_d, data_d, xp, ch["PhiDT"], keep=True)
+    opts = D.SolveOpts(mu0_warm=1e-6)                            # what bench.py --workload car runs with
+    it_sum, bad, Z = engine.solve_chain(prob, z, U_d, data_d, xp, ch["PhiDT"], opts=opts, keep=True)
     torch.cuda.synchronize()
     Z = Z.cpu().numpy()
     bad = bad.cpu().numpy()
@@ -232,10 +240,10 @@ def test_2048_vehicle_runs_of_200_windows():
     assert np.median(err) < 1.5 and np.max(err[20:]) < 50.0, (np.median(err), np.max(err[20:]))
     PhiDT = ch["PhiDT"]
 
-    def oracle_window(w, b, opts=None):
+    def oracle_window(w, b):
         zprev = Z[w - 1, b] if w > 0 else np.zeros(d.nz)
         xpo = (PhiDT @ zprev.reshape(d.K, d.nv))[0] if w > 0 else ch["xhat0"][b]
-        return nls.solve(d, nls.Window(d, U=ch["U"][w, b], data=ch["data"][w, b], xprior=xpo), zprev, opts)
+        return nls.solve(d, nls.Window(d, U=ch["U"][w, b], data=ch["data"][w, b], xprior=xpo), zprev, opts.for_window(w))
 
     rng = np.random.default_rng(3)
     for w, b in zip(rng.integers(0, W, 10), rng.integers(0, B, 10)):
@@ -249,7 +257,10 @@ def test_2048_vehicle_runs_of_200_windows():
     for b in np.nonzero(bad)[0][:4]:
         zs = np.concatenate([np.zeros((1, d.nz)), Z[:-1, b]], 0)
         xps = np.concatenate([ch["xhat0"][b][None], (zs[1:].reshape(W - 1, d.K, d.nv)[:, :, :] * PhiDT[0][None, :, None]).sum(1)], 0)
-        zz, J, iters, status = engine.solve_windows_host(prob, zs, ch["U"][:, b], ch["data"][:, b], xps)
+        # (windows 1.. in one batch with the warm-start options; window 0 of a run, the cold one, is not replayed)
+        zz, J, iters, status = engine.solve_windows_host(prob, zs[1:], ch["U"][1:, b], ch["data"][1:, b], xps[1:], opts=opts.for_window(1))
+        zz = np.concatenate([Z[:1, b], zz], 0)
+        iters, status = np.concatenate([[0], iters]), np.concatenate([[0], status])
         ws = np.nonzero(status > 1)[0]
         good = status <= 1
         # replay of the converged windows.  The arrival cost is re-sampled on the host (differences of 1e-12); most
