@@ -1427,8 +1427,23 @@ VN(solve_kernel)(const __grid_constant__ DevProb P, int B, double* __restrict__ 
                             }
                             pred *= a;
                             if (finite == 0.0) {
-                                for (int i = tid; i < nz; i += NLPF_NT) zt[i] = fma(-a, dz[i], zs[i]);
-                                __syncthreads();
+                                double ztm = 0.0;
+                                for (int i = tid; i < nz; i += NLPF_NT) {
+                                    const double v = fma(-a, dz[i], zs[i]);
+                                    zt[i] = v;
+                                    ztm = fmax(ztm, fabs(v));
+                                }
+                                ztm = block_max(ztm, red);          // (ends with a barrier: zt is visible)
+                                // a first-try step below the tolerance ends the stage without an evaluation at the new
+                                // point: the merit cannot resolve such a step, and H, g there would not be used.  J stays
+                                // the value at the previous iterate (it differs by O(step^2)).
+                                if (lam <= lam_it0 && a * dmx < opt.tol_step * (1.0 + ztm)) {
+                                    accepted = true;
+                                    alpha = a;
+                                    dzmax = dmx;
+                                    nset = nse0;                    // (Jt, mt still hold J, merit)
+                                    break;
+                                }
                                 // FULL evaluation at the trial point: an accepted step (the usual case) needs H and g
                                 // there anyway; a rejected one rebuilds H at z below, as it had to before
                                 eval_window<true>(P, sm, zt, wp, mu, Jt, mt, nset, hmode);

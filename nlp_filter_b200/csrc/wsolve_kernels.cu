@@ -1580,8 +1580,26 @@ wsolve_kernel(const __grid_constant__ DevProb P, int B, double* __restrict__ z_i
                         fin = wmax(fin);
                         pr = a * wsum(pr);
                         if (fin == 0.0) {
-                            for (int i = lane; i < NZ; i += 32) zt[i] = fma(-a, dz[i], zs[i]);
+                            double ztm = 0.0;
+                            for (int i = lane; i < NZ; i += 32) {
+                                const double v = fma(-a, dz[i], zs[i]);
+                                zt[i] = v;
+                                ztm = fmax(ztm, fabs(v));
+                            }
+                            ztm = wmax(ztm);
                             __syncwarp();
+                            // a first-try step below the tolerance ends the stage without an evaluation at the new point:
+                            // the merit cannot resolve such a step (the rounding-bound rule would accept it), and H, g
+                            // there would not be used.  J stays the value at the previous iterate (it differs by O(step^2)).
+                            if (lam <= lam_it0 && a * dmx < opt.tol_step * (1.0 + ztm)) {
+                                for (int i = lane; i < NZ; i += 32) zs[i] = zt[i];
+                                __syncwarp();
+                                ++iters;
+                                ++stage_steps;
+                                status = NLPF_ST_CONVERGED;
+                                pc = PC_STAGE_END;
+                                continue;
+                            }
                             // FULL evaluation at the trial point: an accepted step (the usual case) needs H and g
                             // there anyway, so a cost-only pass would be paid on top (VDP +7 %, GNSS +20 %)
                             alpha = a;

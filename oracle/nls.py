@@ -385,6 +385,7 @@ def solve(desc, win, z0, opts=None):
                 break
             accepted = False
             floor = False
+            small = False
             lam_it0 = lam
             dg = np.diag(H).copy()                 # damping uses the (positive) Gauss-Newton diagonal
             dg = dg + 1e-14 * np.max(dg)
@@ -399,6 +400,12 @@ def solve(desc, win, z0, opts=None):
                 if ok:
                     a = _max_step(desc, z, dz, opts.tau_ftb) if bounded else 1.0
                     zt = z + a * dz
+                    # a first-try step below the tolerance ends the stage without an evaluation at the new point (the
+                    # merit cannot resolve such a step); J stays the value at the previous iterate
+                    if lam <= lam_it0 and a * float(np.max(np.abs(dz))) < opts.tol_step * (1.0 + float(np.max(np.abs(zt)))):
+                        small = True
+                        accepted = True
+                        break
                     Jt, mt, _, _, nzt = evaluate(desc, win, zt, mu, want_grad=False, with_noise=True)
                     if np.isfinite(mt) and mt < merit:
                         accepted = True
@@ -421,6 +428,11 @@ def solve(desc, win, z0, opts=None):
                 break
             step = a * float(np.max(np.abs(dz)))
             z = zt
+            if small:
+                iters += 1
+                stage_steps += 1
+                status = ST_CONVERGED
+                break
             lam = max(lam / (lam_dec_first if lam <= lam_it0 else 10.0), 1e-12)
             iters += 1
             stage_steps += 1
