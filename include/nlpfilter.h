@@ -104,7 +104,8 @@ typedef struct nlpf_desc {
 typedef struct nlpf_opts {
     int max_iter;                 /* total accepted steps per window */
     int max_stage_iter;           /* accepted steps per barrier stage */
-    double tol_step;              /* stop when |step|_inf < tol_step (1 + |z|_inf) */
+    double tol_step;              /* stop when |step|_inf < tol_step (1 + |z|_inf); such a step, when it is the first one tried in
+                                     its iteration, is applied without evaluating the objective at the new point */
     double lam0;                  /* damping lam (H + lam D, D = diagonal of the Gauss-Newton part) of the first try: with the
                                      default 1e-12 a Newton step */
     double mu0, mu_min;           /* barrier schedule (only with bounds) */
@@ -149,7 +150,8 @@ int nlpf_factor_solve(nlpf_problem* p, int B, const double* H, const double* g, 
 /* Whole solve of B independent windows, one CTA per window, iterating on chip.
  * replaces: NLP.solve(), nlp/nlp.py:76-83 (opti.solve() -> CasADi -> IPOPT -> MUMPS).
  *   z_inout[B*nz] initial guess in, minimiser out;
- *   cost_out[B] objective J; iters_out[B]; status_out[B] NLPF_ST_* */
+ *   cost_out[B] objective J at the last evaluated iterate (a final step below tol_step changes it by O(step^2) and is not
+ *   re-evaluated); iters_out[B]; status_out[B] NLPF_ST_* */
 int nlpf_solve(nlpf_problem* p, int B, double* z_inout, const double* U, const double* data,
                const double* xprior, const double* wshift, const nlpf_opts* opts,
                double* cost_out, int* iters_out, int* status_out, void* stream);
