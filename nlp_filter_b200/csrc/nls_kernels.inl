@@ -929,8 +929,12 @@ __device__ void eval_window(const DevProb& P, double* sm, const double* zc, cons
                     const double x0 = zc[o + c0], x1 = zc[o + c1];
                     const double l0 = lw[k * n + 0];
                     const int rhi = o + max(c0, c1), rlo = o + min(c0, c1);
-                    Hp[pk(rhi, rlo)] += l0 * 2.0 * x1;
-                    Hp[pk(o + c1, o + c1)] += l0 * 2.0 * x0;
+                    const double s01 = l0 * 2.0 * x1, s11 = l0 * 2.0 * x0;
+                    // safeguard: the node's block is scaled back until the Gauss-Newton diagonal dominates its rows
+                    // (Gershgorin; t = 1 near the solution, where lw is small) -- keeps H definite away from it
+                    const double t = fmin(1.0, fmin(Hp[pk(o + c0, o + c0)] / fabs(s01), Hp[pk(o + c1, o + c1)] / (fabs(s01) + fabs(s11))));
+                    Hp[pk(rhi, rlo)] += t * s01;
+                    Hp[pk(o + c1, o + c1)] += t * s11;
                 } else {
                     // f0 = v cos th, f1 = v sin th, th = x[2]
                     const int c2 = P.cmap[2];
@@ -938,7 +942,8 @@ __device__ void eval_window(const DevProb& P, double* sm, const double* zc, cons
                     const double v = 8.72649116358 * u0 - 0.856053299155;
                     double s2, c2v;
                     sincos(zc[o + c2], &s2, &c2v);
-                    Hp[pk(o + c2, o + c2)] += lw[k * n + 0] * v * c2v + lw[k * n + 1] * v * s2;
+                    const double s22 = lw[k * n + 0] * v * c2v + lw[k * n + 1] * v * s2;
+                    Hp[pk(o + c2, o + c2)] += fmin(1.0, Hp[pk(o + c2, o + c2)] / fabs(s22)) * s22;      // same safeguard
                 }
             }
         }

@@ -857,8 +857,12 @@ __device__ __forceinline__ void ws_eval(const DevProb& P, double* sm, const WsCo
             __syncwarp();
             for (int k = lane; k < K; k += 32) {           // hess f0 = [[0, -2 x1], [-2 x1, -2 x0]]
                 const double x0 = zc[k * N], x1 = zc[k * N + 1], l0 = lw[k * N];
-                Hp[pk(k * N + 1, k * N)] += l0 * 2.0 * x1;
-                Hp[pk(k * N + 1, k * N + 1)] += l0 * 2.0 * x0;
+                const double s01 = l0 * 2.0 * x1, s11 = l0 * 2.0 * x0;
+                // safeguard: the node's block is scaled back until the Gauss-Newton diagonal dominates its rows
+                // (Gershgorin; t = 1 near the solution, where lw is small) -- keeps H definite away from it
+                const double t = fmin(1.0, fmin(Hp[pk(k * N, k * N)] / fabs(s01), Hp[pk(k * N + 1, k * N + 1)] / (fabs(s01) + fabs(s11))));
+                Hp[pk(k * N + 1, k * N)] += t * s01;
+                Hp[pk(k * N + 1, k * N + 1)] += t * s11;
             }
         }
     }

@@ -19,7 +19,7 @@ def evaluate(seg, S, z, U, data, pinv=None, xprior=None):
         zs = z[s * bs:s * bs + kn]
         win = nls.Window(seg, U=U[s], data=data[s])
         Js, _, gs, Hs = nls.evaluate(seg, win, zs)
-        Hs = Hs + nls.second_order(seg, win, zs)
+        Hs = Hs + nls.second_order(seg, win, zs, Hs)
         J += Js
         g[s * bs:s * bs + kn] += gs
         H[s * bs:s * bs + kn, s * bs:s * bs + kn] += Hs

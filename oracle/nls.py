@@ -218,12 +218,15 @@ def _huber(W, qinv, delta):
 EPS = 2.220446049250313e-16
 
 
-def second_order(desc, win, z):
+def second_order(desc, win, z, Hgn=None):
     """Exact second-order part of the dynamics-cost Hessian, sum_k sum_i lw_ki * (-hess f_i(X_k)),
     for the models whose kernels carry it (van der Pol, kinematic bicycle); zero otherwise.
     lw = weight * W is the half-gradient of the dynamics cost w.r.t. the defect.  Gauss-Newton
     alone converges only linearly on windows with large defects (up to 300 iterations on the
-    4096-window van der Pol batch); with this term the tail disappears (max 18)."""
+    4096-window van der Pol batch); with this term the tail disappears (max 18).
+    Hgn (the Gauss-Newton matrix the term is added to): when given, every node's block is scaled back by
+    t = min(1, min_i Hgn_ii / sum_j |S_ij|) so that the Gauss-Newton diagonal dominates its rows (Gershgorin) -- the
+    kernels' safeguard against an indefinite H away from the solution; t = 1 near it, where lw is small."""
     K, n, nv = desc.K, desc.n, desc.nv
     S = np.zeros((desc.nz, desc.nz))
     if desc.dyn_id not in (D.DYN_VDP, D.DYN_BICYCLE) or not np.any(desc.qinv != 0.0):
@@ -247,6 +250,15 @@ def second_order(desc, win, z):
             v = models.BICYCLE_V_GAIN * U[k, 0] - models.BICYCLE_V_OFF
             th = X[k, 2]
             S[o + cm[2], o + cm[2]] += lw[0] * v * np.cos(th) + lw[1] * v * np.sin(th)
+    if Hgn is not None:
+        dgn = np.diag(Hgn)
+        for k in range(K):
+            o = k * nv
+            r = np.sum(np.abs(S[o:o + nv, o:o + nv]), 1)
+            nzr = r > 0.0
+            if np.any(nzr):
+                t = min(1.0, float(np.min(dgn[o:o + nv][nzr] / r[nzr])))
+                S[o:o + nv, o:o + nv] *= t
     return S
 
 
@@ -389,7 +401,7 @@ def solve(desc, win, z0, opts=None):
             lam_it0 = lam
             dg = np.diag(H).copy()                 # damping uses the (positive) Gauss-Newton diagonal
             dg = dg + 1e-14 * np.max(dg)
-            Hn = H + second_order(desc, win, z)    # exact Hessian where the model provides it
+            Hn = H + second_order(desc, win, z, H)    # exact (safeguarded) Hessian where the model provides it
             while lam <= 1e18:
                 try:
                     L = np.linalg.cholesky(Hn + lam * np.diag(dg))

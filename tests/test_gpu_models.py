@@ -40,7 +40,7 @@ def _compare(d, z, U, data, loss_tol=1e-10):
     for b in range(z.shape[0]):
         win = nls.Window(d, U=U[b] if d.m > 0 else None, data=data[b])
         J, merit, go, Ho = nls.evaluate(d, win, z[b])
-        Ho = Ho + nls.second_order(d, win, z[b])
+        Ho = Ho + nls.second_order(d, win, z[b], Ho)
         assert abs(cost[b, 0] - J) <= loss_tol * abs(J)
         assert np.max(np.abs(g[b] - go)) <= loss_tol * np.max(np.abs(go))
         assert np.max(np.abs(H[b] - Ho)) <= loss_tol * np.max(np.abs(Ho))

@@ -34,7 +34,7 @@ def _check_assemble(d, batch, zs, mu=0.0, tol=1e-11):
         win = nls.Window(d, U=None if batch.get("U") is None else batch["U"][b], data=batch["data"][b],
                          xprior=None if batch.get("xprior") is None else batch["xprior"][b])
         J, merit, go, Ho = nls.evaluate(d, win, zs[b], mu)
-        Ho = Ho + nls.second_order(d, win, zs[b])      # the kernel adds the exact second-order dynamics term
+        Ho = Ho + nls.second_order(d, win, zs[b], Ho)      # the kernel adds the exact second-order dynamics term
         assert abs(cost[b, 0] - J) <= tol * abs(J), (b, cost[b, 0], J)
         assert abs(cost[b, 1] - merit) <= tol * abs(merit) + 1e-12
         assert _rel(g[b], go) < tol, (b, _rel(g[b], go))
