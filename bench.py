@@ -415,10 +415,8 @@ def run_car(args):
     prob = engine.WindowProblem(d)
     dev = lambda a: torch.as_tensor(np.ascontiguousarray(a)).cuda()
     U_all, data_all, xh0 = dev(ch["U"]), dev(ch["data"]), dev(ch["xhat0"])
-    hU, hdata = torch.as_tensor(ch["U"]).pin_memory(), torch.as_tensor(ch["data"]).pin_memory()
     z = torch.zeros((B, d.nz), dtype=torch.float64, device="cuda")
     xp = torch.empty_like(xh0)
-    h_out = torch.empty((B, d.nz), dtype=torch.float64).pin_memory()
     flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device="cuda")
     peak_fp64 = engine.fp64_peak_tflops()
     stats = {}
@@ -429,11 +427,11 @@ def run_car(args):
         xp.copy_(xh0)
         stats["it"], stats["bad"] = engine.solve_chain(prob, z, U_all, data_all, xp, ch["PhiDT"], opts=opts)
 
+    hc = engine.HostChains(prob, B, W, nchunk=args.chain_chunks)     # groups of runs: copy of group c+1 under the solve of group c
+    hc.load(ch["U"], ch["data"], ch["xhat0"])
+
     def step_e2e():
-        U_all.copy_(hU, non_blocking=True)
-        data_all.copy_(hdata, non_blocking=True)
-        step_device()
-        h_out.copy_(z, non_blocking=True)
+        hc.run(ch["PhiDT"], opts)
 
     def timed(fn):
         for _ in range(args.warmup):
@@ -465,8 +463,10 @@ def run_car(args):
             "config": car_config(args, B, W),
             "stats": {"mean_iterations_per_window": it_mean, "windows_not_converged": nbad},
             "e2e": {"value": units * args.steps / (ms_e2e * 1e-3), "unit": "windows/s",
-                    "h2d_bytes_per_step": int(hU.numel() * 8 + hdata.numel() * 8), "d2h_bytes_per_step": int(h_out.numel() * 8),
-                    "ms_per_step": ms_e2e / args.steps},
+                    "h2d_bytes_per_step": int(hc.h2d_bytes), "d2h_bytes_per_step": int(hc.d2h_bytes),
+                    "ms_per_step": ms_e2e / args.steps,
+                    "scope": "pinned host buffers (runs in %d groups, each run-major) -> H2D -> fused-chain launch per group -> D2H of the final estimates; "
+                             "a group's copy overlaps the previous group's solve; NumPy -> pinned staging (HostChains.load, once) is outside" % hc.nchunk},
             "gpu_launches": args.steps * (W * 2 if os.environ.get("NLPF_CHAIN_LOOP") else 1),
             "roofline": {"bound": "fp64", "bound_note": "compute-bound on the FP64 FMA pipe; the contract's vocabulary is hbm|tensor: B200 has no FP64 tcgen05 kind and its FP64 mma.sync peak (nlpf_dmma_probe: 36.7 TFLOP/s) equals the vector peak used here", "kernel": "wsolve_kernel<CfgCar> (fused chain: all windows of a run in one warp, one launch per step)",
                          "achieved": achieved, "peak": peak_fp64, "unit": "TFLOP/s",
@@ -942,6 +942,7 @@ def main():
     ap.add_argument("--workload", default="vdp", choices=["vdp", "gnss", "2rx", "car", "ekf", "ls",
                                                           "assemble-vdp", "assemble-gnss", "assemble-car", "vdp-long", "rc", "mrx"])
     ap.add_argument("--mu0-warm", type=float, default=1e-6, help="car workload: barrier parameter at which the warm-started windows 2.. of a run start (0: mu0)")
+    ap.add_argument("--chain-chunks", type=int, default=8, help="car workload, end-to-end leg: groups of runs whose copies overlap the previous group's solve")
     ap.add_argument("--chain", type=int, default=200, help="chained windows per run (car workload; BASELINE configs[3]: horizon 200)")
     ap.add_argument("--windows", type=int, default=4096, help="windows per GPU per step")
     ap.add_argument("--cpu-windows", type=int, default=0, help="size of the CPU-path sample")

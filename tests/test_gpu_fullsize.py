@@ -179,6 +179,35 @@ def test_fused_chain_kernel_equals_the_per_window_loop(monkeypatch, mu0_warm):
     pv.close()
 
 
+def test_host_chains_equal_the_device_resident_chain_call():
+    """engine.HostChains (bench.py's end-to-end leg of the vehicle workload: groups of runs with their own streams,
+    handles and run-major pinned buffers) against one solve_chain call on device-resident inputs: runs are
+    independent, so grouping must not change a bit."""
+    import torch
+    from nlp_filter_b200 import engine
+    d = shapes.car()
+    B, W = 50, 4
+    ch = synth.car_chain_batch(d, B, W, seed=29)
+    opts = D.SolveOpts(mu0_warm=1e-6)
+    prob = engine.WindowProblem(d)
+    dev = lambda a: torch.as_tensor(np.ascontiguousarray(a)).cuda()
+    z = torch.zeros((B, d.nz), dtype=torch.float64, device="cuda")
+    xp = dev(ch["xhat0"])
+    it_ref, bad_ref = engine.solve_chain(prob, z, dev(ch["U"]), dev(ch["data"]), xp, ch["PhiDT"], opts=opts)
+    torch.cuda.synchronize()
+    for nchunk in (1, 3, 7):
+        hc = engine.HostChains(prob, B, W, nchunk=nchunk)
+        hc.load(ch["U"], ch["data"], ch["xhat0"])
+        hc.run(ch["PhiDT"], opts)
+        hc.run(ch["PhiDT"], opts)                      # staged inputs survive a run
+        torch.cuda.synchronize()
+        zz, it, bad = hc.results()
+        assert np.array_equal(zz, z.cpu().numpy())
+        assert np.array_equal(it, it_ref.cpu().numpy()) and np.array_equal(bad, bad_ref.cpu().numpy())
+        hc.close()
+    prob.close()
+
+
 def test_chunked_end_to_end_batches_equal_the_single_chunk_run():
     """HostBatch cuts a batch into chunks with their own streams, handles and packed staging buffers (what
     bench.py's e2e leg uses at 4096 windows); chunking must not change a bit of the results."""
