@@ -589,8 +589,18 @@ def run_ours(args):
         prob.solve(zi, U, data, xprior, None, None, out=(cost, iters, status))
         pipe.gather(i, zi)
 
-    hb = engine.HostBatch(prob, B)
+    hb = engine.HostBatch(prob, B, nchunk=(args.e2e_chunks if B >= 1024 else 1) if args.e2e_chunks > 0 else None)
     hb.load(bt["z0"], bt["U"], bt["data"], bt.get("xprior"))
+    hb.run()
+    torch.cuda.synchronize()
+    e2e_graph = False
+    if not args.no_e2e_graph:
+        try:                                    # one launch per step instead of ~12 per chunk issued from Python
+            hb.capture()
+            e2e_graph = True
+        except Exception as exc:                # (a launch-overhead optimisation: the plain path computes the same thing)
+            sys.stderr.write("bench.py: CUDA-graph capture of the end-to-end step failed (%s); issuing it call by call\n" % exc)
+            hb._graph = None
 
     def step_e2e():
         pipe = pipes["e2e"]
@@ -725,7 +735,8 @@ def run_ours(args):
                     "ms_per_step": ms_e2e / args.steps,
                     "scope": "pinned host buffers -> H2D -> solve -> D2H of estimates, cost, iterations, status"
                              + (" -> all-gather -> D2H of the gathered estimates" if world > 1 else "")
-                             + "; the NumPy -> pinned staging (HostBatch.load, once) and the NumPy views of the results are outside"},
+                             + "; the NumPy -> pinned staging (HostBatch.load, once) and the NumPy views of the results are outside; %d chunks, %s"
+                             % (hb.nchunk, "replayed as one CUDA graph per step (HostBatch.capture)" if e2e_graph else "issued call by call")},
             "gpu_launches": args.steps * (3 if (args.workload == "vdp" and B > 1776) else 1),
             "roofline": {"bound": "fp64", "bound_note": "compute-bound on the FP64 FMA pipe; the contract's vocabulary is hbm|tensor: B200 has no FP64 tcgen05 kind and its FP64 mma.sync peak (nlpf_dmma_probe: 36.7 TFLOP/s) equals the vector peak used here", "kernel": {"vdp": "wsolve_kernel<CfgVdp>", "gnss": "wsolve_kernel<CfgGnss>", "2rx": "solve_kernel_prb", "rc": "solve_kernel_prb", "mrx": "solve_kernel_prb"}[args.workload], "achieved": achieved, "peak": peak_fp64,
                          "unit": "TFLOP/s", "frac": achieved / peak_fp64 if peak_fp64 > 0 else None,
@@ -942,6 +953,8 @@ def main():
     ap.add_argument("--workload", default="vdp", choices=["vdp", "gnss", "2rx", "car", "ekf", "ls",
                                                           "assemble-vdp", "assemble-gnss", "assemble-car", "vdp-long", "rc", "mrx"])
     ap.add_argument("--mu0-warm", type=float, default=1e-6, help="car workload: barrier parameter at which the warm-started windows 2.. of a run start (0: mu0)")
+    ap.add_argument("--e2e-chunks", type=int, default=8, help="chunks of the end-to-end leg (0: HostBatch's own choice)")
+    ap.add_argument("--no-e2e-graph", action="store_true", help="issue the end-to-end step call by call instead of replaying a CUDA graph")
     ap.add_argument("--chain-chunks", type=int, default=8, help="car workload, end-to-end leg: groups of runs whose copies overlap the previous group's solve")
     ap.add_argument("--chain", type=int, default=200, help="chained windows per run (car workload; BASELINE configs[3]: horizon 200)")
     ap.add_argument("--windows", type=int, default=4096, help="windows per GPU per step")

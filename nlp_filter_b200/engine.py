@@ -199,7 +199,9 @@ class HostBatch(object):
         self.nchunk = max(1, min(int(nchunk), B))
         cuts = [(B * c) // self.nchunk for c in range(self.nchunk + 1)]
         self.chunks = [(cuts[c], cuts[c + 1]) for c in range(self.nchunk)]
-        self.probs = [prob] + [WindowProblem(d) for _ in range(self.nchunk - 1)]
+        # every chunk has a handle of its own (scratch buffers of a handle are re-allocated when a later call on it needs
+        # more -- a captured graph must not share them with the caller's handle)
+        self.probs = [WindowProblem(d) for _ in range(self.nchunk)]
         self.streams = [torch.cuda.Stream() for _ in range(self.nchunk)] if self.nchunk > 1 else [None]
         mU = d.K * d.m if d.m > 0 else 0
         Ld = max(d.Ldata, 1)
@@ -258,10 +260,40 @@ class HostBatch(object):
         self.h_zout[c].copy_(z, non_blocking=True)
         self.h_meta[c].copy_(self.d_meta[c], non_blocking=True)
 
+    def capture(self, opts=None):
+        """Record one run() -- every chunk's copies and kernels on their streams -- into a CUDA graph; run() with the
+        same options then replays it with a single launch.  Issuing a chunk from Python costs ~0.09 ms of host time
+        (copies, memset, three kernels, events through ctypes / torch), which at 3-6 chunks is as long as the van der
+        Pol solve itself and keeps the later chunks' copies from starting in time.  Call after one plain run() (first
+        calls allocate scratch and set kernel attributes, which cannot be captured)."""
+        self._graph, self._graph_key = None, None
+        torch.cuda.synchronize()
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.stream(side):
+            self._issue(opts)                                   # (warm-up on the side stream, as torch's capture rules ask)
+            side.synchronize()
+            with torch.cuda.graph(g, stream=side):
+                self._issue(opts)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        self._graph, self._graph_key = g, self._opts_key(opts)
+
+    @staticmethod
+    def _opts_key(opts):
+        return None if opts is None else tuple(sorted(opts.__dict__.items()))
+
     def run(self, opts=None):
         """H2D of the staged inputs, solve, D2H of the estimates, chunk-pipelined.  Asynchronous with
         respect to the host: the current stream waits for every chunk; call
         torch.cuda.synchronize() (or wait on an event of the current stream) before reading results()."""
+        if getattr(self, "_graph", None) is not None and self._graph_key == self._opts_key(opts):
+            self._graph.replay()
+            return
+        self._issue(opts)
+
+    def _issue(self, opts):
         if self.nchunk == 1:
             self._run_chunk(0, opts)
             return
@@ -285,6 +317,13 @@ class HostBatch(object):
         iters = np.concatenate([m[1].numpy() for m in metas])
         status = np.concatenate([m[2].numpy() for m in metas])
         return z, cost, iters, status
+
+    def close(self):
+        """Destroys the chunks' problem handles (and with them a captured graph's scratch: do not run() afterwards)."""
+        self._graph = None
+        for p in self.probs:
+            p.close()
+        self.probs = []
 
     def device_z(self):
         """(B, nz) contiguous device tensor of the estimates of the last run (for a collective)."""
@@ -423,7 +462,9 @@ def solve_windows_host(prob, z0, U=None, data=None, xprior=None, opts=None):
     hb.run(opts)
     torch.cuda.synchronize()
     z, cost, iters, status = hb.results()
-    return z.copy(), cost.copy(), iters.copy(), status.copy()
+    out = z.copy(), cost.copy(), iters.copy(), status.copy()
+    hb.close()
+    return out
 
 
 # ---------------------------------------------------------------------------------------------

@@ -231,9 +231,21 @@ def test_chunked_end_to_end_batches_equal_the_single_chunk_run():
             hb.run()                                   # staged inputs survive a run
             torch.cuda.synchronize()
             outs.append([a.copy() for a in hb.results()] + [hb.device_z().cpu().numpy()])
+        # the same step recorded as a CUDA graph (HostBatch.capture) and replayed: same bits, also after new inputs
+        hb = engine.HostBatch(prob, B, nchunk=3)
+        hb.load(z0, U, data, xp)
+        hb.run()
+        hb.capture()
+        hb.run()
+        torch.cuda.synchronize()
+        outs.append([a.copy() for a in hb.results()] + [hb.device_z().cpu().numpy()])
         for o in outs[1:]:
             for a, b in zip(o, outs[0]):
                 assert np.array_equal(a, b)
+        hb.load(z0[::-1].copy(), None if U is None else U[::-1].copy(), data[::-1].copy(), None if xp is None else xp[::-1].copy())
+        hb.run()
+        torch.cuda.synchronize()
+        assert np.array_equal(hb.results()[0], outs[0][0][::-1])
         assert np.array_equal(outs[0][0], outs[0][4]) and np.all(outs[0][3] <= 1)
         prob.close()
 
