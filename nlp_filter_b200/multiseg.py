@@ -93,63 +93,102 @@ class MultiSegmentProblem(object):
         return engine._f8(a).reshape(B * self.S, width)
 
     # ---- whole solve ----------------------------------------------------------------------------
-    def solve(self, z, U, data, xprior=None, opts=None, variant=RICCATI):
+    def _state(self, B, has_xp, variant, o):
+        """Static buffers (and, after the first sweep, the CUDA graph of one sweep) of a (batch size, options) combination:
+        a sweep is 4 kernel launches and ~40 element-wise torch ops; issued one by one from Python it costs 4 ms of which
+        1.3 ms are kernels, replayed as a graph it costs the kernels."""
+        key = (B, has_xp, int(variant), tuple(sorted(o.__dict__.items())))
+        st = getattr(self, "_states", {}).get(key)
+        if st is None:
+            f = lambda *shape: torch.empty(shape, dtype=torch.float64, device="cuda")
+            d, S = self.d, self.S
+            st = dict(z=f(B, self.nzt), zt=f(B, self.nzt), U=f(B * S, d.K * max(d.m, 1)), data=f(B * S, max(d.Ldata, 1)),
+                      xp=f(B, self.n) if has_xp else None, cur=self._buffers(B), tri=self._buffers(B), lam=f(B),
+                      iters=torch.zeros((B,), dtype=torch.int32, device="cuda"), status=torch.zeros((B,), dtype=torch.int32, device="cuda"),
+                      active=torch.ones((B,), dtype=torch.bool, device="cuda"), info=torch.empty((B,), dtype=torch.int32, device="cuda"),
+                      dz=f(B, self.nblk * self.bs), graph=None)
+            if not hasattr(self, "_states"):
+                self._states = {}
+            self._states = {key: st}                    # one combination is kept (its buffers are tens of MB)
+        return st
+
+    def _sweep(self, st, o, variant):
+        """One damped Gauss-Newton sweep over the whole batch on the static buffers (no host synchronisation, no
+        data-dependent shapes: capturable)."""
+        S = self.S
+        p = engine._ptr
+        z, zt, lam, cur, tri, active, iters, status, dz, info = (st[k] for k in ("z", "zt", "lam", "cur", "tri", "active", "iters", "status", "dz", "info"))
+        _capi.check(self._lib.nlpf_blocktri_solve(z.shape[0], self.nblk, self.bs, p(cur["Dg"]), p(cur["Lo"]), p(cur["g"]), p(dz),
+                                                  p(info), int(variant), engine._stream()))
+        step = dz[:, :self.nzt]
+        ok = (info == 0) & torch.isfinite(step).all(1) & active
+        torch.sub(z, step, out=zt)
+        self._assemble(zt, st["U"], st["data"], st["xp"], None, tri)
+        acc = ok & torch.isfinite(tri["J"]) & (tri["J"] < cur["J"])
+        rej = active & ~acc
+        # accepted windows move: iterate, segment matrices and objective of the trial point become current
+        m1, m2, m3 = acc[:, None], acc.repeat_interleave(S)[:, None], acc.repeat_interleave(S)[:, None, None]
+        z.copy_(torch.where(m1, zt, z))
+        cur["Hs"].copy_(torch.where(m3, tri["Hs"], cur["Hs"]))
+        cur["gs"].copy_(torch.where(m2, tri["gs"], cur["gs"]))
+        cur["cs"].copy_(torch.where(m2, tri["cs"], cur["cs"]))
+        smax = step.abs().amax(1)
+        zmax = z.abs().amax(1)
+        small = smax < o.tol_step * (1.0 + zmax)
+        # converged: an accepted step below the tolerance -- or a proposed step below it that the objective
+        # cannot resolve any more (J equal to rounding: the rounding-floor case the fused kernels treat with
+        # their first-order noise bound; nlpf_assemble does not report that bound, 1e-10 |J| stands in for it)
+        floor = ok & ~acc & small & ((tri["J"] - cur["J"]) <= 1e-10 * cur["J"].abs())
+        conv = (acc & small) | floor
+        lam.copy_(torch.where(acc, torch.clamp(lam / 10.0, min=1e-12), torch.where(rej, torch.clamp(lam * 10.0, min=1e-4), lam)))
+        iters += acc.to(torch.int32)
+        stalled = rej & ~floor & (lam > 1e18)
+        hit = active & ~conv & ~stalled & (iters >= o.max_iter)
+        status.copy_(torch.where(conv, torch.zeros_like(status), torch.where(stalled, torch.full_like(status, 4), status)))   # 4: NLPF_ST_NOSTEP
+        active &= ~(conv | stalled | hit)
+        self._blocks(z, st["xp"], lam, cur)                  # normal equations of the current point with the new damping
+
+    def solve(self, z, U, data, xprior=None, opts=None, variant=RICCATI, graph=True):
         """z (B, nzt) CUDA tensor in/out; U (B, S, K, m), data (B, S, Ldata_seg), xprior (B, n).
-        Returns (z, J, iters, status) device tensors (status as in include/nlpfilter.h)."""
+        Returns (z, J, iters, status) device tensors (status as in include/nlpfilter.h).  graph=True: from the second
+        sweep on, a sweep is replayed as one CUDA graph (captured once per batch size / options)."""
         o = opts or SolveOpts()
-        d, S = self.d, self.S
+        d = self.d
         z = engine._f8(z, (-1, self.nzt))
         B = z.shape[0]
-        U = self._sub(U, B, d.K * max(d.m, 1))
-        data = self._sub(data, B, max(d.Ldata, 1))
-        xp = None if xprior is None else engine._f8(xprior, (B, self.n))
-        cur, tri = self._buffers(B), self._buffers(B)
-        lam = torch.full((B,), o.lam0 if o.lam0 > 0.0 else 1e-3, dtype=torch.float64, device="cuda")   # exact-Hessian class (nlpf_opts.lam0)
-        iters = torch.zeros((B,), dtype=torch.int32, device="cuda")
-        status = torch.full((B,), 2, dtype=torch.int32, device="cuda")
-        active = torch.ones((B,), dtype=torch.bool, device="cuda")
-        self._assemble(z, U, data, xp, lam, cur)
-        bad0 = ~torch.isfinite(cur["J"])
-        status[bad0] = 3
-        active &= ~bad0
-        zt = torch.empty_like(z)
-        info = torch.empty((B,), dtype=torch.int32, device="cuda")
-        dz = torch.empty((B, self.nblk * self.bs), dtype=torch.float64, device="cuda")
-        p = engine._ptr
+        st = self._state(B, xprior is not None, variant, o)
+        st["z"].copy_(z)
+        st["U"].copy_(self._sub(U, B, d.K * max(d.m, 1)))
+        st["data"].copy_(self._sub(data, B, max(d.Ldata, 1)))
+        if xprior is not None:
+            st["xp"].copy_(engine._f8(xprior, (B, self.n)))
+        st["lam"].fill_(o.lam0 if o.lam0 > 0.0 else 1e-3)      # exact-Hessian class (nlpf_opts.lam0)
+        st["iters"].zero_()
+        st["status"].fill_(2)
+        st["active"].fill_(True)
+        self._assemble(st["z"], st["U"], st["data"], st["xp"], st["lam"], st["cur"])
+        bad0 = ~torch.isfinite(st["cur"]["J"])
+        st["status"].copy_(torch.where(bad0, torch.full_like(st["status"], 3), st["status"]))
+        st["active"] &= ~bad0
         for sweep in range(4 * o.max_iter):
-            if not bool(active.any().item()):               # the one scalar read back per iteration
+            if not bool(st["active"].any().item()):            # the one scalar read back per sweep
                 break
-            _capi.check(self._lib.nlpf_blocktri_solve(B, self.nblk, self.bs, p(cur["Dg"]), p(cur["Lo"]), p(cur["g"]), p(dz),
-                                                      p(info), int(variant), engine._stream()))
-            step = dz[:, :self.nzt]
-            ok = (info == 0) & torch.isfinite(step).all(1) & active
-            torch.sub(z, step, out=zt)
-            self._assemble(zt, U, data, xp, None, tri)
-            acc = ok & torch.isfinite(tri["J"]) & (tri["J"] < cur["J"])
-            rej = active & ~acc
-            # accepted windows move: iterate, segment matrices and objective of the trial point become current
-            m1, m2, m3 = acc[:, None], acc.repeat_interleave(S)[:, None], acc.repeat_interleave(S)[:, None, None]
-            z.copy_(torch.where(m1, zt, z))
-            cur["Hs"].copy_(torch.where(m3, tri["Hs"], cur["Hs"]))
-            cur["gs"].copy_(torch.where(m2, tri["gs"], cur["gs"]))
-            cur["cs"].copy_(torch.where(m2, tri["cs"], cur["cs"]))
-            smax = step.abs().amax(1)
-            zmax = z.abs().amax(1)
-            small = smax < o.tol_step * (1.0 + zmax)
-            # converged: an accepted step below the tolerance -- or a proposed step below it that the objective
-            # cannot resolve any more (J equal to rounding: the rounding-floor case the fused kernels treat with
-            # their first-order noise bound; nlpf_assemble does not report that bound, 1e-10 |J| stands in for it)
-            floor = ok & ~acc & small & ((tri["J"] - cur["J"]) <= 1e-10 * cur["J"].abs())
-            conv = (acc & small) | floor
-            lam.copy_(torch.where(acc, torch.clamp(lam / 10.0, min=1e-12), torch.where(rej, torch.clamp(lam * 10.0, min=1e-4), lam)))
-            iters += acc.to(torch.int32)
-            stalled = rej & ~floor & (lam > 1e18)
-            status[conv] = 0
-            status[stalled] = 4                              # no acceptable step (include/nlpfilter.h: NLPF_ST_NOSTEP)
-            hit = active & ~conv & ~stalled & (iters >= o.max_iter)
-            active &= ~(conv | stalled | hit)
-            self._blocks(z, xp, lam, cur)                    # normal equations of the current point with the new damping
-        return z, cur["J"], iters, status
+            if graph and st["graph"] is None and sweep == 1:   # (the first sweep ran eagerly: kernel attributes, workspaces)
+                torch.cuda.synchronize()
+                side = torch.cuda.Stream()
+                side.wait_stream(torch.cuda.current_stream())
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.stream(side):
+                    with torch.cuda.graph(g, stream=side):
+                        self._sweep(st, o, variant)
+                torch.cuda.current_stream().wait_stream(side)
+                st["graph"] = g                                 # (capturing does not execute: the replay below is sweep 1)
+            if graph and st["graph"] is not None:
+                st["graph"].replay()
+            else:
+                self._sweep(st, o, variant)
+        z.copy_(st["z"])
+        return z, st["cur"]["J"].clone(), st["iters"].clone(), st["status"].clone()
 
     def sample(self, z, t):
         """x(t) for t in [0, S*T_s]: the segment's Lagrange basis (nlp/collocation.py:113-121) -> (B, len(t), n)."""

@@ -74,7 +74,12 @@ def test_200_epoch_horizon_matches_the_dense_oracle(variant):
     bt = synth.vdp_multiseg_batch(seg, S, B, seed=6000)
     ms = multiseg.MultiSegmentProblem(seg, S)
     z = torch.as_tensor(bt["z0"].copy()).cuda()
-    z, J, it, st = ms.solve(z, bt["U"], bt["data"], variant=variant)
+    z_eager = torch.as_tensor(bt["z0"].copy()).cuda()
+    z_eager, J_e, it_e, st_e = ms.solve(z_eager, bt["U"], bt["data"], variant=variant, graph=False)     # every sweep issued op by op
+    z, J, it, st = ms.solve(z, bt["U"], bt["data"], variant=variant)                                     # sweeps 2.. replayed as one CUDA graph
+    assert torch.equal(z, z_eager) and torch.equal(J, J_e) and torch.equal(it, it_e) and torch.equal(st, st_e)
+    z2, J2, it2, st2 = ms.solve(torch.as_tensor(bt["z0"].copy()).cuda(), bt["U"], bt["data"], variant=variant)   # the cached graph, again
+    assert torch.equal(z2, z) and torch.equal(it2, it)
     z, J, it, st = _np(z), _np(J), _np(it), _np(st)
     assert np.all(st == 0), np.bincount(st)
     rms = np.sqrt(np.mean((z.reshape(B, -1, 2) - bt["truth_nodes"]) ** 2))
