@@ -438,7 +438,7 @@ __device__ __forceinline__ int pk(int r, int c) { return ((r * (r + 1)) >> 1) + 
 // from it and skip the O(E K^2 na^2) accumulation (ncu: 24 % of the VDP kernel's samples).
 template <bool FULL>
 __device__ void eval_window(const DevProb& P, double* sm, const double* zc, const WinPtr& wp, double mu,
-                            double& J_out, double& merit_out, double& noise_out, int hmode = 0) {
+                            double& J_out, double& merit_out, double& noise_out, int hmode = 0, bool* clipped_out = nullptr) {
     const int tid = threadIdx.x;
     const int K = P.K, n = P.n, m = P.m, nv = P.nv, ng = P.ng, nz = P.nz, na = P.na, nat = P.nat;
     double* Hp = sm + P.o_H;
@@ -460,6 +460,7 @@ __device__ void eval_window(const DevProb& P, double* sm, const double* zc, cons
     const bool dyn_h = FULL && !P.hconst;            // H has a state-dependent dynamics part
     const bool need_F = dyn_h;                       // ... which needs dF/dv per node in shared memory
 
+    double clipped = 0.0;   // 1: the second-order term of one of this thread's nodes needed its safeguard
     double cost = 0.0;      // thread-local share of J
     double bar = 0.0;       // thread-local share of the barrier
     double nse = 0.0;       // thread-local share of the first-order rounding bound of J (in units of eps)
@@ -935,6 +936,7 @@ __device__ void eval_window(const DevProb& P, double* sm, const double* zc, cons
                     const double t = fmin(1.0, fmin(Hp[pk(o + c0, o + c0)] / fabs(s01), Hp[pk(o + c1, o + c1)] / (fabs(s01) + fabs(s11))));
                     Hp[pk(rhi, rlo)] += t * s01;
                     Hp[pk(o + c1, o + c1)] += t * s11;
+                    if (t < 1.0) clipped = 1.0;
                 } else {
                     // f0 = v cos th, f1 = v sin th, th = x[2]
                     const int c2 = P.cmap[2];
@@ -943,15 +945,18 @@ __device__ void eval_window(const DevProb& P, double* sm, const double* zc, cons
                     double s2, c2v;
                     sincos(zc[o + c2], &s2, &c2v);
                     const double s22 = lw[k * n + 0] * v * c2v + lw[k * n + 1] * v * s2;
-                    Hp[pk(o + c2, o + c2)] += fmin(1.0, Hp[pk(o + c2, o + c2)] / fabs(s22)) * s22;      // same safeguard
+                    const double t = fmin(1.0, Hp[pk(o + c2, o + c2)] / fabs(s22));      // same safeguard
+                    Hp[pk(o + c2, o + c2)] += t * s22;
+                    if (t < 1.0) clipped = 1.0;
                 }
             }
         }
     }
     // ---- phase I: reductions ----
-    double rv[4] = {cost, bar, nse, bad ? 1.0 : 0.0};
-    block_reduce<3, 1>(rv, red);
+    double rv[5] = {cost, bar, nse, bad ? 1.0 : 0.0, clipped};
+    block_reduce<3, 2>(rv, red);
     const double J = rv[0], B = rv[1], NS = rv[2], anybad = rv[3];
+    if (clipped_out) *clipped_out = rv[4] > 0.0;
     double merit = 0.5 * J + B;
     if (anybad > 0.0 || !isfinite(merit)) merit = INFINITY;
     J_out = J;
@@ -964,8 +969,8 @@ __device__ void eval_window(const DevProb& P, double* sm, const double* zc, cons
 // evaluation of a window, re-assembly after a rejected step, new barrier stage).  Inlining all five
 // sites gave a 1.7 KB stack frame and five copies of the assembly code in the instruction stream.
 __device__ __noinline__ void eval_window_cold(const DevProb& P, double* sm, const double* zc, const WinPtr& wp, double mu,
-                                              double& J_out, double& merit_out, double& noise_out, int hmode) {
-    eval_window<true>(P, sm, zc, wp, mu, J_out, merit_out, noise_out, hmode);
+                                              double& J_out, double& merit_out, double& noise_out, int hmode, bool* clipped_out) {
+    eval_window<true>(P, sm, zc, wp, mu, J_out, merit_out, noise_out, hmode, clipped_out);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1361,7 +1366,8 @@ VN(solve_kernel)(const __grid_constant__ DevProb P, int B, double* __restrict__ 
         int status = NLPF_ST_MAXITER;
         double lam = opt.lam0;
         double J, merit, nse0;
-        eval_window_cold(P, sm, zs, wp, mu, J, merit, nse0, hmode);
+        bool clip_z = false, clip_t = false;      // the second-order term at z / at the trial point needed its safeguard
+        eval_window_cold(P, sm, zs, wp, mu, J, merit, nse0, hmode, &clip_z);
         if (!isfinite(merit)) {
             status = NLPF_ST_NUMERIC;
         } else {
@@ -1390,12 +1396,13 @@ VN(solve_kernel)(const __grid_constant__ DevProb P, int B, double* __restrict__ 
                     bool accepted = false, at_floor = false;
                     bool h_valid = true;      // Hp still holds H(z)
                     double alpha = 1.0, Jt = J, mt = merit, dzmax = 0.0, nset = 0.0;
+                    if (clip_z) lam = fmax(lam, opt.lam_jump_indef);     // H is probably indefinite: do not try it undamped
                     const double lam_it0 = lam;
                     while (lam <= 1e18) {
                         bool tried = false;   // a trial point was evaluated (else: pivot not positive / step not finite)
                         if (!h_valid) {       // the factorisation overwrote H: rebuild it at z
                             double Jd, md, nd;
-                            eval_window_cold(P, sm, zs, wp, mu, Jd, md, nd, hmode);
+                            eval_window_cold(P, sm, zs, wp, mu, Jd, md, nd, hmode, nullptr);
                             h_valid = true;
                         }
                         for (int i = tid; i < nz; i += NLPF_NT) {
@@ -1451,7 +1458,7 @@ VN(solve_kernel)(const __grid_constant__ DevProb P, int B, double* __restrict__ 
                                 }
                                 // FULL evaluation at the trial point: an accepted step (the usual case) needs H and g
                                 // there anyway; a rejected one rebuilds H at z below, as it had to before
-                                eval_window<true>(P, sm, zt, wp, mu, Jt, mt, nset, hmode);
+                                eval_window<true>(P, sm, zt, wp, mu, Jt, mt, nset, hmode, &clip_t);
                                 tried = true;
                                 if (isfinite(mt) && mt < merit) {
                                     accepted = true;
@@ -1477,7 +1484,7 @@ VN(solve_kernel)(const __grid_constant__ DevProb P, int B, double* __restrict__ 
                         status = NLPF_ST_STALLED;
                         if (!h_valid) {   // leave H, g consistent with z for the stationarity test and a following stage
                             double Jd, md, nd;
-                            eval_window_cold(P, sm, zs, wp, mu, Jd, md, nd, hmode);
+                            eval_window_cold(P, sm, zs, wp, mu, Jd, md, nd, hmode, nullptr);
                         }
                         // "stalled" is a success only at a stationary point: the diagonally scaled gradient step must
                         // be below NLPF_STALL_GTOL (NaN fails the test); otherwise the window is reported as failed
@@ -1511,6 +1518,7 @@ VN(solve_kernel)(const __grid_constant__ DevProb P, int B, double* __restrict__ 
                     J = Jt;               // H, g, dd already belong to the accepted point
                     merit = mt;
                     nse0 = nset;
+                    clip_z = clip_t;
                     if (step < opt.tol_step * (1.0 + zm)) {
                         status = NLPF_ST_CONVERGED;
                         break;
@@ -1522,7 +1530,7 @@ VN(solve_kernel)(const __grid_constant__ DevProb P, int B, double* __restrict__ 
                 }
                 if (!bounded || mu <= opt.mu_min || iters >= opt.max_iter) break;
                 mu = fmax(opt.mu_min, fmin(0.2 * mu, mu * sqrt(mu)));
-                eval_window_cold(P, sm, zs, wp, mu, J, merit, nse0, hmode);
+                eval_window_cold(P, sm, zs, wp, mu, J, merit, nse0, hmode, &clip_z);
             }
         }
         for (int i = tid; i < nz; i += NLPF_NT) z_io[(size_t)b * nz + i] = zs[i];

@@ -342,7 +342,7 @@ __device__ __forceinline__ WsConst ws_stage(const DevProb& P, double* smem) {
 template <class C, bool FULL>
 __device__ __forceinline__ void ws_eval(const DevProb& P, double* sm, const WsConst& cs, const double* zc,
                                         const double* Ug, const double* dg, const double* xp, const double* h0, double mu,
-                                        double& J_out, double& merit_out, double& noise_out) {
+                                        double& J_out, double& merit_out, double& noise_out, bool* clipped_out = nullptr) {
     typedef WsLayout<C> L;
     constexpr int K = C::K, N = C::N, M = C::M, E = C::E, NM = C::NM, DYN = C::DYN;
     constexpr int NZ = L::NZ;
@@ -855,6 +855,7 @@ __device__ __forceinline__ void ws_eval(const DevProb& P, double* sm, const WsCo
         for (int i = lane; i < NZ; i += 32) dd[i] = Hp[pk(i, i)];
         if constexpr (DYN == NLPF_DYN_VDP) {
             __syncwarp();
+            bool clipped = false;
             for (int k = lane; k < K; k += 32) {           // hess f0 = [[0, -2 x1], [-2 x1, -2 x0]]
                 const double x0 = zc[k * N], x1 = zc[k * N + 1], l0 = lw[k * N];
                 const double s01 = l0 * 2.0 * x1, s11 = l0 * 2.0 * x0;
@@ -863,7 +864,10 @@ __device__ __forceinline__ void ws_eval(const DevProb& P, double* sm, const WsCo
                 const double t = fmin(1.0, fmin(Hp[pk(k * N, k * N)] / fabs(s01), Hp[pk(k * N + 1, k * N + 1)] / (fabs(s01) + fabs(s11))));
                 Hp[pk(k * N + 1, k * N)] += t * s01;
                 Hp[pk(k * N + 1, k * N + 1)] += t * s11;
+                clipped = clipped || (t < 1.0);
             }
+            // (the driver starts an iteration whose Hessian needed the safeguard at lam >= lam_jump_indef)
+            if (clipped_out) *clipped_out = __any_sync(0xffffffffu, clipped);
         }
     }
     const double J = wsum(cost);
@@ -1506,12 +1510,15 @@ wsolve_kernel(const __grid_constant__ DevProb P, int B, double* __restrict__ z_i
         double lam = opt.lam0, lam_it0 = opt.lam0, J = 0.0, merit = 0.0, nse0 = 0.0;
         double Jt = 0.0, mt = 0.0, nset = 0.0, dzmax = 0.0, alpha = 1.0, pred = 0.0, dm = 0.0;
         bool h_valid = true;
+        bool clip_z = false, clip_t = false;     // the second-order term at z / at the trial point needed its safeguard
         int ev = EV_FIRST;
         while (true) {
             {
                 double Je, me, ne;
                 const long long pt0 = prof ? clock64() : 0;
-                ws_eval<C, true>(P, sm, cs, (ev == EV_TRIAL) ? zt : zs, Ug, dg, xp, hlin, mu, Je, me, ne);
+                bool clip_e = false;
+                ws_eval<C, true>(P, sm, cs, (ev == EV_TRIAL) ? zt : zs, Ug, dg, xp, hlin, mu, Je, me, ne, &clip_e);
+                if (ev == EV_TRIAL) clip_t = clip_e; else clip_z = clip_e;
                 if (prof && lane == 0) { atomicAdd(prof + 0, (unsigned long long)(clock64() - pt0)); atomicAdd(prof + 2, 1ULL); }
                 if (ev == EV_TRIAL) { Jt = Je; mt = me; nset = ne; }
                 else if (ev == EV_FIRST || ev == EV_STAGE) { J = Je; merit = me; nse0 = ne; }
@@ -1541,6 +1548,7 @@ wsolve_kernel(const __grid_constant__ DevProb P, int B, double* __restrict__ z_i
                         if (mu > opt.mu_min && stage_steps >= 1 && gm < 10.0 * mu) { status = NLPF_ST_CONVERGED; pc = PC_STAGE_END; continue; }
                     }
                     h_valid = true;
+                    if (clip_z) lam = fmax(lam, opt.lam_jump_indef);    // H is probably indefinite: do not try it undamped
                     lam_it0 = lam;
                     pc = PC_LAM_TOP;
                 } else if (pc == PC_LAM_TOP) {
@@ -1635,6 +1643,7 @@ wsolve_kernel(const __grid_constant__ DevProb P, int B, double* __restrict__ z_i
                     ++iters;
                     ++stage_steps;
                     J = Jt;             // H, g, dd already belong to the accepted point
+                    clip_z = clip_t;
                     merit = mt;
                     nse0 = nset;
                     __syncwarp();

@@ -218,7 +218,7 @@ def _huber(W, qinv, delta):
 EPS = 2.220446049250313e-16
 
 
-def second_order(desc, win, z, Hgn=None):
+def second_order(desc, win, z, Hgn=None, info=None):
     """Exact second-order part of the dynamics-cost Hessian, sum_k sum_i lw_ki * (-hess f_i(X_k)),
     for the models whose kernels carry it (van der Pol, kinematic bicycle); zero otherwise.
     lw = weight * W is the half-gradient of the dynamics cost w.r.t. the defect.  Gauss-Newton
@@ -226,9 +226,12 @@ def second_order(desc, win, z, Hgn=None):
     4096-window van der Pol batch); with this term the tail disappears (max 18).
     Hgn (the Gauss-Newton matrix the term is added to): when given, every node's block is scaled back by
     t = min(1, min_i Hgn_ii / sum_j |S_ij|) so that the Gauss-Newton diagonal dominates its rows (Gershgorin) -- the
-    kernels' safeguard against an indefinite H away from the solution; t = 1 near it, where lw is small."""
+    kernels' safeguard against an indefinite H away from the solution; t = 1 near it, where lw is small.
+    info (dict): info["clipped"] = some node had t < 1 (the solver then starts the iteration damped)."""
     K, n, nv = desc.K, desc.n, desc.nv
     S = np.zeros((desc.nz, desc.nz))
+    if info is not None:
+        info["clipped"] = False
     if desc.dyn_id not in (D.DYN_VDP, D.DYN_BICYCLE) or not np.any(desc.qinv != 0.0):
         return S
     W, _ = defects(desc, z, win)
@@ -259,6 +262,8 @@ def second_order(desc, win, z, Hgn=None):
             if np.any(nzr):
                 t = min(1.0, float(np.min(dgn[o:o + nv][nzr] / r[nzr])))
                 S[o:o + nv, o:o + nv] *= t
+                if info is not None and t < 1.0:
+                    info["clipped"] = True
     return S
 
 
@@ -398,10 +403,13 @@ def solve(desc, win, z0, opts=None):
             accepted = False
             floor = False
             small = False
-            lam_it0 = lam
             dg = np.diag(H).copy()                 # damping uses the (positive) Gauss-Newton diagonal
             dg = dg + 1e-14 * np.max(dg)
-            Hn = H + second_order(desc, win, z, H)    # exact (safeguarded) Hessian where the model provides it
+            so_info = {}
+            Hn = H + second_order(desc, win, z, H, so_info)    # exact (safeguarded) Hessian where the model provides it
+            if so_info["clipped"]:                 # the safeguard was needed: H is probably indefinite, no undamped try
+                lam = max(lam, lam_jump_indef)
+            lam_it0 = lam
             while lam <= 1e18:
                 try:
                     L = np.linalg.cholesky(Hn + lam * np.diag(dg))
