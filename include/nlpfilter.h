@@ -67,7 +67,7 @@ extern "C" {
 #define NLPF_STALL_GTOL 1e-6
 /* defaults of the damping schedule (nlpf_opts.lam0, lam_jump, lam_jump_indef, lam_dec_first <= 0 select them) */
 #define NLPF_LAM0 1e-12
-#define NLPF_LAM_JUMP 1e-4
+#define NLPF_LAM_JUMP 1e-3
 #define NLPF_LAM_JUMP_INDEF 0.1
 #define NLPF_LAM_DEC_FIRST 1000.0
 

@@ -38,7 +38,7 @@ ST_NUMERIC = 3          # non-finite cost at the starting point
 ST_NOSTEP = 4           # no damping value produced a decrease at a NON-stationary point (failure)
 # defaults of the damping schedule (include/nlpfilter.h, NLPF_LAM_*; nlpf_opts fields <= 0 select them)
 LAM0 = 1e-12
-LAM_JUMP = 1e-4         # a step that did not decrease the merit: lam <- max(10 lam, lam_jump)
+LAM_JUMP = 1e-3         # a step that did not decrease the merit: lam <- max(10 lam, lam_jump)
 LAM_JUMP_INDEF = 0.1    # a pivot that is not positive or a non-finite step: lam <- max(10 lam, lam_jump_indef)
 LAM_DEC_FIRST = 1000.0  # accepted at the first damping value tried: lam / lam_dec_first (floor 1e-12); after rejections: lam / 10
 

@@ -8,14 +8,9 @@ from nlp_filter_b200 import engine, shapes, synth, desc as D
 
 SETS = {"round1": dict(lam0=1e-3, lam_jump=1e-30, lam_jump_indef=1e-30, lam_dec_first=10.0),
         "default": dict(),
-        "ji.1 df1000": dict(lam_jump_indef=0.1, lam_dec_first=1000.0),
-        "ji.01 df1000": dict(lam_jump_indef=0.01, lam_dec_first=1000.0),
-        "ji.1 df10": dict(lam_jump_indef=0.1, lam_dec_first=10.0),
-        "ji.001 df10": dict(lam_jump_indef=0.001, lam_dec_first=10.0),
-        "ji.003 df10": dict(lam_jump_indef=0.003, lam_dec_first=10.0),
-        "ji.01 df100": dict(lam_jump_indef=0.01, lam_dec_first=100.0),
-        "ji.1 df100": dict(lam_jump_indef=0.1, lam_dec_first=100.0),
-        "l0=1e-3 ji.01": dict(lam0=1e-3, lam_jump_indef=0.01)}
+        "ji.03": dict(lam_jump_indef=0.03), "ji.2": dict(lam_jump_indef=0.2), "ji.3": dict(lam_jump_indef=0.3), "ji.5": dict(lam_jump_indef=0.5),
+        "ji1": dict(lam_jump_indef=1.0), "ji.3 df100": dict(lam_jump_indef=0.3, lam_dec_first=100.0),
+        "ji.3 lj1e-3": dict(lam_jump_indef=0.3, lam_jump=1e-3), "ji.1 lj1e-2": dict(lam_jump=1e-2)}
 d = shapes.vdp_mhe()
 prob = engine.WindowProblem(d)
 tot = {k: 0.0 for k in SETS}
