@@ -11,7 +11,8 @@ run() {  # name regex args...
   timeout 900 ncu --set full --clock-control none --import-source on -k regex:$rx -s 3 -c 1 -f -o gpurun_out/prof_r2c_$name \
      python bench.py "$@" --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_r2c_$name.log 2>&1 || tail -3 gpurun_out/ncu_r2c_$name.log
 }
-run vdp wsolve_kernel --workload vdp
-run gnss wsolve_kernel --workload gnss
+# (one chunk, no graph: every wsolve_kernel launch of the process is then the full 4096-window batch, so -s 3 -c 1 lands on it)
+run vdp wsolve_kernel --workload vdp --e2e-chunks 1 --no-e2e-graph
+run gnss wsolve_kernel --workload gnss --e2e-chunks 1 --no-e2e-graph
 run car wsolve_kernel --workload car --chain 25
 ls -la gpurun_out/prof_r2c_*.ncu-rep
