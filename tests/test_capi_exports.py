@@ -69,3 +69,30 @@ def test_ctypes_struct_mirrors_match_the_header_layout(tmp_path):
         assert int(out["d." + f]) == getattr(_capi.CDesc, f).offset, f
     for f in fields_o:
         assert int(out["o." + f]) == getattr(_capi.COpts, f).offset, f
+
+
+def test_damping_schedule_defaults_agree_between_header_and_oracle():
+    """NLPF_LAM0 / NLPF_LAM_JUMP / NLPF_LAM_JUMP_INDEF / NLPF_LAM_DEC_FIRST in include/nlpfilter.h (what the library
+    substitutes for nlpf_opts fields left at 0) are the constants oracle/nls.py uses; the ctypes mirror of nlpf_opts
+    carries every field of the header's struct, in order."""
+    import os
+    import re
+    from nlp_filter_b200 import _capi, desc as D
+    from oracle import nls
+    hdr = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "include", "nlpfilter.h")).read()
+    get = lambda name: float(re.search(r"#define\s+%s\s+([0-9.eE+-]+)" % name, hdr).group(1))
+    assert get("NLPF_LAM0") == nls.LAM0 and get("NLPF_LAM_JUMP") == nls.LAM_JUMP
+    assert get("NLPF_LAM_JUMP_INDEF") == nls.LAM_JUMP_INDEF and get("NLPF_LAM_DEC_FIRST") == nls.LAM_DEC_FIRST
+    assert nls.damping_schedule(D.SolveOpts()) == (nls.LAM0, nls.LAM_JUMP, nls.LAM_JUMP_INDEF, nls.LAM_DEC_FIRST)
+    assert nls.damping_schedule(D.SolveOpts(lam0=1e-3, lam_jump=0.5, lam_jump_indef=2.0, lam_dec_first=7.0)) == (1e-3, 0.5, 2.0, 7.0)
+    body = re.search(r"typedef struct nlpf_opts \{(.*?)\} nlpf_opts;", hdr, re.S).group(1)
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    names = []
+    for decl in body.split(";"):
+        decl = decl.strip()
+        if decl:
+            names += [n.strip() for n in decl.split(None, 1)[1].split(",")]
+    assert names == [f[0] for f in _capi.COpts._fields_], (names, [f[0] for f in _capi.COpts._fields_])
+    o = D.SolveOpts(mu0_warm=1e-6)
+    assert o.for_window(0) is o and o.for_window(3).mu0 == 1e-6 and o.for_window(3).mu0_warm == 1e-6
+    assert D.SolveOpts().for_window(5).mu0 == 0.1

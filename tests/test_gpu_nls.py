@@ -253,3 +253,35 @@ def test_bad_window_is_reported_and_does_not_disturb_its_neighbours(shape):
     assert np.array_equal(z[ok], ref[0][ok]) and np.array_equal(iters[ok], ref[2][ok])
     assert np.array_equal(z[7], bt["z0"].reshape(40, -1)[7])          # the start point is returned untouched
     prob.close()
+
+
+@pytest.mark.parametrize("sched", [dict(), dict(lam0=1e-3, lam_jump=1e-30, lam_jump_indef=1e-30, lam_dec_first=10.0),
+                                   dict(lam0=1e-6, lam_jump=1e-2, lam_jump_indef=1.0, lam_dec_first=100.0)])
+def test_damping_schedule_options_reach_both_kernels_and_the_oracle(sched):
+    """nlpf_opts.lam0 / lam_jump / lam_jump_indef / lam_dec_first (0 = the NLPF_LAM_* defaults; the second set is the
+    round-1 schedule): the warp-per-window kernel (van der Pol batch, far starts: rejected steps and failed pivots
+    happen) and the CTA-per-window kernel (RC-car batch) walk the same damping path as the oracle -- same iteration
+    counts on nearly every window, same minimiser on all of them."""
+    eng, nls = _engine(), _oracle()
+    opts = D.SolveOpts(**sched)
+    for d, bt, n_check in ((shapes.vdp_mhe(), synth.vdp_mhe_batch(shapes.vdp_mhe(), 64, seed=31), 24),
+                           (shapes.rc(), synth.rc_batch(shapes.rc(), 6, seed=32), 3)):
+        prob = eng.WindowProblem(d)
+        z, J, it, st = eng.solve_windows_host(prob, bt["z0"], bt.get("U"), bt["data"], bt.get("xprior"), opts=opts)
+        assert np.all(st <= 1)
+        same = 0
+        for b in range(n_check):
+            win = nls.Window(d, U=None if bt.get("U") is None else bt["U"][b], data=bt["data"][b],
+                             xprior=None if bt.get("xprior") is None else bt["xprior"][b])
+            zo, info = nls.solve(d, win, bt["z0"][b], opts)
+            assert info["status"] <= 1
+            dz = (np.abs(z[b] - zo) / (1 + np.abs(zo))).reshape(d.K, d.nv)
+            if d.n == 6:
+                # RC-car model (nlp/dynamics.py:117-136): x5' = (v / 0.28) tan(delta) does not depend on the state and x5
+                # is neither measured nor used by another component -- its level is a null direction of the problem
+                # (only the regularisation fixes it); every other component is compared
+                dz = np.delete(dz, 5, axis=1)
+            assert np.max(dz) < 1e-6, (b, sched, np.max(dz, 0))
+            same += int(it[b] == info["iters"])
+        assert same >= n_check - max(1, n_check // 8), (same, n_check, sched)
+        prob.close()
