@@ -29,7 +29,9 @@
                           // point (the gradient decides, not the factorisation); +2.5 % on the van der Pol batch.
 #endif
 #ifndef WS_SOA
-#define WS_SOA 1
+#define WS_SOA 0          // structure-of-arrays copy of the pseudorange records before the solve (ws_soa_kernel).  Measured:
+                          // +0.6 % on the GNSS batch when a window took 8 iterations, -10 % now that it takes 2 (the copy
+                          // of 103 MB is a fixed 0.04 ms per call): off; -DWS_SOA=1 builds it in
 #endif
 #ifndef WS_LINQ
 #define WS_LINQ 1         // linear measurements with constant weights as a quadratic form (see ws_eval)
